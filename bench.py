@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py -- GWAS markers/sec on the BASELINE.json configuration (n=10,000 x p=1,000,000
+SNPs, 1 trait; the gwaslmm marker scan) plus GRM FP64 TFLOP/s.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+One process per GPU (torchrun for N>1).  Markers are sharded by contiguous column block
+across ranks (strong scaling: the 1M-marker problem is fixed); the scan needs no
+collective.  A "step" is one pass of the marker scan over the rank's shard: the TMA
+streaming kernel + the per-marker finalisation (statistic, SE, beta, -log10 p).
+
+Timed with CUDA events on the library's launching stream (returned through the C ABI) and
+cross-checked by wall clock between device synchronisations; max over ranks.
+The reference is pure Julia and no Julia runtime exists in this image, so the reference arm
+and `cpu_baseline` time the oracle's C/OpenMP restatement of the reference's per-marker
+algorithm (kind "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "genomicbreedingmodels.jl_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+SEED = 42
+KIND_DIPLOID = 0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=10_000)
+    ap.add_argument("--p", type=int, default=1_000_000, help="total markers (sharded over the GPUs)")
+    ap.add_argument("--model", default="lmm", choices=["ols", "lmm"])
+    ap.add_argument("--e2e-markers", type=int, default=100_000, help="markers in the host-resident e2e sample")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--grm-n", type=int, default=5_000)
+    ap.add_argument("--grm-p", type=int, default=100_000)
+    ap.add_argument("--no-grm", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-markers", type=int, default=0, help="markers in the CPU sample (0: sized for ~10-20 s)")
+    ap.add_argument("--pipeline", action="store_true", help="also time the whole gwaslmm pipeline (GRM + PC1) once")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+                for nm, v in zip(names, s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def shard_bounds(p: int, world: int, rank: int):
+    return (p * rank) // world, (p * (rank + 1)) // world
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm: the oracle's C/OpenMP restatement of the reference's per-marker loop
+# --------------------------------------------------------------------------------------
+def cpu_sample_rate(n: int, markers: int, reps: int = 1):
+    """markers/s of the reference algorithm (std filter, standardise, hcat, pinv(X'X), statistic;
+    /root/reference/src/gwas.jl:112-115, :129, :241-245) on all host cores."""
+    from oracle import cbind, synth
+
+    A = synth.block(SEED, n, 0, markers, KIND_DIPLOID)
+    y = synth.phenotype(SEED, n, 1_000_000, KIND_DIPLOID)
+    ys = (y - y.mean()) / y.std(ddof=1)
+    rng = np.random.default_rng(1)
+    pc = rng.normal(size=n)
+    pc -= pc.mean()
+    pc /= np.linalg.norm(pc)
+    cbind.gwasols_raw(A[:, :64], ys, pc)  # warm-up (thread pool, page faults)
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cbind.gwasols_raw(A, ys, pc)
+        best = min(best, time.perf_counter() - t0)
+    return markers / best, best, cbind.num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n = args.n
+    # bounded sample: ~1 s of CPU work per step
+    rate0, _, cores = cpu_sample_rate(n, 512)
+    markers = args.cpu_markers or int(max(512, min(200_000, rate0 * 1.0)))
+    for _ in range(args.warmup):
+        cpu_sample_rate(n, min(markers, 2048))
+    from oracle import cbind, synth
+
+    A = synth.block(SEED, n, 0, markers, KIND_DIPLOID)
+    y = synth.phenotype(SEED, n, args.p, KIND_DIPLOID)
+    ys = (y - y.mean()) / y.std(ddof=1)
+    pc = np.random.default_rng(1).normal(size=n)
+    pc -= pc.mean()
+    pc /= np.linalg.norm(pc)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cbind.gwasols_raw(A, ys, pc)
+    dt = time.perf_counter() - t0
+    value = markers * args.steps / dt
+    sample = f"{markers} of {args.p} markers per step (n={n}), C/OpenMP restatement of gwas.jl:112-115,:129,:241-245"
+    line = {
+        "impl": "reference", "metric": "GWAS markers/sec", "value": value, "unit": "markers/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"gwas{args.model} marker scan n={n} p={args.p} 1 trait (BASELINE configs[2])",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "markers/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "markers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference is pure Julia; no Julia runtime in the image: oracle port timed (DESIGN.md)",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import gbm_b200
+    from gbm_b200 import _lib
+    from oracle import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    gbm_b200.init(local_rank)
+    lib = _lib.load()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n, p = args.n, args.p
+    j0, j1 = shard_bounds(p, world, rank)
+    p_loc = j1 - j0
+    model = _lib.MODEL_LMM if args.model == "lmm" else _lib.MODEL_OLS
+
+    # ---- inputs, resident in HBM before the timed region -------------------------------
+    dm = gbm_b200.DeviceMatrix.generate(SEED, n, p_loc, KIND_DIPLOID, col0=j0)
+    y = synth.phenotype(SEED, n, p, KIND_DIPLOID)
+    ys = (y - y.mean()) / y.std(ddof=1)
+    pc = np.random.default_rng(1).normal(size=n)  # stand-in covariate for the scan-only step
+    pc -= pc.mean()
+    pc /= np.linalg.norm(pc)
+    Y = np.asfortranarray(ys[:, None])
+    C = np.asfortranarray(pc[:, None])
+    # outputs stay on the device (l x 4 doubles + filter mask)
+    outs = {k: torch.empty(p_loc, dtype=torch.float64, device="cuda") for k in ("beta", "se", "stat", "nlp", "mean", "sd")}
+    keep = torch.empty(p_loc, dtype=torch.uint8, device="cuda")
+
+    def step():
+        _lib.check(lib.gbm_scan(dm._h, _lib.ptr(Y), 1, n, _lib.ptr(C), 1, n, model, 0, _lib.ptr(outs["beta"]),
+                                _lib.ptr(outs["se"]), _lib.ptr(outs["stat"]), _lib.ptr(outs["nlp"]),
+                                _lib.ptr(outs["mean"]), _lib.ptr(outs["sd"]), _lib.ptr(keep)))
+        return _lib.last_timing()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    main_ms, kern_ms = [], []
+    with ClockSampler(local_rank) as clocks:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            tm = step()  # returns after a stream synchronise
+            main_ms.append(tm["main_ms"])
+            kern_ms.append(tm["kernel_ms"])
+        barrier()
+        wall = time.perf_counter() - t0
+    dev_s = sum(kern_ms) * 1e-3  # CUDA-event time of all kernels of the K steps on this rank
+    t = torch.tensor([dev_s, wall, float(np.mean(main_ms))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_s, wall, main_avg_ms = (float(x) for x in t.cpu())
+    value = p * args.steps / dev_s
+    wall_value = p * args.steps / wall
+
+    peak, peak_src = measured_peaks()
+    algo_bytes = 8.0 * n * p_loc  # 8n bytes per marker, each genotype read once
+    achieved = algo_bytes / (main_avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "scan_sums_kernel<16,2>", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": main_avg_ms}
+    keep_count = int(keep.sum().item())
+
+    line = {
+        "metric": "GWAS markers/sec", "value": value, "unit": "markers/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"gwas{args.model} marker scan n={n} p={p} 1 trait, PC1 covariate (BASELINE configs[2])",
+                   "n": n, "p": p, "markers_per_gpu": p_loc, "sharding": f"column-block x{world}",
+                   "cache": "inputs larger than L2 (shard >= 10 GB vs 126 MB L2)", "markers_kept": keep_count,
+                   "generator": "oracle/synth.py diploid, on-device"},
+        "wall_value": wall_value, "roofline": roofline, "gpu_launches": 2 * args.steps,
+    }
+
+    # ---- rank-0 extras: clocks, e2e, GRM, CPU baseline ---------------------------------
+    line["clocks"] = clocks.summary()
+
+    if not args.no_e2e:
+        pe = min(args.e2e_markers, p_loc)
+        host = torch.empty((pe, n), dtype=torch.float64, pin_memory=True)  # (p, n) C-order == n x p column-major
+        sub = gbm_b200.DeviceMatrix.generate(SEED, n, pe, KIND_DIPLOID, col0=j0)
+        info = sub.info()
+        assert info["lda"] == n
+        src = torch.empty(0)
+        _ = src
+        # device -> pinned host (untimed set-up)
+        import ctypes
+
+        cudart = ctypes.CDLL("libcudart.so.12")
+        rc = cudart.cudaMemcpy(ctypes.c_void_p(host.data_ptr()), ctypes.c_void_p(info["device_ptr"]),
+                               ctypes.c_size_t(8 * n * pe), ctypes.c_int(2))
+        assert rc == 0, rc
+        sub.free()
+        hout = {k: np.empty(pe) for k in ("beta", "se", "stat", "nlp", "mean", "sd")}
+        hkeep = np.empty(pe, dtype=np.uint8)
+
+        def e2e_step():
+            _lib.check(lib.gbm_scan_host(_lib.ptr(host), n, pe, n, _lib.ptr(Y), 1, n, _lib.ptr(C), 1, n, model, 0,
+                                         _lib.ptr(hout["beta"]), _lib.ptr(hout["se"]), _lib.ptr(hout["stat"]),
+                                         _lib.ptr(hout["nlp"]), _lib.ptr(hout["mean"]), _lib.ptr(hout["sd"]),
+                                         _lib.ptr(hkeep)))
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        line["e2e"] = {"value": pe * world * args.e2e_steps / dt, "unit": "markers/s",
+                       "h2d_bytes_per_step": 8 * n * pe + 16 * n, "d2h_bytes_per_step": pe * (6 * 8 + 1),
+                       "sample": f"{pe} host-resident (pinned) markers per GPU per step through gbm_scan_host",
+                       "h2d_gbps": 8.0 * n * pe * args.e2e_steps / dt / 1e9}
+        del host
+
+    dm.free()
+
+    if rank == 0 and not args.no_grm:
+        gn, gp = args.grm_n, args.grm_p
+        gm = gbm_b200.DeviceMatrix.generate(SEED, gn, gp, KIND_DIPLOID)
+        dK = torch.empty(gn * gn, dtype=torch.float64, device="cuda")
+        tfs = []
+        for i in range(4):
+            _, tf = gm.grm(_lib.GRM_SIMPLE, 2, 0, out=dK)
+            if i:
+                tfs.append(tf)
+        gm.free()
+        # cuBLAS DGEMM peak on this box (the practical FP64 tensor roofline)
+        a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+        b = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+        torch.matmul(a, b)
+        best = 0.0
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, 2 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        del a, b, dK
+        line["grm"] = {"metric": "GRM FP64 TFLOP/s", "value": float(np.median(tfs)), "unit": "TFLOP/s",
+                       "flops_convention": "n(n+1)p (SYRK)", "n": gn, "p": gp,
+                       "workload": f"grmsimple n={gn} p={gp} diploid (BASELINE configs[1])",
+                       "cublas_dgemm_8192_tflops": best, "frac_of_cublas_dgemm": float(np.median(tfs)) / best,
+                       "datasheet_fp64_tflops": 40.0, "frac_of_datasheet": float(np.median(tfs)) / 40.0}
+
+    if rank == 0 and args.pipeline:
+        line["pipeline"] = run_pipeline(gbm_b200, _lib, n, p_loc, j0, ys)
+
+    if rank == 0 and not args.no_cpu:
+        rate0, _, cores = cpu_sample_rate(n, 512)
+        markers = args.cpu_markers or int(max(1024, min(400_000, rate0 * 12.0)))
+        rate, secs, cores = cpu_sample_rate(n, markers)
+        line["cpu_baseline"] = {"value": rate, "unit": "markers/s", "cores": cores, "kind": "port",
+                                "sample": f"{markers} of {p} markers (n={n}) in {secs:.1f} s; C/OpenMP restatement of "
+                                          "the reference's per-marker loop (gwas.jl:112-115,:129,:241-245); the "
+                                          "reference is Julia and cannot run in this image"}
+
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_pipeline(gbm_b200, _lib, n, p_loc, j0, ys):
+    """Whole gwaslmm once on one GPU: colstats/filter + GRM (DMMA) + K standardise + PC1
+    (cuSOLVER) + scan.  The eigen step is timed separately, as BASELINE.json asks."""
+    import torch
+
+    out = {}
+    dm = gbm_b200.DeviceMatrix.generate(SEED, n, p_loc, KIND_DIPLOID, col0=j0)
+    t0 = time.perf_counter()
+    st = dm.colstats()
+    out["colstats_s"] = time.perf_counter() - t0
+    dK = torch.empty(n * n, dtype=torch.float64, device="cuda")
+    t0 = time.perf_counter()
+    _, tf = dm.grm(_lib.GRM_SIMPLE, 2, 0, out=dK)
+    out["grm_s"] = time.perf_counter() - t0
+    out["grm_tflops"] = tf
+    t0 = time.perf_counter()
+    pc, eig_ms = gbm_b200.kstd_pc1_device(dK.data_ptr(), n)
+    out["kstd_pc1_s"] = time.perf_counter() - t0
+    out["cusolver_eig_s"] = eig_ms * 1e-3
+    t0 = time.perf_counter()
+    res = dm.scan(ys, pc[:, None], model=_lib.MODEL_LMM)
+    out["scan_s"] = time.perf_counter() - t0
+    out["scan_kernel_ms"] = _lib.last_timing()["kernel_ms"]
+    out["markers_kept"] = int(st["idx_cols"].size)
+    out["max_neglog10p"] = float(np.nanmax(res["neglog10p"]))
+    tot = out["colstats_s"] + out["grm_s"] + out["kstd_pc1_s"] + out["scan_s"]
+    out["total_s"] = tot
+    out["markers_per_s_whole_gwaslmm"] = p_loc / tot
+    dm.free()
+    return out
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,977 @@
+// C ABI of libgbm_b200.so (declared in include/gbm_b200.h).  Host-side orchestration only:
+// argument checks that mirror the reference's error behaviour, device buffers, the small
+// host-side linear algebra on the n x (k + T) side vectors, kernel launches, timing.
+#include "../../include/gbm_b200.h"
+
+#include <cusolverDn.h>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+struct gbm_matrix {
+  double* d = nullptr;
+  int64_t n = 0, p = 0, lda = 0;
+  bool owned = false;
+};
+
+namespace gbm {
+
+static thread_local std::string g_error;
+static std::mutex g_mutex;  // entry points are serialised (SURVEY.md 8b "Threading")
+void set_error(const std::string& msg) { g_error = msg; }
+State& state() {
+  static State s;
+  return s;
+}
+void require_ready() {
+  if (!state().ready) throw Error{GBM_ERR_NOT_INITIALISED, "gbm_init has not been called (no CUDA device selected)"};
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    GBM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (!p || qres != cudaDriverEntryPointSuccess) GBM_THROW(GBM_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+void make_tensor_map_2d_f64(CUtensorMap* map, const double* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                            uint32_t box_rows, uint32_t box_cols) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (ld_elems & 1u) != 0)
+    GBM_THROW(GBM_ERR_ARGUMENT, "device matrix must be 16-byte aligned with an even leading dimension");
+  cuuint64_t gdim[2] = {rows, cols};
+  cuuint64_t gstride[1] = {ld_elems * sizeof(double)};
+  cuuint32_t box[2] = {box_rows, box_cols};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_tiled()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) GBM_THROW(GBM_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+}
+
+static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+static bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// stream-ordered scratch buffer
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  cudaStream_t s;
+  DevBuf(size_t count, cudaStream_t stream) : s(stream) {
+    if (count) GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), stream));
+  }
+  ~DevBuf() {
+    if (p) cudaFreeAsync(p, s);
+  }
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+// event-pair timing on the library stream
+struct Span {
+  cudaEvent_t a, b;
+  cudaStream_t s;
+  bool open = false;
+  Span(cudaStream_t stream) : s(stream) {
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+  }
+  ~Span() {
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+  }
+  void start() {
+    cudaEventRecord(a, s);
+    open = true;
+  }
+  void stop() { cudaEventRecord(b, s); }
+  double ms() {
+    if (!open) return 0.0;
+    cudaEventSynchronize(b);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, a, b);
+    return t;
+  }
+};
+
+static void reset_timing() {
+  State& st = state();
+  st.h2d_ms = st.kernel_ms = st.main_ms = st.d2h_ms = 0.0;
+  st.launches = 0;
+}
+
+static void copy_out(void* user, const void* dev, size_t bytes, cudaStream_t s) {
+  if (user && bytes) GBM_CUDA(cudaMemcpyAsync(user, dev, bytes, cudaMemcpyDefault, s));
+}
+
+// --------------------------------------------------------------------------------------
+// side vectors: orthonormalise [1, C] and residualise Y on the host (n x (k+T), tiny)
+// --------------------------------------------------------------------------------------
+struct SideVectors {
+  int k_eff = 0;              // covariates that survived orthogonalisation
+  std::vector<double> W;      // n x k_eff, orthonormal, orthogonal to 1
+  std::vector<double> R;      // n x T residualised traits  (I - 11'/n - WW') y
+  std::vector<double> yMy;    // T
+};
+
+static SideVectors prepare_side_vectors(const double* Y, int64_t n, int64_t T, int64_t ldy, const double* C,
+                                        int64_t k, int64_t ldc) {
+  SideVectors sv;
+  std::vector<double> hY(static_cast<size_t>(n) * T), hC(static_cast<size_t>(n) * std::max<int64_t>(k, 0));
+  if (T > 0)
+    GBM_CUDA(cudaMemcpy2D(hY.data(), n * sizeof(double), Y, ldy * sizeof(double), n * sizeof(double), T,
+                          cudaMemcpyDefault));
+  if (k > 0)
+    GBM_CUDA(cudaMemcpy2D(hC.data(), n * sizeof(double), C, ldc * sizeof(double), n * sizeof(double), k,
+                          cudaMemcpyDefault));
+  auto centre = [&](double* v) {
+    long double s = 0;
+    for (int64_t i = 0; i < n; ++i) s += v[i];
+    const double m = static_cast<double>(s / n);
+    for (int64_t i = 0; i < n; ++i) v[i] -= m;
+  };
+  auto dot = [&](const double* a, const double* b) {
+    long double s = 0;
+    for (int64_t i = 0; i < n; ++i) s += static_cast<long double>(a[i]) * b[i];
+    return static_cast<double>(s);
+  };
+  // modified Gram-Schmidt, twice, against 1 and the accepted covariates
+  for (int64_t c = 0; c < k; ++c) {
+    double* v = hC.data() + c * n;
+    const double norm0 = sqrt(dot(v, v));
+    for (int pass = 0; pass < 2; ++pass) {
+      centre(v);
+      for (int a = 0; a < sv.k_eff; ++a) {
+        const double* w = sv.W.data() + static_cast<size_t>(a) * n;
+        const double h = dot(w, v);
+        for (int64_t i = 0; i < n; ++i) v[i] -= h * w[i];
+      }
+    }
+    const double norm = sqrt(dot(v, v));
+    if (!(norm > 1e-10 * norm0) || !(norm > 0.0)) continue;  // collinear with 1 / earlier covariates
+    sv.W.resize(static_cast<size_t>(sv.k_eff + 1) * n);
+    double* w = sv.W.data() + static_cast<size_t>(sv.k_eff) * n;
+    for (int64_t i = 0; i < n; ++i) w[i] = v[i] / norm;
+    sv.k_eff++;
+  }
+  sv.R.resize(static_cast<size_t>(n) * T);
+  sv.yMy.resize(T);
+  for (int64_t t = 0; t < T; ++t) {
+    double* r = sv.R.data() + t * n;
+    memcpy(r, hY.data() + t * n, sizeof(double) * n);
+    for (int pass = 0; pass < 2; ++pass) {
+      centre(r);
+      for (int a = 0; a < sv.k_eff; ++a) {
+        const double* w = sv.W.data() + static_cast<size_t>(a) * n;
+        const double h = dot(w, r);
+        for (int64_t i = 0; i < n; ++i) r[i] -= h * w[i];
+      }
+    }
+    sv.yMy[t] = dot(r, r);
+  }
+  return sv;
+}
+
+// Device copies of the side vectors, one per pass over the matrix (a pass carries the k
+// covariate vectors plus up to 14 - k traits).
+struct Pass {
+  int64_t t0;
+  int tcount, M, stride;
+  DevBuf<double> dQ, dyMy;
+  Pass(int64_t t0_, int tcount_, int M_, int stride_, size_t qcount, cudaStream_t s)
+      : t0(t0_), tcount(tcount_), M(M_), stride(stride_), dQ(qcount, s), dyMy(tcount_ > 0 ? tcount_ : 1, s) {}
+};
+
+static std::vector<std::unique_ptr<Pass>> build_passes(const SideVectors& sv, int64_t n, int64_t T) {
+  State& st = state();
+  const int k = sv.k_eff;
+  const int max_m = scan_max_side_vectors();
+  if (k >= max_m) GBM_THROW(GBM_ERR_ARGUMENT, "too many covariates (at most 13)");
+  const int t_per_pass = max_m - k;
+  const int64_t ldq = round_up(n, 2);
+  std::vector<std::unique_ptr<Pass>> passes;
+  for (int64_t t0 = 0; t0 < T; t0 += t_per_pass) {
+    const int tcount = static_cast<int>(std::min<int64_t>(t_per_pass, T - t0));
+    const int M = k + tcount;
+    const int stride = scan_record_stride(M, false);
+    const int Mp = stride - 2;
+    std::unique_ptr<Pass> ps(new Pass(t0, tcount, M, stride, static_cast<size_t>(ldq) * Mp, st.stream));
+    GBM_CUDA(cudaMemsetAsync(ps->dQ.p, 0, sizeof(double) * ldq * Mp, st.stream));
+    if (k > 0)
+      GBM_CUDA(cudaMemcpy2DAsync(ps->dQ.p, ldq * sizeof(double), sv.W.data(), n * sizeof(double), n * sizeof(double),
+                                 k, cudaMemcpyHostToDevice, st.stream));
+    GBM_CUDA(cudaMemcpy2DAsync(ps->dQ.p + static_cast<size_t>(k) * ldq, ldq * sizeof(double),
+                               sv.R.data() + static_cast<size_t>(t0) * n, n * sizeof(double), n * sizeof(double),
+                               tcount, cudaMemcpyHostToDevice, st.stream));
+    GBM_CUDA(cudaMemcpyAsync(ps->dyMy.p, sv.yMy.data() + t0, sizeof(double) * tcount, cudaMemcpyHostToDevice,
+                             st.stream));
+    passes.push_back(std::move(ps));
+  }
+  // the host vectors are pageable: make sure the copies have drained before sv can go away
+  GBM_CUDA(cudaStreamSynchronize(st.stream));
+  return passes;
+}
+
+// Streaming pass(es) + finalisation over a device-resident column block.  dev_out holds
+// DEVICE arrays of the full problem (leading dimension ld_out); this block writes entries
+// col0 .. col0 + p_blk - 1 of each trait column.
+struct ScanOutputs {
+  double *beta, *se, *stat, *nlp, *mean, *sd;
+  uint8_t* keep;
+};
+
+static void scan_block(const double* dA, int64_t n, int64_t p_blk, int64_t lda,
+                       const std::vector<std::unique_ptr<Pass>>& passes, int k_eff, int model, int flags,
+                       const ScanOutputs& dev_out, int64_t ld_out, int64_t col0, Span* main_span) {
+  State& st = state();
+  const int64_t ldq = round_up(n, 2);
+  for (const auto& ps : passes) {
+    DevBuf<double> rec(static_cast<size_t>(p_blk) * ps->stride, st.stream);
+    if (main_span) main_span->start();
+    launch_scan_sums(dA, n, p_blk, lda, ps->dQ.p, ps->M, ldq, false, rec.p, st.sm_count, st.stream);
+    if (main_span) main_span->stop();
+    FinalizeParams fp;
+    fp.n = n;
+    fp.p = p_blk;
+    fp.ld_out = ld_out;
+    fp.k = k_eff;
+    fp.T = ps->tcount;
+    fp.rec_stride = ps->stride;
+    fp.model = model;
+    fp.flags = flags;
+    fp.rec = rec.p;
+    fp.yMy = ps->dyMy.p;
+    auto off = [&](double* base) { return base ? base + ps->t0 * ld_out + col0 : nullptr; };
+    fp.beta = off(dev_out.beta);
+    fp.se = off(dev_out.se);
+    fp.stat = off(dev_out.stat);
+    fp.nlp = off(dev_out.nlp);
+    const bool first = ps->t0 == 0;
+    fp.mean = (first && dev_out.mean) ? dev_out.mean + col0 : nullptr;
+    fp.sd = (first && dev_out.sd) ? dev_out.sd + col0 : nullptr;
+    fp.keep = (first && dev_out.keep) ? dev_out.keep + col0 : nullptr;
+    launch_scan_finalize(fp, st.stream);
+    st.launches += 2;
+  }
+}
+
+}  // namespace gbm
+
+using namespace gbm;
+
+#define GBM_API_BEGIN                            \
+  std::lock_guard<std::mutex> lock__(g_mutex);   \
+  try {
+#define GBM_API_END                              \
+  }                                              \
+  catch (const gbm::Error& e) {                  \
+    set_error(e.msg);                            \
+    return e.code;                               \
+  }                                              \
+  catch (const std::exception& e) {              \
+    set_error(std::string("internal: ") + e.what()); \
+    return GBM_ERR_RUNTIME;                      \
+  }                                              \
+  return GBM_OK;
+
+extern "C" {
+
+int gbm_abi_version(void) { return GBM_ABI_VERSION; }
+const char* gbm_last_error(void) { return g_error.c_str(); }
+
+int gbm_init(int device) {
+  GBM_API_BEGIN
+  State& st = state();
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    GBM_THROW(GBM_ERR_CUDA, "no CUDA device: libgbm_b200 has no CPU fallback");
+  if (device < 0 || device >= count) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_init: device index out of range");
+  GBM_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  GBM_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    GBM_THROW(GBM_ERR_CUDA, std::string("libgbm_b200 is built for sm_100a (B200) only; found ") + prop.name);
+  if (st.ready && st.device == device) return GBM_OK;
+  st.device = device;
+  st.sm_count = prop.multiProcessorCount;
+  if (!st.own_stream) GBM_CUDA(cudaStreamCreateWithFlags(&st.own_stream, cudaStreamNonBlocking));
+  if (!st.copy_stream) GBM_CUDA(cudaStreamCreateWithFlags(&st.copy_stream, cudaStreamNonBlocking));
+  st.stream = st.own_stream;
+  st.ready = true;
+  GBM_API_END
+}
+
+int gbm_shutdown(void) {
+  GBM_API_BEGIN
+  State& st = state();
+  if (!st.ready) return GBM_OK;
+  cudaStreamSynchronize(st.stream);
+  if (st.cusolver) {
+    cusolverDnDestroy(reinterpret_cast<cusolverDnHandle_t>(st.cusolver));
+    st.cusolver = nullptr;
+  }
+  if (st.own_stream) cudaStreamDestroy(st.own_stream);
+  if (st.copy_stream) cudaStreamDestroy(st.copy_stream);
+  st.own_stream = st.copy_stream = st.stream = nullptr;
+  st.ready = false;
+  GBM_API_END
+}
+
+int gbm_set_stream(void* cuda_stream) {
+  GBM_API_BEGIN
+  require_ready();
+  State& st = state();
+  st.stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : st.own_stream;
+  GBM_API_END
+}
+
+int gbm_synchronize(void) {
+  GBM_API_BEGIN
+  require_ready();
+  GBM_CUDA(cudaStreamSynchronize(state().stream));
+  GBM_API_END
+}
+
+int gbm_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* hbm_bytes, char* name, int name_len) {
+  GBM_API_BEGIN
+  require_ready();
+  cudaDeviceProp prop;
+  GBM_CUDA(cudaGetDeviceProperties(&prop, state().device));
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  if (hbm_bytes) *hbm_bytes = static_cast<int64_t>(prop.totalGlobalMem);
+  if (name && name_len > 0) {
+    strncpy(name, prop.name, name_len - 1);
+    name[name_len - 1] = 0;
+  }
+  GBM_API_END
+}
+
+int gbm_last_timing(gbm_timing* t) {
+  GBM_API_BEGIN
+  if (!t) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_last_timing: null output");
+  State& st = state();
+  t->h2d_ms = st.h2d_ms;
+  t->kernel_ms = st.kernel_ms;
+  t->main_ms = st.main_ms;
+  t->d2h_ms = st.d2h_ms;
+  t->launches = st.launches;
+  GBM_API_END
+}
+
+// ------------------------------------------------------------------------------------
+// matrices
+// ------------------------------------------------------------------------------------
+static void check_dims(int64_t n, int64_t p, int64_t lda) {
+  if (n < 2) GBM_THROW(GBM_ERR_ARGUMENT, "matrix needs at least 2 rows (entries)");
+  if (p < 1) GBM_THROW(GBM_ERR_ARGUMENT, "matrix needs at least 1 column (locus-allele)");
+  if (lda < n) GBM_THROW(GBM_ERR_ARGUMENT, "leading dimension smaller than the row count");
+  if (n > (int64_t(1) << 31) - 512 || p > (int64_t(1) << 31) - 512)
+    GBM_THROW(GBM_ERR_ARGUMENT, "dimension exceeds the 2^31 tensor-map coordinate range");
+}
+
+int gbm_matrix_upload(const double* A, int64_t n, int64_t p, int64_t lda, gbm_matrix** out) {
+  GBM_API_BEGIN
+  require_ready();
+  if (!A || !out) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_matrix_upload: null pointer");
+  check_dims(n, p, lda);
+  State& st = state();
+  reset_timing();
+  gbm_matrix* m = new gbm_matrix;
+  m->n = n;
+  m->p = p;
+  m->lda = round_up(n, 16);
+  m->owned = true;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&m->d), sizeof(double) * m->lda * p);
+  if (e != cudaSuccess) {
+    delete m;
+    GBM_THROW(GBM_ERR_CUDA, std::string("cudaMalloc of the genotype slab failed: ") + cudaGetErrorString(e));
+  }
+  Span sp(st.stream);
+  sp.start();
+  if (m->lda != n) GBM_CUDA(cudaMemsetAsync(m->d, 0, sizeof(double) * m->lda * p, st.stream));
+  GBM_CUDA(cudaMemcpy2DAsync(m->d, m->lda * sizeof(double), A, lda * sizeof(double), n * sizeof(double), p,
+                             cudaMemcpyDefault, st.stream));
+  sp.stop();
+  st.h2d_ms = sp.ms();
+  *out = m;
+  GBM_API_END
+}
+
+int gbm_matrix_upload_indexed(const double* A, int64_t n0, int64_t p0, int64_t lda, const int64_t* rows, int64_t n,
+                              const int64_t* cols, int64_t p, gbm_matrix** out) {
+  GBM_API_BEGIN
+  require_ready();
+  if (!A || !out) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_matrix_upload_indexed: null pointer");
+  check_dims(n0, p0, lda);
+  if (!rows) n = n0;
+  if (!cols) p = p0;
+  check_dims(n, p, n);
+  State& st = state();
+  reset_timing();
+  // index validation mirrors extractxyetc (/root/reference/src/prediction.jl:82-111)
+  std::vector<int64_t> hr, hc;
+  if (rows) {
+    hr.resize(n);
+    GBM_CUDA(cudaMemcpy(hr.data(), rows, sizeof(int64_t) * n, cudaMemcpyDefault));
+    for (int64_t v : hr)
+      if (v < 1 || v > n0) GBM_THROW(GBM_ERR_ARGUMENT, "The indexes of the entries, `idx_entries` are out of bounds.");
+  }
+  if (cols) {
+    hc.resize(p);
+    GBM_CUDA(cudaMemcpy(hc.data(), cols, sizeof(int64_t) * p, cudaMemcpyDefault));
+    for (int64_t v : hc)
+      if (v < 1 || v > p0)
+        GBM_THROW(GBM_ERR_ARGUMENT, "The indexes of the loci_alleles, `idx_loci_alleles` are out of bounds.");
+  }
+  gbm_matrix* m = new gbm_matrix;
+  m->n = n;
+  m->p = p;
+  m->lda = round_up(n, 16);
+  m->owned = true;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&m->d), sizeof(double) * m->lda * p);
+  if (e != cudaSuccess) {
+    delete m;
+    GBM_THROW(GBM_ERR_CUDA, std::string("cudaMalloc of the genotype slab failed: ") + cudaGetErrorString(e));
+  }
+  GBM_CUDA(cudaMemsetAsync(m->d, 0, sizeof(double) * m->lda * p, st.stream));
+  DevBuf<int64_t> dr(rows ? n : 0, st.stream), dc(cols ? p : 0, st.stream);
+  if (rows) GBM_CUDA(cudaMemcpyAsync(dr.p, hr.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, st.stream));
+  if (cols) GBM_CUDA(cudaMemcpyAsync(dc.p, hc.data(), sizeof(int64_t) * p, cudaMemcpyHostToDevice, st.stream));
+  // stage source columns through the device in blocks, gather on the device
+  const bool src_dev = is_device_ptr(A);
+  const int64_t blk = std::max<int64_t>(1, std::min<int64_t>(p, (int64_t(256) << 20) / (8 * n0)));
+  DevBuf<double> stage(src_dev ? 0 : static_cast<size_t>(n0) * blk, st.stream);
+  Span sp(st.stream);
+  sp.start();
+  for (int64_t j0 = 0; j0 < p; j0 += blk) {
+    const int64_t pc = std::min(blk, p - j0);
+    if (src_dev) {
+      launch_gather(A, lda, rows ? dr.p : nullptr, n, cols ? dc.p + j0 : nullptr, pc, m->d + j0 * m->lda, m->lda,
+                    st.stream);
+      if (!cols) A += pc * lda;
+    } else {
+      // copy the needed source columns contiguously into the stage (cols gathers on the host side of the copy)
+      if (!cols) {
+        GBM_CUDA(cudaMemcpy2DAsync(stage.p, n0 * sizeof(double), A + j0 * lda, lda * sizeof(double),
+                                   n0 * sizeof(double), pc, cudaMemcpyDefault, st.stream));
+      } else {
+        for (int64_t j = 0; j < pc; ++j)
+          GBM_CUDA(cudaMemcpyAsync(stage.p + j * n0, A + (hc[j0 + j] - 1) * lda, sizeof(double) * n0,
+                                   cudaMemcpyDefault, st.stream));
+      }
+      launch_gather(stage.p, n0, rows ? dr.p : nullptr, n, nullptr, pc, m->d + j0 * m->lda, m->lda, st.stream);
+    }
+    st.launches++;
+  }
+  sp.stop();
+  GBM_CUDA(cudaStreamSynchronize(st.stream));
+  st.h2d_ms = sp.ms();
+  *out = m;
+  GBM_API_END
+}
+
+int gbm_matrix_wrap(double* dA, int64_t n, int64_t p, int64_t lda, gbm_matrix** out) {
+  GBM_API_BEGIN
+  require_ready();
+  if (!dA || !out) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_matrix_wrap: null pointer");
+  check_dims(n, p, lda);
+  if (!is_device_ptr(dA)) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_matrix_wrap: not a device pointer");
+  if ((lda & 1) || (reinterpret_cast<uintptr_t>(dA) & 15u))
+    GBM_THROW(GBM_ERR_ARGUMENT, "gbm_matrix_wrap: needs a 16-byte aligned buffer with an even leading dimension");
+  gbm_matrix* m = new gbm_matrix;
+  m->d = dA;
+  m->n = n;
+  m->p = p;
+  m->lda = lda;
+  m->owned = false;
+  *out = m;
+  GBM_API_END
+}
+
+int gbm_matrix_generate(uint64_t seed, int64_t n, int64_t p, int64_t col0, int kind, gbm_matrix** out) {
+  GBM_API_BEGIN
+  require_ready();
+  if (!out) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_matrix_generate: null pointer");
+  check_dims(n, p, n);
+  if (kind < 0 || kind > 2) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_matrix_generate: unknown kind");
+  State& st = state();
+  gbm_matrix* m = new gbm_matrix;
+  m->n = n;
+  m->p = p;
+  m->lda = round_up(n, 16);
+  m->owned = true;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&m->d), sizeof(double) * m->lda * p);
+  if (e != cudaSuccess) {
+    delete m;
+    GBM_THROW(GBM_ERR_CUDA, std::string("cudaMalloc of the genotype slab failed: ") + cudaGetErrorString(e));
+  }
+  if (m->lda != n) GBM_CUDA(cudaMemsetAsync(m->d, 0, sizeof(double) * m->lda * p, st.stream));
+  launch_generate(m->d, n, p, m->lda, col0, seed, kind, st.stream);
+  GBM_CUDA(cudaGetLastError());
+  GBM_CUDA(cudaStreamSynchronize(st.stream));
+  *out = m;
+  GBM_API_END
+}
+
+int gbm_matrix_download(const gbm_matrix* m, int64_t j0, int64_t ncols, double* dst, int64_t ldd) {
+  GBM_API_BEGIN
+  require_ready();
+  if (!m || !dst) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_matrix_download: null pointer");
+  if (j0 < 0 || ncols < 0 || j0 + ncols > m->p || ldd < m->n)
+    GBM_THROW(GBM_ERR_ARGUMENT, "gbm_matrix_download: range out of bounds");
+  State& st = state();
+  GBM_CUDA(cudaMemcpy2DAsync(dst, ldd * sizeof(double), m->d + j0 * m->lda, m->lda * sizeof(double),
+                             m->n * sizeof(double), ncols, cudaMemcpyDefault, st.stream));
+  GBM_CUDA(cudaStreamSynchronize(st.stream));
+  GBM_API_END
+}
+
+int gbm_matrix_info(const gbm_matrix* m, int64_t* n, int64_t* p, int64_t* lda, double** device_ptr) {
+  GBM_API_BEGIN
+  if (!m) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_matrix_info: null handle");
+  if (n) *n = m->n;
+  if (p) *p = m->p;
+  if (lda) *lda = m->lda;
+  if (device_ptr) *device_ptr = m->d;
+  GBM_API_END
+}
+
+int gbm_matrix_free(gbm_matrix* m) {
+  GBM_API_BEGIN
+  if (m) {
+    if (m->owned && m->d) {
+      cudaStreamSynchronize(state().stream);
+      cudaFree(m->d);
+    }
+    delete m;
+  }
+  GBM_API_END
+}
+
+// ------------------------------------------------------------------------------------
+// gwasprep pieces
+// ------------------------------------------------------------------------------------
+int gbm_colstats(const gbm_matrix* m, double* mean, double* sd, double* min_nonzero, uint8_t* keep,
+                 int64_t* idx_cols, int64_t* n_keep, double* min_nonzero_kept) {
+  GBM_API_BEGIN
+  require_ready();
+  if (!m) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_colstats: null handle");
+  State& st = state();
+  reset_timing();
+  const int64_t p = m->p;
+  const int stride = scan_record_stride(0, true);
+  DevBuf<double> rec(static_cast<size_t>(p) * stride, st.stream);
+  DevBuf<double> dmean(p, st.stream), dsd(p, st.stream), dmin(p, st.stream), dminkept(1, st.stream);
+  DevBuf<uint8_t> dkeep(p, st.stream);
+  DevBuf<int64_t> didx(p, st.stream), dcount(1, st.stream);
+  Span all(st.stream), mainsp(st.stream);
+  all.start();
+  mainsp.start();
+  launch_scan_sums(m->d, m->n, p, m->lda, nullptr, 0, 0, true, rec.p, st.sm_count, st.stream);
+  mainsp.stop();
+  launch_colstats_finalize(rec.p, stride, m->n, p, dmean.p, dsd.p, dmin.p, dkeep.p, st.stream);
+  launch_compact_keep(dkeep.p, dmin.p, p, didx.p, dcount.p, dminkept.p, st.stream);
+  all.stop();
+  st.launches = 3;
+  Span d2h(st.stream);
+  d2h.start();
+  copy_out(mean, dmean.p, sizeof(double) * p, st.stream);
+  copy_out(sd, dsd.p, sizeof(double) * p, st.stream);
+  copy_out(min_nonzero, dmin.p, sizeof(double) * p, st.stream);
+  copy_out(keep, dkeep.p, p, st.stream);
+  int64_t count = 0;
+  GBM_CUDA(cudaMemcpyAsync(&count, dcount.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st.stream));
+  GBM_CUDA(cudaStreamSynchronize(st.stream));
+  if (idx_cols && count > 0) copy_out(idx_cols, didx.p, sizeof(int64_t) * count, st.stream);
+  copy_out(min_nonzero_kept, dminkept.p, sizeof(double), st.stream);
+  if (n_keep) {
+    if (is_device_ptr(n_keep))
+      copy_out(n_keep, dcount.p, sizeof(int64_t), st.stream);
+    else
+      *n_keep = count;
+  }
+  d2h.stop();
+  GBM_CUDA(cudaStreamSynchronize(st.stream));
+  st.kernel_ms = all.ms();
+  st.main_ms = mainsp.ms();
+  st.d2h_ms = d2h.ms();
+  GBM_API_END
+}
+
+// ------------------------------------------------------------------------------------
+// GRM
+// ------------------------------------------------------------------------------------
+static void column_means_padded(const gbm_matrix* m, double* dmu_pad /* round_up(p,16), zeroed */) {
+  State& st = state();
+  const int stride = scan_record_stride(0, true);
+  DevBuf<double> rec(static_cast<size_t>(m->p) * stride, st.stream);
+  launch_scan_sums(m->d, m->n, m->p, m->lda, nullptr, 0, 0, true, rec.p, st.sm_count, st.stream);
+  launch_colstats_finalize(rec.p, stride, m->n, m->p, dmu_pad, nullptr, nullptr, nullptr, st.stream);
+  st.launches += 2;
+}
+
+static void grm_accumulate_impl(const gbm_matrix* m, int centre, double* dK, double* dsumq /*device, nullable*/,
+                                double* tflops) {
+  State& st = state();
+  const int64_t ppad = round_up(m->p, 16);
+  DevBuf<double> dmu(ppad, st.stream);
+  GBM_CUDA(cudaMemsetAsync(dmu.p, 0, sizeof(double) * ppad, st.stream));
+  Span all(st.stream), mainsp(st.stream);
+  all.start();
+  if (centre || dsumq) column_means_padded(m, dmu.p);
+  if (dsumq) {
+    launch_sum_q1mq(dmu.p, m->p, dsumq, st.stream);
+    st.launches++;
+  }
+  if (!centre) GBM_CUDA(cudaMemsetAsync(dmu.p, 0, sizeof(double) * ppad, st.stream));
+  mainsp.start();
+  launch_grm_accumulate(m->d, m->n, m->p, m->lda, dmu.p, dK, st.sm_count, st.stream);
+  mainsp.stop();
+  all.stop();
+  st.launches++;
+  GBM_CUDA(cudaStreamSynchronize(st.stream));
+  st.kernel_ms += all.ms();
+  const double ms = mainsp.ms();
+  st.main_ms += ms;
+  if (tflops) *tflops = static_cast<double>(m->n) * static_cast<double>(m->n + 1) * static_cast<double>(m->p) /
+                        (ms * 1e-3) / 1e12;
+}
+
+int gbm_grm_accumulate(const gbm_matrix* m, int centre, double* dK, double* sum_q1mq, double* tflops) {
+  GBM_API_BEGIN
+  require_ready();
+  if (!m || !dK) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_grm_accumulate: null pointer");
+  if (!is_device_ptr(dK)) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_grm_accumulate: dK must be a device pointer");
+  State& st = state();
+  reset_timing();
+  DevBuf<double> dsum(1, st.stream);
+  GBM_CUDA(cudaMemsetAsync(dsum.p, 0, sizeof(double), st.stream));
+  grm_accumulate_impl(m, centre, dK, sum_q1mq ? dsum.p : nullptr, tflops);
+  if (sum_q1mq) {
+    double h = 0.0;
+    GBM_CUDA(cudaMemcpyAsync(&h, dsum.p, sizeof(double), cudaMemcpyDeviceToHost, st.stream));
+    GBM_CUDA(cudaStreamSynchronize(st.stream));
+    if (is_device_ptr(sum_q1mq)) {
+      double prev = 0.0;
+      GBM_CUDA(cudaMemcpy(&prev, sum_q1mq, sizeof(double), cudaMemcpyDeviceToHost));
+      prev += h;
+      GBM_CUDA(cudaMemcpy(sum_q1mq, &prev, sizeof(double), cudaMemcpyHostToDevice));
+    } else {
+      *sum_q1mq += h;
+    }
+  }
+  GBM_API_END
+}
+
+int gbm_grm_finalize(double* dK, int64_t n, double scale) {
+  GBM_API_BEGIN
+  require_ready();
+  if (!dK || n < 1) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_grm_finalize: bad arguments");
+  if (!is_device_ptr(dK)) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_grm_finalize: dK must be a device pointer");
+  State& st = state();
+  launch_grm_finalize(dK, n, scale, st.stream);
+  st.launches++;
+  GBM_CUDA(cudaStreamSynchronize(st.stream));
+  GBM_API_END
+}
+
+int gbm_grm(const gbm_matrix* m, int grm_type, int ploidy, int flags, double* K, double* tflops) {
+  GBM_API_BEGIN
+  require_ready();
+  if (!m || !K) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_grm: null pointer");
+  if (grm_type != GBM_GRM_SIMPLE && grm_type != GBM_GRM_PLOIDY_AWARE)
+    GBM_THROW(GBM_ERR_ARGUMENT, "Unrecognised `GRM_type`. Please select from:\n\t‣ simple\n\t‣ ploidy-aware");
+  if (grm_type == GBM_GRM_PLOIDY_AWARE && ploidy < 1) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_grm: ploidy must be >= 1");
+  State& st = state();
+  reset_timing();
+  const int64_t n = m->n;
+  const bool dev_out = is_device_ptr(K);
+  DevBuf<double> tmp(dev_out ? 0 : static_cast<size_t>(n) * n, st.stream);
+  double* dK = dev_out ? K : tmp.p;
+  GBM_CUDA(cudaMemsetAsync(dK, 0, sizeof(double) * n * n, st.stream));
+  DevBuf<double> dsum(1, st.stream);
+  GBM_CUDA(cudaMemsetAsync(dsum.p, 0, sizeof(double), st.stream));
+  const int centre = (grm_type == GBM_GRM_PLOIDY_AWARE) ? 1 : ((flags & GBM_GRM_NO_CENTRE) ? 0 : 1);
+  grm_accumulate_impl(m, centre, dK, grm_type == GBM_GRM_PLOIDY_AWARE ? dsum.p : nullptr, tflops);
+  double scale = 1.0 / static_cast<double>(m->p);
+  if (grm_type == GBM_GRM_PLOIDY_AWARE) {
+    double h = 0.0;
+    GBM_CUDA(cudaMemcpyAsync(&h, dsum.p, sizeof(double), cudaMemcpyDeviceToHost, st.stream));
+    GBM_CUDA(cudaStreamSynchronize(st.stream));
+    if (!(h > 0.0)) GBM_THROW(GBM_ERR_RUNTIME, "gbm_grm: sum q(1-q) is not positive (all loci fixed)");
+    scale = static_cast<double>(ploidy) / h;
+  }
+  launch_grm_finalize(dK, n, scale, st.stream);
+  st.launches++;
+  if (!dev_out) {
+    Span d2h(st.stream);
+    d2h.start();
+    GBM_CUDA(cudaMemcpyAsync(K, dK, sizeof(double) * n * n, cudaMemcpyDefault, st.stream));
+    d2h.stop();
+    st.d2h_ms = d2h.ms();
+  }
+  GBM_CUDA(cudaStreamSynchronize(st.stream));
+  GBM_API_END
+}
+
+// ------------------------------------------------------------------------------------
+// K standardisation + PC1
+// ------------------------------------------------------------------------------------
+int gbm_kstd_pc1(const double* K, int64_t n, double* Kstd, double* pc1, double* eig_ms) {
+  GBM_API_BEGIN
+  require_ready();
+  if (!K || n < 2) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_kstd_pc1: bad arguments");
+  State& st = state();
+  reset_timing();
+  const int64_t ld = round_up(n, 16);
+  DevBuf<double> dKs(static_cast<size_t>(ld) * n, st.stream);
+  Span h2d(st.stream);
+  h2d.start();
+  if (ld != n) GBM_CUDA(cudaMemsetAsync(dKs.p, 0, sizeof(double) * ld * n, st.stream));
+  GBM_CUDA(cudaMemcpy2DAsync(dKs.p, ld * sizeof(double), K, n * sizeof(double), n * sizeof(double), n,
+                             cudaMemcpyDefault, st.stream));
+  h2d.stop();
+  Span all(st.stream);
+  all.start();
+  // column mean / sd of K through the streaming scan (two-pass-equivalent shifted sums)
+  const int stride = scan_record_stride(0, true);
+  DevBuf<double> rec(static_cast<size_t>(n) * stride, st.stream), dmean(n, st.stream), dsd(n, st.stream);
+  launch_scan_sums(dKs.p, n, n, ld, nullptr, 0, 0, true, rec.p, st.sm_count, st.stream);
+  launch_colstats_finalize(rec.p, stride, n, n, dmean.p, dsd.p, nullptr, nullptr, st.stream);
+  launch_k_standardise(dKs.p, n, ld, dmean.p, dsd.p, st.stream);
+  st.launches += 3;
+  if (Kstd)
+    GBM_CUDA(cudaMemcpy2DAsync(Kstd, n * sizeof(double), dKs.p, ld * sizeof(double), n * sizeof(double), n,
+                               cudaMemcpyDefault, st.stream));
+  if (pc1) {
+    DevBuf<double> dZ(static_cast<size_t>(ld) * n, st.stream);
+    if (ld != n) GBM_CUDA(cudaMemsetAsync(dZ.p, 0, sizeof(double) * ld * n, st.stream));
+    launch_row_centre(dKs.p, dZ.p, n, ld, st.stream);
+    // B = Z Z' through the DMMA SYRK (no centring), full symmetric
+    DevBuf<double> dB(static_cast<size_t>(n) * n, st.stream);
+    GBM_CUDA(cudaMemsetAsync(dB.p, 0, sizeof(double) * n * n, st.stream));
+    const int64_t npad = round_up(n, 16);
+    DevBuf<double> dzero(npad, st.stream);
+    GBM_CUDA(cudaMemsetAsync(dzero.p, 0, sizeof(double) * npad, st.stream));
+    launch_grm_accumulate(dZ.p, n, n, ld, dzero.p, dB.p, st.sm_count, st.stream);
+    launch_grm_finalize(dB.p, n, 1.0, st.stream);
+    st.launches += 3;
+    // largest eigenpair of B through cuSOLVER (timed separately, as BASELINE.json asks)
+    if (!st.cusolver) {
+      cusolverDnHandle_t h;
+      if (cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS) GBM_THROW(GBM_ERR_CUDA, "cusolverDnCreate failed");
+      st.cusolver = h;
+    }
+    cusolverDnHandle_t h = reinterpret_cast<cusolverDnHandle_t>(st.cusolver);
+    if (cusolverDnSetStream(h, st.stream) != CUSOLVER_STATUS_SUCCESS) GBM_THROW(GBM_ERR_CUDA, "cusolverDnSetStream failed");
+    if (n > 2147483647) GBM_THROW(GBM_ERR_ARGUMENT, "n too large for cuSOLVER");
+    const int ni = static_cast<int>(n);
+    int lwork = 0, meig = 0;
+    DevBuf<double> dW(n, st.stream);
+    DevBuf<int> dinfo(1, st.stream);
+    if (cusolverDnDsyevdx_bufferSize(h, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_LOWER, ni,
+                                     dB.p, ni, 0.0, 0.0, ni, ni, &meig, dW.p, &lwork) != CUSOLVER_STATUS_SUCCESS)
+      GBM_THROW(GBM_ERR_CUDA, "cusolverDnDsyevdx_bufferSize failed");
+    DevBuf<double> dwork(static_cast<size_t>(lwork), st.stream);
+    Span eig(st.stream);
+    eig.start();
+    cusolverStatus_t cs = cusolverDnDsyevdx(h, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_LOWER,
+                                            ni, dB.p, ni, 0.0, 0.0, ni, ni, &meig, dW.p, dwork.p, lwork, dinfo.p);
+    eig.stop();
+    if (cs != CUSOLVER_STATUS_SUCCESS) GBM_THROW(GBM_ERR_CUDA, "cusolverDnDsyevdx failed, status " + std::to_string((int)cs));
+    int info = 0;
+    GBM_CUDA(cudaMemcpyAsync(&info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost, st.stream));
+    GBM_CUDA(cudaStreamSynchronize(st.stream));
+    if (info != 0 || meig != 1) GBM_THROW(GBM_ERR_RUNTIME, "PCA of the GRM failed (syevdx info " + std::to_string(info) + ")");
+    copy_out(pc1, dB.p, sizeof(double) * n, st.stream);  // first column = the eigenvector
+    if (eig_ms) *eig_ms = eig.ms();
+  }
+  all.stop();
+  GBM_CUDA(cudaStreamSynchronize(st.stream));
+  st.h2d_ms = h2d.ms();
+  st.kernel_ms = all.ms();
+  GBM_API_END
+}
+
+// ------------------------------------------------------------------------------------
+// scan
+// ------------------------------------------------------------------------------------
+static void check_scan_args(int64_t n, const double* Y, int64_t T, int64_t ldy, const double* C, int64_t k,
+                            int64_t ldc, int model) {
+  if (T < 1 || !Y) GBM_THROW(GBM_ERR_ARGUMENT, "scan: at least one trait is required");
+  if (ldy < n) GBM_THROW(GBM_ERR_ARGUMENT, "scan: ldy smaller than the number of entries");
+  if (k < 0 || (k > 0 && (!C || ldc < n))) GBM_THROW(GBM_ERR_ARGUMENT, "scan: bad covariate arguments");
+  if (model != GBM_MODEL_OLS && model != GBM_MODEL_LMM) GBM_THROW(GBM_ERR_ARGUMENT, "scan: unknown model");
+  if (n - k - 2 < 1) GBM_THROW(GBM_ERR_ARGUMENT, "scan: not enough entries for the number of covariates");
+}
+
+struct DevOutputs {
+  DevBuf<double> beta, se, stat, nlp, mean, sd;
+  DevBuf<uint8_t> keep;
+  DevOutputs(int64_t p, int64_t T, bool b, bool s, bool st_, bool nl, bool m, bool sd_, bool k, cudaStream_t stream)
+      : beta(b ? p * T : 0, stream), se(s ? p * T : 0, stream), stat(st_ ? p * T : 0, stream),
+        nlp(nl ? p * T : 0, stream), mean(m ? p : 0, stream), sd(sd_ ? p : 0, stream), keep(k ? p : 0, stream) {}
+  ScanOutputs view() { return ScanOutputs{beta.p, se.p, stat.p, nlp.p, mean.p, sd.p, keep.p}; }
+};
+
+int gbm_scan(const gbm_matrix* m, const double* Y, int64_t T, int64_t ldy, const double* C, int64_t k, int64_t ldc,
+             int model, int flags, double* beta, double* se, double* stat, double* neglog10p, double* mean,
+             double* sd, uint8_t* keep) {
+  GBM_API_BEGIN
+  require_ready();
+  if (!m) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_scan: null handle");
+  check_scan_args(m->n, Y, T, ldy, C, k, ldc, model);
+  State& st = state();
+  reset_timing();
+  const int64_t p = m->p;
+  SideVectors sv = prepare_side_vectors(Y, m->n, T, ldy, C, k, ldc);
+  for (int64_t t = 0; t < T; ++t)
+    if (!(sv.yMy[t] > 0.0)) GBM_THROW(GBM_ERR_ARGUMENT, "No variance in the trait after removing the covariates.");
+  DevOutputs out(p, T, beta, se, stat, neglog10p, mean, sd, keep, st.stream);
+  auto passes = build_passes(sv, m->n, T);
+  Span all(st.stream), mainsp(st.stream);
+  all.start();
+  scan_block(m->d, m->n, p, m->lda, passes, sv.k_eff, model, flags, out.view(), p, 0, &mainsp);
+  all.stop();
+  Span d2h(st.stream);
+  d2h.start();
+  copy_out(beta, out.beta.p, sizeof(double) * p * T, st.stream);
+  copy_out(se, out.se.p, sizeof(double) * p * T, st.stream);
+  copy_out(stat, out.stat.p, sizeof(double) * p * T, st.stream);
+  copy_out(neglog10p, out.nlp.p, sizeof(double) * p * T, st.stream);
+  copy_out(mean, out.mean.p, sizeof(double) * p, st.stream);
+  copy_out(sd, out.sd.p, sizeof(double) * p, st.stream);
+  copy_out(keep, out.keep.p, p, st.stream);
+  d2h.stop();
+  GBM_CUDA(cudaStreamSynchronize(st.stream));
+  st.kernel_ms = all.ms();
+  st.main_ms = mainsp.ms();
+  st.d2h_ms = d2h.ms();
+  GBM_API_END
+}
+
+int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const double* Y, int64_t T, int64_t ldy,
+                  const double* C, int64_t k, int64_t ldc, int model, int flags, double* beta, double* se,
+                  double* stat, double* neglog10p, double* mean, double* sd, uint8_t* keep) {
+  GBM_API_BEGIN
+  require_ready();
+  if (!A) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_scan_host: null matrix");
+  check_dims(n, p, lda);
+  check_scan_args(n, Y, T, ldy, C, k, ldc, model);
+  State& st = state();
+  reset_timing();
+  SideVectors sv = prepare_side_vectors(Y, n, T, ldy, C, k, ldc);
+  for (int64_t t = 0; t < T; ++t)
+    if (!(sv.yMy[t] > 0.0)) GBM_THROW(GBM_ERR_ARGUMENT, "No variance in the trait after removing the covariates.");
+  DevOutputs out(p, T, beta, se, stat, neglog10p, mean, sd, keep, st.stream);
+  auto passes = build_passes(sv, n, T);
+  // column blocks of ~256 MB, double-buffered: the copy engine fills one buffer while the
+  // scan kernel streams the other
+  const int64_t ldd = round_up(n, 16);
+  int64_t blk = std::max<int64_t>(16, ((int64_t(256) << 20) / (8 * ldd)) / 16 * 16);
+  blk = std::min(blk, round_up(p, 16));
+  double* buf[2] = {nullptr, nullptr};
+  cudaEvent_t copied[2], consumed[2];
+  for (int b = 0; b < 2; ++b) {
+    GBM_CUDA(cudaMalloc(reinterpret_cast<void**>(&buf[b]), sizeof(double) * ldd * blk));
+    if (ldd != n) GBM_CUDA(cudaMemsetAsync(buf[b], 0, sizeof(double) * ldd * blk, st.copy_stream));
+    GBM_CUDA(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+    GBM_CUDA(cudaEventCreateWithFlags(&consumed[b], cudaEventDisableTiming));
+  }
+  Span all(st.stream);
+  all.start();
+  GBM_CUDA(cudaEventRecord(consumed[0], st.stream));
+  GBM_CUDA(cudaEventRecord(consumed[1], st.stream));
+  int b = 0;
+  for (int64_t j0 = 0; j0 < p; j0 += blk, b ^= 1) {
+    const int64_t pc = std::min(blk, p - j0);
+    GBM_CUDA(cudaStreamWaitEvent(st.copy_stream, consumed[b], 0));
+    GBM_CUDA(cudaMemcpy2DAsync(buf[b], ldd * sizeof(double), A + j0 * lda, lda * sizeof(double), n * sizeof(double),
+                               pc, cudaMemcpyDefault, st.copy_stream));
+    GBM_CUDA(cudaEventRecord(copied[b], st.copy_stream));
+    GBM_CUDA(cudaStreamWaitEvent(st.stream, copied[b], 0));
+    scan_block(buf[b], n, pc, ldd, passes, sv.k_eff, model, flags, out.view(), p, j0, nullptr);
+    GBM_CUDA(cudaEventRecord(consumed[b], st.stream));
+  }
+  all.stop();
+  copy_out(beta, out.beta.p, sizeof(double) * p * T, st.stream);
+  copy_out(se, out.se.p, sizeof(double) * p * T, st.stream);
+  copy_out(stat, out.stat.p, sizeof(double) * p * T, st.stream);
+  copy_out(neglog10p, out.nlp.p, sizeof(double) * p * T, st.stream);
+  copy_out(mean, out.mean.p, sizeof(double) * p, st.stream);
+  copy_out(sd, out.sd.p, sizeof(double) * p, st.stream);
+  copy_out(keep, out.keep.p, p, st.stream);
+  GBM_CUDA(cudaStreamSynchronize(st.stream));
+  GBM_CUDA(cudaStreamSynchronize(st.copy_stream));
+  st.kernel_ms = all.ms();  // copy + compute overlapped: wall time of the pipeline on the device
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(buf[i]);
+    cudaEventDestroy(copied[i]);
+    cudaEventDestroy(consumed[i]);
+  }
+  GBM_API_END
+}
+
+int gbm_neglog10_sf(const double* stat, int64_t len, int dist, double df, double* out) {
+  GBM_API_BEGIN
+  require_ready();
+  if (!stat || !out || len < 0) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_neglog10_sf: bad arguments");
+  if (dist != 0 && dist != 1) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_neglog10_sf: dist must be 0 (t) or 1 (normal)");
+  if (dist == 0 && !(df > 0)) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_neglog10_sf: df must be positive");
+  State& st = state();
+  DevBuf<double> din(len, st.stream), dout(len, st.stream);
+  GBM_CUDA(cudaMemcpyAsync(din.p, stat, sizeof(double) * len, cudaMemcpyDefault, st.stream));
+  launch_neglog10_sf(din.p, len, dist, df, dout.p, st.stream);
+  copy_out(out, dout.p, sizeof(double) * len, st.stream);
+  GBM_CUDA(cudaStreamSynchronize(st.stream));
+  GBM_API_END
+}
+
+int gbm_measure_copy_bandwidth(int64_t bytes, int reps, double* gbps) {
+  GBM_API_BEGIN
+  require_ready();
+  if (bytes < 1024 || reps < 1 || !gbps) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_measure_copy_bandwidth: bad arguments");
+  State& st = state();
+  DevBuf<uint8_t> a(bytes, st.stream), b(bytes, st.stream);
+  GBM_CUDA(cudaMemsetAsync(a.p, 1, bytes, st.stream));
+  GBM_CUDA(cudaMemcpyAsync(b.p, a.p, bytes, cudaMemcpyDeviceToDevice, st.stream));
+  double best = 0.0;
+  for (int r = 0; r < reps; ++r) {
+    Span sp(st.stream);
+    sp.start();
+    GBM_CUDA(cudaMemcpyAsync(b.p, a.p, bytes, cudaMemcpyDeviceToDevice, st.stream));
+    sp.stop();
+    const double ms = sp.ms();
+    best = std::max(best, 2.0 * static_cast<double>(bytes) / (ms * 1e-3) / 1e9);
+  }
+  *gbps = best;
+  GBM_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+// Internal launch interfaces between the C-ABI translation unit and the kernel units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gbm {
+
+// generate.cu
+void launch_generate(double* A, int64_t n, int64_t p, int64_t lda, int64_t col0, uint64_t seed, int kind,
+                     cudaStream_t stream);
+
+// scan.cu ------------------------------------------------------------------------------
+// Per-marker record written by the streaming kernel: [mean, SS, dot_1 .. dot_M (, minnz)]
+// where SS = sum (a - mean)^2 and dot_m = sum a * q_m (q_m orthogonal to 1).
+int scan_record_stride(int M, bool minnz);
+// Largest M (number of side vectors) one pass supports.
+int scan_max_side_vectors();
+// Streams the n x p matrix once (TMA -> smem ring -> FP64 accumulators).  Q is n x M
+// column-major with leading dimension ldq (device, ldq even, every column orthogonal to 1).
+void launch_scan_sums(const double* A, int64_t n, int64_t p, int64_t lda, const double* Q, int M, int64_t ldq,
+                      bool minnz, double* rec, int sm_count, cudaStream_t stream);
+
+struct FinalizeParams {
+  int64_t n, p;
+  int64_t ld_out;      // leading dimension of the p x T outputs
+  int k, T;            // covariates (orthonormal, first k dots) and traits (next T dots)
+  int rec_stride;
+  int model, flags;
+  const double* rec;   // [p][rec_stride]
+  const double* yMy;   // [T] device
+  double* beta;        // p x T (nullable)
+  double* se;
+  double* stat;
+  double* nlp;
+  double* mean;        // p (nullable)
+  double* sd;
+  uint8_t* keep;
+};
+void launch_scan_finalize(const FinalizeParams& prm, cudaStream_t stream);
+
+// colstats finalisation: mean / sd / min_nonzero / keep from records with M = 0, minnz
+void launch_colstats_finalize(const double* rec, int rec_stride, int64_t n, int64_t p, double* mean, double* sd,
+                              double* minnz, uint8_t* keep, cudaStream_t stream);
+// idx_cols (1-based ascending) + count + min over kept columns of minnz; single pass on device
+void launch_compact_keep(const uint8_t* keep, const double* minnz, int64_t p, int64_t* idx_cols, int64_t* n_keep,
+                         double* min_kept, cudaStream_t stream);
+
+void launch_neglog10_sf(const double* stat, int64_t len, int dist, double df, double* out, cudaStream_t stream);
+
+// grm.cu -------------------------------------------------------------------------------
+// dK (n x n col-major, ld n) += lower-triangle tiles of sum_j (a_j - mu_j)(a_j - mu_j)'.
+// mu: device, length >= round_up(p, 16), zero padded (all zeros = uncentred).
+void launch_grm_accumulate(const double* A, int64_t n, int64_t p, int64_t lda, const double* mu, double* dK,
+                           int sm_count, cudaStream_t stream);
+// scale the lower triangle and mirror it into the upper one
+void launch_grm_finalize(double* dK, int64_t n, double scale, cudaStream_t stream);
+// out[0] += sum_j mu_j (1 - mu_j)
+void launch_sum_q1mq(const double* mu, int64_t p, double* out, cudaStream_t stream);
+
+// pc1.cu -------------------------------------------------------------------------------
+// In place: K <- (K - colmean) / colsd ; then Z = Kstd - rowmean (written to Z). n x n, pitch ld.
+void launch_k_standardise(double* K, int64_t n, int64_t ld, const double* colmean, const double* colsd,
+                          cudaStream_t stream);
+void launch_row_centre(const double* Ks, double* Z, int64_t n, int64_t ld, cudaStream_t stream);
+// gather rows/cols (1-based indices, nullable) from a device source into a padded device matrix
+void launch_gather(const double* src, int64_t lds, const int64_t* rows, int64_t n, const int64_t* cols, int64_t p,
+                   double* dst, int64_t ldd, cudaStream_t stream);
+
+}  // namespace gbm

@@ -1,0 +1,206 @@
+"""Thin object layer over the C ABI: a device-resident genotype matrix and the kernels
+that run on it.  All arithmetic happens in libgbm_b200.so on the GPU."""
+from __future__ import annotations
+
+from ctypes import byref, c_double, c_int64, c_void_p
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, ptr
+
+
+def _f64(a, order="F"):
+    return np.require(a, dtype=np.float64, requirements=[order.upper() + "_CONTIGUOUS", "ALIGNED"])
+
+
+class DeviceMatrix:
+    """n x p column-major Float64 allele-frequency slab resident in HBM (``gbm_matrix``).
+
+    Replaces the host copy ``G::Matrix{Float64} = allele_frequencies[rows, cols]`` of
+    ``extractxyetc`` (/root/reference/src/prediction.jl:129)."""
+
+    def __init__(self, handle: c_void_p, n: int, p: int, keepalive=None):
+        self._h = handle
+        self.n, self.p = int(n), int(p)
+        self._keepalive = keepalive
+
+    # ---- constructors ----------------------------------------------------------------
+    @classmethod
+    def upload(cls, A, rows=None, cols=None) -> "DeviceMatrix":
+        """From a host array (NumPy, any layout; copied to column-major if needed) or a CUDA
+        torch tensor.  ``rows`` / ``cols`` are optional 1-based index vectors."""
+        lib = _lib.lib()
+        if isinstance(A, np.ndarray):
+            if A.ndim != 2:
+                raise _lib.ArgumentError("allele frequencies must be a matrix")
+            A = _f64(A)
+            n0, p0 = A.shape
+            lda = n0
+        else:  # torch tensor, column-major view expected: shape (p, n) contiguous == n x p col-major
+            raise TypeError("upload() takes a NumPy array; use wrap_device() for device memory")
+        h = c_void_p()
+        if rows is None and cols is None:
+            check(lib.gbm_matrix_upload(ptr(A), n0, p0, lda, byref(h)))
+            return cls(h, n0, p0)
+        r = None if rows is None else np.ascontiguousarray(rows, dtype=np.int64)
+        c = None if cols is None else np.ascontiguousarray(cols, dtype=np.int64)
+        n = n0 if r is None else r.size
+        p = p0 if c is None else c.size
+        check(lib.gbm_matrix_upload_indexed(ptr(A), n0, p0, lda, ptr(r), n, ptr(c), p, byref(h)))
+        return cls(h, n, p)
+
+    @classmethod
+    def wrap_device(cls, data_ptr: int, n: int, p: int, lda: int, keepalive=None) -> "DeviceMatrix":
+        h = c_void_p()
+        check(_lib.lib().gbm_matrix_wrap(c_void_p(data_ptr), n, p, lda, byref(h)))
+        return cls(h, n, p, keepalive)
+
+    @classmethod
+    def generate(cls, seed: int, n: int, p: int, kind: int, col0: int = 0) -> "DeviceMatrix":
+        """Synthetic columns col0..col0+p-1 made on the device (oracle/synth.py arithmetic)."""
+        h = c_void_p()
+        check(_lib.lib().gbm_matrix_generate(seed, n, p, col0, kind, byref(h)))
+        return cls(h, n, p)
+
+    # ---- housekeeping ----------------------------------------------------------------
+    def info(self):
+        n, p, lda, d = c_int64(), c_int64(), c_int64(), c_void_p()
+        check(_lib.load().gbm_matrix_info(self._h, byref(n), byref(p), byref(lda), byref(d)))
+        return {"n": n.value, "p": p.value, "lda": lda.value, "device_ptr": d.value}
+
+    def download(self, j0: int = 0, ncols: int | None = None) -> np.ndarray:
+        ncols = self.p - j0 if ncols is None else ncols
+        out = np.empty((self.n, ncols), dtype=np.float64, order="F")
+        check(_lib.load().gbm_matrix_download(self._h, j0, ncols, ptr(out), self.n))
+        return out
+
+    def free(self):
+        if self._h is not None:
+            check(_lib.load().gbm_matrix_free(self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    # ---- kernels ---------------------------------------------------------------------
+    def colstats(self):
+        """std(G, dims=1), the fixed-locus filter and the ploidy probe
+        (/root/reference/src/gwas.jl:112-113, :119).  Returns a dict with mean, sd,
+        min_nonzero, keep (bool), idx_cols (1-based int64, ascending), min_nonzero_kept."""
+        p = self.p
+        mean, sd, mnz = np.empty(p), np.empty(p), np.empty(p)
+        keep = np.empty(p, dtype=np.uint8)
+        idx = np.empty(p, dtype=np.int64)
+        nk, mk = c_int64(), c_double()
+        check(_lib.load().gbm_colstats(self._h, ptr(mean), ptr(sd), ptr(mnz), ptr(keep), ptr(idx), byref(nk),
+                                       byref(mk)))
+        return {"mean": mean, "sd": sd, "min_nonzero": mnz, "keep": keep.astype(bool),
+                "idx_cols": idx[: nk.value].copy(), "min_nonzero_kept": mk.value}
+
+    def grm(self, grm_type: int = _lib.GRM_SIMPLE, ploidy: int = 2, flags: int = 0, out=None):
+        """Full symmetric GRM (n x n).  ``out`` may be a CUDA torch tensor (n*n float64) to
+        keep the result on the device; otherwise a NumPy array is returned.
+        Returns (K, tflops)."""
+        n = self.n
+        K = np.empty((n, n), dtype=np.float64, order="F") if out is None else out
+        tf = c_double()
+        check(_lib.load().gbm_grm(self._h, grm_type, ploidy, flags, ptr(K), byref(tf)))
+        return K, tf.value
+
+    def grm_accumulate(self, dK_ptr: int, centre: bool = True):
+        """Marker-shard partial: dK += sum_j (a_j - mu_j)(a_j - mu_j)' (lower triangle).
+        Returns (sum_j q_j(1-q_j), tflops)."""
+        s, tf = c_double(0.0), c_double()
+        check(_lib.load().gbm_grm_accumulate(self._h, int(centre), c_void_p(dK_ptr), byref(s), byref(tf)))
+        return s.value, tf.value
+
+    def scan(self, Y, C=None, model: int = _lib.MODEL_OLS, flags: int = 0, want=("beta", "se", "stat", "neglog10p")):
+        """Per-marker association scan (/root/reference/src/gwas.jl:239-249, :363-389).
+        Y: n or n x T (used as given); C: n x k covariates without intercept (PC1)."""
+        Y = np.asarray(Y, dtype=np.float64)
+        if Y.shape[0] != self.n:
+            raise _lib.ArgumentError("phenotype length does not match the number of entries")
+        Y = _f64(Y.reshape(self.n, -1))
+        T = Y.shape[1]
+        if C is None:
+            Cm, k = None, 0
+        else:
+            Cm = _f64(np.asarray(C, dtype=np.float64).reshape(self.n, -1))
+            k = Cm.shape[1]
+        p = self.p
+        out = {name: np.empty((p, T), dtype=np.float64, order="F") for name in want}
+        mean, sd = np.empty(p), np.empty(p)
+        keep = np.empty(p, dtype=np.uint8)
+        check(_lib.load().gbm_scan(self._h, ptr(Y), T, self.n, ptr(Cm), k, self.n, model, flags,
+                                   ptr(out.get("beta")), ptr(out.get("se")), ptr(out.get("stat")),
+                                   ptr(out.get("neglog10p")), ptr(mean), ptr(sd), ptr(keep)))
+        out.update(mean=mean, sd=sd, keep=keep.astype(bool))
+        return out
+
+
+def grm_finalize(dK_ptr: int, n: int, scale: float):
+    check(_lib.lib().gbm_grm_finalize(c_void_p(dK_ptr), n, scale))
+
+
+def kstd_pc1(K, want_kstd: bool = True, want_pc1: bool = True):
+    """K column-standardisation (/root/reference/src/gwas.jl:130) and PC1 of the result
+    (MultivariateStats PCA, gwas.jl:234).  K: NumPy n x n.  Returns (Kstd | None, pc1, eig_ms)."""
+    K = _f64(K)
+    n = K.shape[0]
+    if K.shape != (n, n):
+        raise _lib.ArgumentError("GRM must be square")
+    Ks = np.empty((n, n), dtype=np.float64, order="F") if want_kstd else None
+    pc = np.empty(n) if want_pc1 else None
+    ms = c_double(0.0)
+    check(_lib.lib().gbm_kstd_pc1(ptr(K), n, ptr(Ks), ptr(pc), byref(ms)))
+    return Ks, pc, ms.value
+
+
+def kstd_pc1_device(dK_ptr: int, n: int):
+    """Same from a DEVICE n x n GRM; only PC1 comes back to the host."""
+    pc = np.empty(n)
+    ms = c_double()
+    check(_lib.lib().gbm_kstd_pc1(c_void_p(dK_ptr), n, None, ptr(pc), byref(ms)))
+    return pc, ms.value
+
+
+def scan_host(A, Y, C=None, model: int = _lib.MODEL_OLS, flags: int = 0):
+    """End-to-end scan from a HOST matrix (pinned or pageable): H2D in column blocks
+    overlapped with the scan kernel."""
+    if isinstance(A, np.ndarray):
+        A = _f64(A)
+        n, p = A.shape
+        a_ptr = ptr(A)
+    else:  # torch CPU tensor of shape (p, n), contiguous  == n x p column-major
+        p, n = A.shape
+        a_ptr = ptr(A)
+    Y = _f64(np.asarray(Y, dtype=np.float64).reshape(n, -1))
+    T = Y.shape[1]
+    Cm = None if C is None else _f64(np.asarray(C, dtype=np.float64).reshape(n, -1))
+    k = 0 if Cm is None else Cm.shape[1]
+    out = {name: np.empty((p, T), dtype=np.float64, order="F") for name in ("beta", "se", "stat", "neglog10p")}
+    mean, sd = np.empty(p), np.empty(p)
+    keep = np.empty(p, dtype=np.uint8)
+    check(_lib.lib().gbm_scan_host(a_ptr, n, p, n, ptr(Y), T, n, ptr(Cm), k, n, model, flags, ptr(out["beta"]),
+                                   ptr(out["se"]), ptr(out["stat"]), ptr(out["neglog10p"]), ptr(mean), ptr(sd),
+                                   ptr(keep)))
+    out.update(mean=mean, sd=sd, keep=keep.astype(bool))
+    return out
+
+
+def neglog10_sf(stat, dist: str, df: float = 1.0) -> np.ndarray:
+    s = np.ascontiguousarray(stat, dtype=np.float64).ravel()
+    out = np.empty_like(s)
+    d = {"t": 0, "normal": 1}[dist]
+    check(_lib.lib().gbm_neglog10_sf(ptr(s), s.size, d, float(df), ptr(out)))
+    return out
+
+
+def measure_copy_bandwidth(nbytes: int = 1 << 30, reps: int = 5) -> float:
+    g = c_double()
+    check(_lib.lib().gbm_measure_copy_bandwidth(nbytes, reps, byref(g)))
+    return g.value

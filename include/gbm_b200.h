@@ -1,0 +1,158 @@
+/* gbm_b200.h -- C ABI of libgbm_b200.so: the B200 (sm_100a) implementation of the
+ * GWAS-scan / GRM hot path of GenomicBreedingModels.jl v0.3.0.
+ *
+ * The reference has no FFI layer of its own (pure Julia).  Its boundary for this path is
+ * the exported keyword API
+ *     gwasprep  /root/reference/src/gwas.jl:77-142
+ *     gwasols   /root/reference/src/gwas.jl:206-259
+ *     gwaslmm   /root/reference/src/gwas.jl:329-399
+ * plus GenomicBreedingCore's grmsimple / grmploidyaware (call sites gwas.jl:120, :124).
+ * The entry points below are what a Julia `ccall` shim binds so that those functions keep
+ * their signatures (INTEGRATION.md shows the shim); each one cites the reference lines it
+ * replaces.
+ *
+ * Conventions
+ *  - every function returns 0 (GBM_OK) or an error code; gbm_last_error() has the text.
+ *    GBM_ERR_ARGUMENT maps to Julia ArgumentError, GBM_ERR_RUNTIME to ErrorException.
+ *  - matrices are column-major Float64 (Julia layout).  Indices returned are 1-based Int64.
+ *  - every `double*`, `int64_t*`, `uint8_t*` data argument may be a HOST pointer (pageable or
+ *    pinned) or a DEVICE pointer of the selected GPU; the library tells them apart
+ *    (unified virtual addressing).  Host pointers are never retained after return.
+ *  - device memory is library-owned behind the opaque gbm_matrix handle.
+ *  - one process drives one GPU (gbm_init(device)); multi-GPU runs use one process per GPU
+ *    and shard markers by column block (gbm_grm_accumulate + an all-reduce by the host).
+ *  - there is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef GBM_B200_H
+#define GBM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GBM_ABI_VERSION 1
+
+#define GBM_OK 0
+#define GBM_ERR_ARGUMENT 1 /* Julia ArgumentError */
+#define GBM_ERR_RUNTIME 2  /* Julia ErrorException */
+#define GBM_ERR_CUDA 3     /* CUDA / cuSOLVER failure */
+#define GBM_ERR_NOT_INITIALISED 4
+
+/* GRM_type string enum of gwasprep (gwas.jl:101-107) */
+#define GBM_GRM_SIMPLE 0
+#define GBM_GRM_PLOIDY_AWARE 1
+/* gbm_grm flags */
+#define GBM_GRM_NO_CENTRE 1 /* simple GRM as A*A'/p (recalled upstream variant), default is centred */
+
+/* scan models */
+#define GBM_MODEL_OLS 0 /* gwasols statistic, p-values from TDist(n-1)   (gwas.jl:245, :252) */
+#define GBM_MODEL_LMM 1 /* gwaslmm z statistic, p-values from Normal()   (gwas.jl:385, :392) */
+/* scan flags */
+#define GBM_PVALUE_TWO_SIDED 1 /* default is the one-sided upper tail of |stat| */
+
+/* synthetic generator kinds (oracle/synth.py defines the arithmetic) */
+#define GBM_KIND_DIPLOID 0
+#define GBM_KIND_TETRAPLOID 1
+#define GBM_KIND_CONTINUOUS 2
+
+typedef struct gbm_matrix gbm_matrix; /* n x p column-major Float64 slab resident in HBM */
+
+/* timings of the last call, CUDA events on the library stream (milliseconds) */
+typedef struct gbm_timing {
+  double h2d_ms;    /* host -> device copies                        */
+  double kernel_ms; /* all kernels of the call                      */
+  double main_ms;   /* the dominant kernel alone (scan sums / DMMA) */
+  double d2h_ms;    /* device -> host copies                        */
+  int64_t launches; /* kernels launched by the call                 */
+} gbm_timing;
+
+/* ---- life cycle ------------------------------------------------------------------- */
+int gbm_abi_version(void);
+const char* gbm_last_error(void);
+int gbm_init(int device);            /* selects the GPU, creates stream + cuSOLVER handle   */
+int gbm_shutdown(void);
+int gbm_set_stream(void* cuda_stream); /* run on the caller's cudaStream_t (NULL: own stream) */
+int gbm_synchronize(void);
+int gbm_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* hbm_bytes, char* name, int name_len);
+int gbm_last_timing(gbm_timing* t);
+
+/* ---- genotype matrix handles: replaces the n x p copy `G::Matrix{Float64} =
+ *      genomes.allele_frequencies[rows, cols]` of extractxyetc
+ *      (/root/reference/src/prediction.jl:129) -------------------------------------- */
+/* A: n x p column-major with leading dimension lda (host or device). The device copy is
+ * re-pitched to a 128-byte multiple. */
+int gbm_matrix_upload(const double* A, int64_t n, int64_t p, int64_t lda, gbm_matrix** out);
+/* gather upload: rows[i] / cols[j] are 1-based indices into the n0 x p0 source (either may
+ * be NULL = all); this is allele_frequencies[idx_entries[idx], idx_loci_alleles]. */
+int gbm_matrix_upload_indexed(const double* A, int64_t n0, int64_t p0, int64_t lda, const int64_t* rows,
+                              int64_t n, const int64_t* cols, int64_t p, gbm_matrix** out);
+/* wrap an existing device buffer (not owned, not freed). lda must be even. */
+int gbm_matrix_wrap(double* dA, int64_t n, int64_t p, int64_t lda, gbm_matrix** out);
+/* synthetic columns col0 .. col0+p-1 of the counter-based generator, made on the device */
+int gbm_matrix_generate(uint64_t seed, int64_t n, int64_t p, int64_t col0, int kind, gbm_matrix** out);
+int gbm_matrix_download(const gbm_matrix* m, int64_t j0, int64_t ncols, double* dst, int64_t ldd);
+int gbm_matrix_info(const gbm_matrix* m, int64_t* n, int64_t* p, int64_t* lda, double** device_ptr);
+int gbm_matrix_free(gbm_matrix* m);
+
+/* ---- gwasprep: fixed-locus filter and ploidy inference ------------------------------
+ * v = std(G, dims=1); idx_cols = findall(v > eps && finite)   (gwas.jl:112-113)
+ * minimum(G[G .!= 0.0]) over kept columns                     (gwas.jl:119)
+ * All outputs nullable. mean/sd/min_nonzero/keep have length p; idx_cols has room for p
+ * entries, *n_keep receives l. ploidy = Int(round(1/min_nonzero_kept)). */
+int gbm_colstats(const gbm_matrix* m, double* mean, double* sd, double* min_nonzero, uint8_t* keep,
+                 int64_t* idx_cols, int64_t* n_keep, double* min_nonzero_kept);
+
+/* ---- GRM: grmsimple(genomes) / grmploidyaware(genomes; ploidy)  (gwas.jl:120, :124) ---
+ * K (n x n, column-major, host or device) receives the full symmetric matrix.
+ *   simple       : (A - 1 mu')(A - 1 mu')' / p          (GBM_GRM_NO_CENTRE: A A' / p)
+ *   ploidy-aware : ploidy (A - 1 q')(A - 1 q')' / sum_j q_j (1 - q_j)
+ * tflops (nullable) receives n(n+1)p / time of the DMMA kernel. */
+int gbm_grm(const gbm_matrix* m, int grm_type, int ploidy, int flags, double* K, double* tflops);
+/* marker-sharded form: dK (DEVICE, n x n, zeroed by the caller or holding earlier partials)
+ * += lower triangle of sum_j (a_j - mu_j)(a_j - mu_j)' over this shard's columns;
+ * *sum_q1mq += sum_j q_j (1 - q_j).  After an all-reduce of dK (and the two scalars) over
+ * the ranks, gbm_grm_finalize scales and mirrors. */
+int gbm_grm_accumulate(const gbm_matrix* m, int centre, double* dK, double* sum_q1mq, double* tflops);
+int gbm_grm_finalize(double* dK, int64_t n, double scale);
+
+/* ---- K standardisation + PC1 ---------------------------------------------------------
+ * Kstd = (K .- mean(K, dims=1)) ./ std(K, dims=1)               (gwas.jl:130)
+ * pc1  = MultivariateStats.fit(PCA, Kstd; maxoutdim=1).proj[:,1] (gwas.jl:234, :357):
+ *        rows centred, top left singular vector (unit norm, sign arbitrary), through
+ *        cuSOLVER.  K host or device; Kstd nullable; eig_ms (nullable) = cuSOLVER time. */
+int gbm_kstd_pc1(const double* K, int64_t n, double* Kstd, double* pc1, double* eig_ms);
+
+/* ---- the marker scan: the loops of gwasols (gwas.jl:239-249) and gwaslmm (:363-389) ---
+ * Y : n x T phenotypes (ldy), used as given (the caller standardises, gwas.jl:128)
+ * C : n x k covariates WITHOUT the intercept (ldc), k >= 0; the reference uses k = 1 (PC1)
+ * Per marker j and trait t, with M the projector off [1, C] and g_j the standardised
+ * column (gwas.jl:129):
+ *   beta  = coefficient of g_j               se = its standard error
+ *   stat  = GBM_MODEL_OLS: b[end]/sqrt(Vinv[end,end])           (gwas.jl:245)
+ *           GBM_MODEL_LMM: z of `x` in y ~ 1 + PC1 + x + (1|entries), REML (gwas.jl:358-385)
+ *   neglog10p = -log10 P(D > |stat|), D = TDist(n-1) resp. Normal()   (gwas.jl:252, :392)
+ * Outputs (all nullable): beta, se, stat, neglog10p are p x T column-major (ld p);
+ * mean, sd (length p) and keep (length p, the fixed-locus filter). Entries of filtered
+ * or degenerate markers are NaN. */
+int gbm_scan(const gbm_matrix* m, const double* Y, int64_t T, int64_t ldy, const double* C, int64_t k,
+             int64_t ldc, int model, int flags, double* beta, double* se, double* stat, double* neglog10p,
+             double* mean, double* sd, uint8_t* keep);
+
+/* One call from host memory to results (the end-to-end path): uploads A in column blocks
+ * through pinned staging while the previous block is scanned. Same outputs as gbm_scan. */
+int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const double* Y, int64_t T, int64_t ldy,
+                  const double* C, int64_t k, int64_t ldc, int model, int flags, double* beta, double* se,
+                  double* stat, double* neglog10p, double* mean, double* sd, uint8_t* keep);
+
+/* -log10 upper-tail probabilities on the device (log-space; finite where 1 - cdf saturates) */
+int gbm_neglog10_sf(const double* stat, int64_t len, int dist /*0: TDist(df), 1: Normal*/, double df, double* out);
+
+/* measured device-to-device copy bandwidth (GB/s, read+write bytes) -- for rooflines */
+int gbm_measure_copy_bandwidth(int64_t bytes, int reps, double* gbps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GBM_B200_H */

@@ -1,0 +1,326 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via ctypes) against the CPU oracle on
+the same seeded inputs.  Tolerances are BASELINE.json's: statistics / GRM within 1e-9
+relative, -log10 p within 1e-6 absolute, the marker filter bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import cbind, gwas_oracle as go, synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+def rel_err(a, b, floor=1e-3):
+    """max |a-b| / max(|b|, floor*scale): relative with an absolute floor for values that are
+    differences of O(scale) quantities (a t statistic near 0 is sums of O(sqrt(n)) terms)."""
+    a, b = np.asarray(a), np.asarray(b)
+    scale = max(float(np.nanmax(np.abs(b))), 1e-300)
+    return float(np.nanmax(np.abs(a - b) / np.maximum(np.abs(b), floor * scale)))
+
+
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", [synth.KIND_DIPLOID, synth.KIND_TETRAPLOID, synth.KIND_CONTINUOUS])
+@pytest.mark.parametrize("n,p,col0", [(300, 257, 0), (1001, 64, 5), (2, 17, 0), (4099, 33, 1000)])
+def test_generator_bit_exact(gbm, kind, n, p, col0):
+    dm = gbm.DeviceMatrix.generate(42, n, p, kind, col0)
+    got = dm.download()
+    dm.free()
+    want = synth.block(42, n, col0, p, kind)
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("n,p", [(300, 1000), (257, 31), (2, 5), (513, 16), (1025, 200), (10000, 64)])
+@pytest.mark.parametrize("kind", [synth.KIND_DIPLOID, synth.KIND_CONTINUOUS])
+def test_upload_download_roundtrip_and_colstats(gbm, n, p, kind):
+    A = synth.block(7, n, 0, p, kind)
+    dm = gbm.DeviceMatrix.upload(A)
+    assert np.array_equal(dm.download(), A)
+    st = dm.colstats()
+    dm.free()
+    mu, v = go.column_std(A)
+    idx = go.fixed_locus_filter(v)
+    assert np.array_equal(st["idx_cols"], idx)  # bit-exact filter, 1-based ascending
+    assert np.array_equal(st["keep"], v > go.EPS)
+    np.testing.assert_allclose(st["mean"], mu, rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(st["sd"][idx - 1], v[idx - 1], rtol=1e-12)
+    assert np.all(st["sd"][~st["keep"]] <= go.EPS)
+    # ploidy probe: minimum(G[G .!= 0]) over kept columns (gwas.jl:119)
+    G = A[:, idx - 1]
+    if G.size and (G != 0).any():
+        assert st["min_nonzero_kept"] == G[G != 0].min()
+
+
+def test_constant_non_dyadic_column_is_filtered(gbm):
+    rng = np.random.default_rng(0)
+    A = np.asfortranarray(rng.random((777, 40)))
+    A[:, 3] = 0.3
+    A[:, 11] = 1.0 / 3.0
+    A[:, 20] = 0.7
+    dm = gbm.DeviceMatrix.upload(A)
+    st = dm.colstats()
+    dm.free()
+    assert not st["keep"][[3, 11, 20]].any() and st["keep"].sum() == 37
+    assert np.all(st["sd"][[3, 11, 20]] == 0.0)
+    _, v = go.column_std(A)
+    assert np.array_equal(st["idx_cols"], go.fixed_locus_filter(v))
+
+
+def _problem(seed, n, p, kind):
+    A = synth.block(seed, n, 0, p, kind)
+    y = synth.phenotype(seed, n, p, kind)
+    ys = (y - y.mean()) / y.std(ddof=1)
+    rng = np.random.default_rng(seed)
+    pc = rng.normal(size=n)
+    pc -= pc.mean()
+    pc /= np.linalg.norm(pc)
+    return A, ys, pc
+
+
+@pytest.mark.parametrize("n,p,kind", [
+    (300, 2000, synth.KIND_CONTINUOUS),   # BASELINE config 1 shape (reduced p)
+    (300, 10000, synth.KIND_TETRAPLOID),  # config 1 full size, doctest-style tetraploid rounding
+    (1000, 500, synth.KIND_DIPLOID),
+    (255, 33, synth.KIND_DIPLOID),        # ragged: n not a multiple of the 256-row stage, p not of 16
+    (257, 16, synth.KIND_CONTINUOUS),
+    (2001, 47, synth.KIND_TETRAPLOID),    # odd n: re-pitched upload
+    (5, 3, synth.KIND_CONTINUOUS),
+])
+def test_scan_matches_oracle(gbm, n, p, kind):
+    A, ys, pc = _problem(11, n, p, kind)
+    dm = gbm.DeviceMatrix.upload(A)
+    ols = dm.scan(ys, pc[:, None], model=0)
+    lmm = dm.scan(ys, pc[:, None], model=1)
+    dm.free()
+    mu, v = go.column_std(A)
+    keep = v > go.EPS
+    assert np.array_equal(ols["keep"], keep)
+    assert np.array_equal(lmm["keep"], keep)
+    ref = go.scan_closed_form(A[:, keep], ys, pc)
+    # the literal per-marker pinv route of the reference (gwas.jl:241-245)
+    G = (A[:, keep] - mu[keep]) / v[keep]
+    lit = go.gwasols_literal(G, ys, pc)
+    if n > 3:
+        assert rel_err(ols["stat"][keep, 0], lit) < 1e-8  # the literal route itself carries ~1e-11
+        assert rel_err(ols["stat"][keep, 0], ref["stat_ols"]) < RTOL
+        assert rel_err(ols["beta"][keep, 0], ref["beta"]) < RTOL
+        assert rel_err(ols["se"][keep, 0], ref["se_ols"], floor=0) < RTOL
+    if n > 4:
+        assert rel_err(lmm["stat"][keep, 0], ref["stat_lmm"]) < RTOL
+        assert rel_err(lmm["se"][keep, 0], ref["se_lmm"], floor=0) < RTOL
+    assert np.all(np.isnan(ols["stat"][~keep, 0]))
+
+
+def test_scan_matches_c_twin_literal(gbm):
+    n, p = 500, 3000
+    A, ys, pc = _problem(3, n, p, synth.KIND_DIPLOID)
+    so, sl, keep = cbind.gwasols_raw(A, ys, pc)
+    dm = gbm.DeviceMatrix.upload(A)
+    ols = dm.scan(ys, pc[:, None], model=0, want=("stat",))
+    lmm = dm.scan(ys, pc[:, None], model=1, want=("stat",))
+    dm.free()
+    assert np.array_equal(ols["keep"], keep)
+    assert rel_err(ols["stat"][keep, 0], so[keep]) < 1e-8
+    assert rel_err(lmm["stat"][keep, 0], sl[keep]) < 1e-8
+
+
+def test_scan_pvalues(gbm):
+    n, p = 400, 1500
+    A, ys, pc = _problem(5, n, p, synth.KIND_DIPLOID)
+    dm = gbm.DeviceMatrix.upload(A)
+    ols = dm.scan(ys, pc[:, None], model=0)
+    lmm = dm.scan(ys, pc[:, None], model=1)
+    dm.free()
+    keep = ols["keep"]
+    sel = np.flatnonzero(keep)[:: max(1, keep.sum() // 200)]
+    want_t = go.neglog10_sf_t(ols["stat"][sel, 0], n - 1)        # TDist(n-1), gwas.jl:252
+    want_z = go.neglog10_sf_normal(lmm["stat"][sel, 0])          # Normal(),  gwas.jl:392
+    assert np.max(np.abs(ols["neglog10p"][sel, 0] - want_t)) < 1e-6
+    assert np.max(np.abs(lmm["neglog10p"][sel, 0] - want_z)) < 1e-6
+
+
+@pytest.mark.parametrize("df", [3.0, 30.0, 299.0, 9999.0, 1e6])
+def test_neglog10_sf_grid(gbm, df):
+    t = np.concatenate([np.linspace(0, 10, 41), np.array([12.0, 20.0, 37.5, 40.0, 80.0, 200.0, -3.0])])
+    got_t = gbm.neglog10_sf(t, "t", df)
+    got_z = gbm.neglog10_sf(t, "normal")
+    want_t = go.neglog10_sf_t(t, df)
+    want_z = go.neglog10_sf_normal(t)
+    assert np.max(np.abs(got_t - want_t)) < 1e-6
+    assert np.max(np.abs(got_z - want_z)) < 1e-6
+    # p itself within 1e-9 relative where it is representable
+    ok = want_t < 300
+    assert np.max(np.abs(10.0 ** (want_t[ok] - got_t[ok]) - 1.0)) < 1e-9
+
+
+@pytest.mark.parametrize("T,k", [(1, 0), (3, 1), (5, 2), (13, 1), (20, 1)])
+def test_scan_multi_trait_and_covariates(gbm, T, k):
+    n, p = 600, 300
+    A = synth.block(9, n, 0, p, synth.KIND_CONTINUOUS)
+    rng = np.random.default_rng(T * 10 + k)
+    Y = rng.normal(size=(n, T))
+    C = rng.normal(size=(n, k)) if k else None
+    dm = gbm.DeviceMatrix.upload(A)
+    res = dm.scan(Y, C, model=1)
+    dm.free()
+    mu, v = go.column_std(A)
+    keep = v > go.EPS
+    Q = np.hstack([np.ones((n, 1))] + ([C] if k else []))
+    Qo, _ = np.linalg.qr(Q)
+    d = A[:, keep] - mu[keep]
+    Md = d - Qo @ (Qo.T @ d)
+    xMx = np.einsum("ij,ij->j", Md, Md)
+    for t in range(T):
+        My = Y[:, t] - Qo @ (Qo.T @ Y[:, t])
+        s = (My @ Md) / np.sqrt(xMx)
+        z = s / np.sqrt((My @ My - s * s) / (n - k - 2))
+        assert rel_err(res["stat"][keep, t], z) < RTOL
+
+
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,p,kind", [(300, 1000, synth.KIND_CONTINUOUS), (129, 77, synth.KIND_DIPLOID),
+                                      (640, 4099, synth.KIND_TETRAPLOID), (1000, 20000, synth.KIND_DIPLOID)])
+def test_grm_matches_oracle(gbm, n, p, kind):
+    A = synth.block(21, n, 0, p, kind)
+    dm = gbm.DeviceMatrix.upload(A)
+    Ks, tf = dm.grm(0, 2, 0)
+    Ku, _ = dm.grm(0, 2, 1)
+    Kp, _ = dm.grm(1, 4, 0)
+    dm.free()
+    for got, want in ((Ks, go.grm_simple(A)), (Ku, go.grm_simple(A, center=False)), (Kp, go.grm_ploidy_aware(A, 4))):
+        assert np.array_equal(got, got.T)  # mirrored exactly
+        scale = np.abs(want).max()
+        assert np.max(np.abs(got - want)) < RTOL * scale
+        big = np.abs(want) > 1e-3 * scale
+        assert np.max(np.abs(got[big] / want[big] - 1.0)) < RTOL
+
+
+@pytest.mark.parametrize("n", [64, 300, 515])
+def test_kstd_pc1_matches_oracle(gbm, n):
+    A = synth.block(33, n, 0, 2000, synth.KIND_CONTINUOUS)
+    K = go.grm_simple(A)
+    Ks, pc, _ = gbm.kstd_pc1(K)
+    want_Ks = go.standardise_K(K)
+    np.testing.assert_allclose(Ks, want_Ks, rtol=1e-10, atol=1e-11)
+    want_pc = go.pca_pc1(want_Ks)
+    sgn = np.sign(pc @ want_pc)
+    assert abs(np.linalg.norm(pc) - 1) < 1e-12 and abs(pc.sum()) < 1e-10
+    assert np.max(np.abs(sgn * pc - want_pc)) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------
+def _structs(gbm, n, p, kind, seed=42):
+    A = synth.block(seed, n, 0, p, kind)
+    y = synth.phenotype(seed, n, p, kind)
+    g = gbm.Genomes.from_matrix(A)
+    ph = gbm.Phenomes.from_matrix(y, entries=g.entries)
+    return A, y, g, ph
+
+
+@pytest.mark.parametrize("GRM_type", ["simple", "ploidy-aware"])
+def test_gwasols_gwaslmm_end_to_end(gbm, GRM_type):
+    """BASELINE config 1: n=300, l=10_000, 1 trait -- the whole reference pipeline."""
+    n, p = 300, 10000
+    A, y, g, ph = _structs(gbm, n, p, synth.KIND_TETRAPLOID)
+    f1 = gbm.gwasols(genomes=g, phenomes=ph, GRM_type=GRM_type)
+    f2 = gbm.gwaslmm(genomes=g, phenomes=ph, GRM_type=GRM_type)
+    assert f1.model == "GWAS_OLS" and f2.model == "GWAS_LMM"  # doctests gwas.jl:194-200, :317-323
+    b_ref, prep, pc = go.gwasols(A, g.entries, y[:, None], ph.entries, GRM_type=GRM_type)
+    z_ref, _, _ = go.gwaslmm(A, g.entries, y[:, None], ph.entries, GRM_type=GRM_type)
+    assert np.array_equal(f1.extras["idx_cols"], prep.idx_cols)
+    assert f1.b_hat_labels == [g.loci_alleles[j - 1] for j in prep.idx_cols]
+    if GRM_type == "ploidy-aware":
+        assert f1.extras["ploidy"] == prep.ploidy == 4
+    assert rel_err(f1.b_hat, b_ref) < 1e-8
+    assert rel_err(f2.b_hat, z_ref) < RTOL
+    assert f1.checkdims() and f2.checkdims() and f1.metrics == {"": 0.0}
+
+
+def test_gwasols_argmax_equal_across_grm_types(gbm):
+    """The reference's own doctest assertion (gwas.jl:202-203, :325-326)."""
+    _, _, g, ph = _structs(gbm, 300, 4000, synth.KIND_TETRAPLOID, seed=5)
+    a = gbm.gwasols(genomes=g, phenomes=ph, GRM_type="simple")
+    b = gbm.gwasols(genomes=g, phenomes=ph, GRM_type="ploidy-aware")
+    assert np.argmax(a.b_hat) == np.argmax(b.b_hat)
+
+
+def test_gwasprep_doctest_invariants(gbm):
+    """gwasprep doctest (gwas.jl:53-74)."""
+    n, p = 300, 3000
+    A, y, g, ph = _structs(gbm, n, p, synth.KIND_TETRAPLOID)
+    G, ys, K, fit = gbm.gwasprep(genomes=g, phenomes=ph)
+    assert np.all(np.abs(G.mean(axis=0)) < 1e-10)
+    assert np.all(np.abs(G.std(axis=0, ddof=1) - 1) < 1e-10)
+    assert abs(ys.mean()) < 1e-10 and abs(ys.std(ddof=1) - 1) < 1e-10
+    assert G.shape[0] == ys.shape[0] and K.shape == (n, n)
+    assert len(fit.entries) == n and fit.b_hat.shape[0] == G.shape[1]
+    prep = go.gwasprep(A, g.entries, y[:, None], ph.entries)
+    np.testing.assert_allclose(G, prep.G, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(K, prep.K, rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(ys, prep.y, rtol=1e-13)
+
+
+def test_index_subsets_and_errors(gbm):
+    n, p = 200, 500
+    A, y, g, ph = _structs(gbm, n, p, synth.KIND_CONTINUOUS)
+    cols = np.arange(3, 400, 2, dtype=np.int64)
+    f = gbm.gwasols(genomes=g, phenomes=ph, idx_loci_alleles=cols)
+    b_ref, prep, _ = go.gwasols(A, g.entries, y[:, None], ph.entries, idx_loci_alleles=cols)
+    assert np.array_equal(f.extras["idx_cols"], prep.idx_cols)
+    assert rel_err(f.b_hat, b_ref) < 1e-8
+    with pytest.raises(gbm.ArgumentError):
+        gbm.gwasols(genomes=g, phenomes=ph, GRM_type="fancy")
+    with pytest.raises(gbm.ArgumentError):
+        gbm.gwasols(genomes=g, phenomes=ph, idx_loci_alleles=[0, 1])
+    with pytest.raises(gbm.ArgumentError):
+        gbm.gwasols(genomes=g, phenomes=ph, idx_entries=[1, n + 1])
+    with pytest.raises(gbm.ArgumentError):  # dropped entries -> GRM/G row mismatch
+        gbm.gwasols(genomes=g, phenomes=ph, idx_entries=list(range(1, 101)))
+
+
+def test_scan_host_matches_resident_scan(gbm):
+    n, p = 1000, 5000
+    A, ys, pc = _problem(13, n, p, synth.KIND_DIPLOID)
+    dm = gbm.DeviceMatrix.upload(A)
+    a = dm.scan(ys, pc[:, None], model=1)
+    dm.free()
+    b = gbm.scan_host(A, ys, pc[:, None], model=1)
+    for key in ("beta", "se", "stat", "neglog10p", "mean", "sd"):
+        assert np.array_equal(a[key], b[key], equal_nan=True), key
+    assert np.array_equal(a["keep"], b["keep"])
+
+
+def test_scan_is_deterministic_and_shard_invariant(gbm):
+    """Per-marker results do not depend on how the columns are sharded."""
+    n, p = 1500, 4000
+    A, ys, pc = _problem(17, n, p, synth.KIND_DIPLOID)
+    dm = gbm.DeviceMatrix.upload(A)
+    full = dm.scan(ys, pc[:, None], model=0)
+    again = dm.scan(ys, pc[:, None], model=0)
+    dm.free()
+    assert np.array_equal(full["stat"], again["stat"], equal_nan=True)
+    parts = []
+    for j0, j1 in ((0, 1000), (1000, 1777), (1777, 4000)):
+        d = gbm.DeviceMatrix.upload(np.asfortranarray(A[:, j0:j1]))
+        parts.append(d.scan(ys, pc[:, None], model=0)["stat"])
+        d.free()
+    assert np.array_equal(np.vstack(parts), full["stat"], equal_nan=True)
+
+
+def test_grm_sharded_accumulate_equals_single(gbm):
+    import torch
+
+    n, p = 384, 6000
+    A = synth.block(4, n, 0, p, synth.KIND_DIPLOID)
+    dm = gbm.DeviceMatrix.upload(A)
+    K1, _ = dm.grm(0, 2, 0)
+    dm.free()
+    dK = torch.zeros(n * n, dtype=torch.float64, device="cuda:0")
+    for j0, j1 in ((0, 2500), (2500, 6000)):
+        d = gbm.DeviceMatrix.upload(np.asfortranarray(A[:, j0:j1]))
+        d.grm_accumulate(dK.data_ptr(), centre=True)
+        d.free()
+    gbm.grm_finalize(dK.data_ptr(), n, 1.0 / p)
+    K2 = dK.cpu().numpy().reshape(n, n).T
+    assert np.max(np.abs(K1 - K2)) < 1e-12 * np.abs(K1).max()
