@@ -124,18 +124,35 @@ def shard_bounds(p: int, world: int, rank: int):
 # --------------------------------------------------------------------------------------
 # CPU arm: the oracle's C/OpenMP restatement of the reference's per-marker loop
 # --------------------------------------------------------------------------------------
-def cpu_sample_rate(n: int, markers: int, reps: int = 1):
-    """markers/s of the reference algorithm (std filter, standardise, hcat, pinv(X'X), statistic;
-    /root/reference/src/gwas.jl:112-115, :129, :241-245) on all host cores."""
-    from oracle import cbind, synth
+def synth_block_chunked(n: int, markers: int, chunk: int = 512):
+    """synth.block in column chunks (its uint64 temporaries are ~10x the output)."""
+    from oracle import synth
 
-    A = synth.block(SEED, n, 0, markers, KIND_DIPLOID)
-    y = synth.phenotype(SEED, n, 1_000_000, KIND_DIPLOID)
+    A = np.empty((n, markers), dtype=np.float64, order="F")
+    for j0 in range(0, markers, chunk):
+        j1 = min(markers, j0 + chunk)
+        A[:, j0:j1] = synth.block(SEED, n, j0, j1 - j0, KIND_DIPLOID)
+    return A
+
+
+def cpu_inputs(n: int, p: int):
+    from oracle import synth
+
+    y = synth.phenotype(SEED, n, p, KIND_DIPLOID)
     ys = (y - y.mean()) / y.std(ddof=1)
-    rng = np.random.default_rng(1)
-    pc = rng.normal(size=n)
+    pc = np.random.default_rng(1).normal(size=n)
     pc -= pc.mean()
     pc /= np.linalg.norm(pc)
+    return ys, pc
+
+
+def cpu_sample_rate(n: int, p: int, markers: int, reps: int = 1):
+    """markers/s of the reference algorithm (std filter, standardise, hcat, pinv(X'X), statistic;
+    /root/reference/src/gwas.jl:112-115, :129, :241-245) on all host cores."""
+    from oracle import cbind
+
+    A = synth_block_chunked(n, markers)
+    ys, pc = cpu_inputs(n, p)
     cbind.gwasols_raw(A[:, :64], ys, pc)  # warm-up (thread pool, page faults)
     best = float("inf")
     for _ in range(reps):
@@ -149,20 +166,16 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    n = args.n
-    # bounded sample: ~1 s of CPU work per step
-    rate0, _, cores = cpu_sample_rate(n, 512)
-    markers = args.cpu_markers or int(max(512, min(200_000, rate0 * 1.0)))
-    for _ in range(args.warmup):
-        cpu_sample_rate(n, min(markers, 2048))
-    from oracle import cbind, synth
+    from oracle import cbind
 
-    A = synth.block(SEED, n, 0, markers, KIND_DIPLOID)
-    y = synth.phenotype(SEED, n, args.p, KIND_DIPLOID)
-    ys = (y - y.mean()) / y.std(ddof=1)
-    pc = np.random.default_rng(1).normal(size=n)
-    pc -= pc.mean()
-    pc /= np.linalg.norm(pc)
+    n = args.n
+    # bounded sample: ~1 s of CPU work per step, at most 2 GB of genotypes
+    rate0, _, cores = cpu_sample_rate(n, args.p, 512)
+    markers = args.cpu_markers or int(max(512, min(25_000, rate0 * 1.0)))
+    A = synth_block_chunked(n, markers)
+    ys, pc = cpu_inputs(n, args.p)
+    for _ in range(args.warmup):
+        cbind.gwasols_raw(A[:, : min(markers, 2048)], ys, pc)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cbind.gwasols_raw(A, ys, pc)
@@ -232,11 +245,11 @@ def main():
     outs = {k: torch.empty(p_loc, dtype=torch.float64, device="cuda") for k in ("beta", "se", "stat", "nlp", "mean", "sd")}
     keep = torch.empty(p_loc, dtype=torch.uint8, device="cuda")
 
+    plan = gbm_b200.ScanPlan(dm, Y, C, model=model)  # y / PC1 prepared and resident before the timed region
+
     def step():
-        _lib.check(lib.gbm_scan(dm._h, _lib.ptr(Y), 1, n, _lib.ptr(C), 1, n, model, 0, _lib.ptr(outs["beta"]),
-                                _lib.ptr(outs["se"]), _lib.ptr(outs["stat"]), _lib.ptr(outs["nlp"]),
-                                _lib.ptr(outs["mean"]), _lib.ptr(outs["sd"]), _lib.ptr(keep)))
-        return _lib.last_timing()
+        # one pass over the shard: streaming-sums kernel + finalisation kernel, device outputs in place
+        return plan.run(outs["beta"], outs["se"], outs["stat"], outs["nlp"], outs["mean"], outs["sd"], keep)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -286,8 +299,6 @@ def main():
         sub = gbm_b200.DeviceMatrix.generate(SEED, n, pe, KIND_DIPLOID, col0=j0)
         info = sub.info()
         assert info["lda"] == n
-        src = torch.empty(0)
-        _ = src
         # device -> pinned host (untimed set-up)
         import ctypes
 
@@ -322,6 +333,7 @@ def main():
                        "h2d_gbps": 8.0 * n * pe * args.e2e_steps / dt / 1e9}
         del host
 
+    plan.free()
     dm.free()
 
     if rank == 0 and not args.no_grm:
@@ -357,9 +369,9 @@ def main():
         line["pipeline"] = run_pipeline(gbm_b200, _lib, n, p_loc, j0, ys)
 
     if rank == 0 and not args.no_cpu:
-        rate0, _, cores = cpu_sample_rate(n, 512)
-        markers = args.cpu_markers or int(max(1024, min(400_000, rate0 * 12.0)))
-        rate, secs, cores = cpu_sample_rate(n, markers)
+        rate0, _, cores = cpu_sample_rate(n, p, 512)
+        markers = args.cpu_markers or int(max(1024, min(40_000, rate0 * 12.0)))  # ~12 s, <= 3.2 GB of genotypes
+        rate, secs, cores = cpu_sample_rate(n, p, markers)
         line["cpu_baseline"] = {"value": rate, "unit": "markers/s", "cores": cores, "kind": "port",
                                 "sample": f"{markers} of {p} markers (n={n}) in {secs:.1f} s; C/OpenMP restatement of "
                                           "the reference's per-marker loop (gwas.jl:112-115,:129,:241-245); the "

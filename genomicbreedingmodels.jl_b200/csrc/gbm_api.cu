@@ -244,12 +244,16 @@ struct ScanOutputs {
 };
 
 static void scan_block(const double* dA, int64_t n, int64_t p_blk, int64_t lda,
-                       const std::vector<std::unique_ptr<Pass>>& passes, int k_eff, int model, int flags,
-                       const ScanOutputs& dev_out, int64_t ld_out, int64_t col0, Span* main_span) {
+                       const std::vector<std::unique_ptr<Pass>>& passes, const std::vector<double*>& rec_bufs,
+                       int k_eff, int model, int flags, const ScanOutputs& dev_out, int64_t ld_out, int64_t col0,
+                       Span* main_span) {
   State& st = state();
   const int64_t ldq = round_up(n, 2);
-  for (const auto& ps : passes) {
-    DevBuf<double> rec(static_cast<size_t>(p_blk) * ps->stride, st.stream);
+  for (size_t pi = 0; pi < passes.size(); ++pi) {
+    const auto& ps = passes[pi];
+    const bool own_rec = rec_bufs.empty();
+    DevBuf<double> rec_tmp(own_rec ? static_cast<size_t>(p_blk) * ps->stride : 0, st.stream);
+    struct { double* p; } rec{own_rec ? rec_tmp.p : rec_bufs[pi]};
     if (main_span) main_span->start();
     launch_scan_sums(dA, n, p_blk, lda, ps->dQ.p, ps->M, ldq, false, rec.p, st.sm_count, st.stream);
     if (main_span) main_span->stop();
@@ -321,6 +325,12 @@ int gbm_init(int device) {
   if (!st.own_stream) GBM_CUDA(cudaStreamCreateWithFlags(&st.own_stream, cudaStreamNonBlocking));
   if (!st.copy_stream) GBM_CUDA(cudaStreamCreateWithFlags(&st.copy_stream, cudaStreamNonBlocking));
   st.stream = st.own_stream;
+  {  // keep stream-ordered scratch allocations cached instead of returning them at every sync
+    cudaMemPool_t pool;
+    GBM_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;
+    GBM_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  }
   st.ready = true;
   GBM_API_END
 }
@@ -831,49 +841,155 @@ static void check_scan_args(int64_t n, const double* Y, int64_t T, int64_t ldy, 
   if (n - k - 2 < 1) GBM_THROW(GBM_ERR_ARGUMENT, "scan: not enough entries for the number of covariates");
 }
 
-struct DevOutputs {
-  DevBuf<double> beta, se, stat, nlp, mean, sd;
-  DevBuf<uint8_t> keep;
-  DevOutputs(int64_t p, int64_t T, bool b, bool s, bool st_, bool nl, bool m, bool sd_, bool k, cudaStream_t stream)
-      : beta(b ? p * T : 0, stream), se(s ? p * T : 0, stream), stat(st_ ? p * T : 0, stream),
-        nlp(nl ? p * T : 0, stream), mean(m ? p : 0, stream), sd(sd_ ? p : 0, stream), keep(k ? p : 0, stream) {}
-  ScanOutputs view() { return ScanOutputs{beta.p, se.p, stat.p, nlp.p, mean.p, sd.p, keep.p}; }
+// Resolves the user's output pointers: device pointers are written by the kernels in place,
+// host pointers get a device scratch array that is copied out afterwards.
+struct OutTargets {
+  struct Slot {
+    void* user = nullptr;
+    void* dev = nullptr;
+    void* scratch = nullptr;
+    size_t bytes = 0;
+  };
+  Slot slot[7];
+  cudaStream_t s;
+  explicit OutTargets(cudaStream_t stream) : s(stream) {}
+  ~OutTargets() {
+    for (auto& q : slot)
+      if (q.scratch) cudaFreeAsync(q.scratch, s);
+  }
+  OutTargets(const OutTargets&) = delete;
+  OutTargets& operator=(const OutTargets&) = delete;
+  void bind(int i, void* user, size_t bytes) {
+    Slot& q = slot[i];
+    q.user = user;
+    if (!user) {
+      q.dev = nullptr;
+      return;
+    }
+    if (is_device_ptr(user)) {
+      q.dev = user;
+      return;
+    }
+    if (!q.scratch || q.bytes < bytes) {
+      if (q.scratch) cudaFreeAsync(q.scratch, s);
+      GBM_CUDA(cudaMallocAsync(&q.scratch, bytes, s));
+      q.bytes = bytes;
+    }
+    q.dev = q.scratch;
+  }
+  void bind_all(int64_t p, int64_t T, double* beta, double* se, double* stat, double* nlp, double* mean,
+                double* sd, uint8_t* keep) {
+    bind(0, beta, sizeof(double) * p * T);
+    bind(1, se, sizeof(double) * p * T);
+    bind(2, stat, sizeof(double) * p * T);
+    bind(3, nlp, sizeof(double) * p * T);
+    bind(4, mean, sizeof(double) * p);
+    bind(5, sd, sizeof(double) * p);
+    bind(6, keep, static_cast<size_t>(p));
+  }
+  ScanOutputs view() const {
+    return ScanOutputs{static_cast<double*>(slot[0].dev), static_cast<double*>(slot[1].dev),
+                       static_cast<double*>(slot[2].dev), static_cast<double*>(slot[3].dev),
+                       static_cast<double*>(slot[4].dev), static_cast<double*>(slot[5].dev),
+                       static_cast<uint8_t*>(slot[6].dev)};
+  }
+  void copy_back(int64_t p, int64_t T) {
+    const size_t sz[7] = {sizeof(double) * p * T, sizeof(double) * p * T, sizeof(double) * p * T,
+                          sizeof(double) * p * T, sizeof(double) * p,     sizeof(double) * p,
+                          static_cast<size_t>(p)};
+    for (int i = 0; i < 7; ++i)
+      if (slot[i].user && slot[i].dev != slot[i].user) copy_out(slot[i].user, slot[i].dev, sz[i], s);
+  }
 };
 
-int gbm_scan(const gbm_matrix* m, const double* Y, int64_t T, int64_t ldy, const double* C, int64_t k, int64_t ldc,
-             int model, int flags, double* beta, double* se, double* stat, double* neglog10p, double* mean,
-             double* sd, uint8_t* keep) {
+}  // extern "C"  (plan type lives at global scope)
+
+struct gbm_scan_plan {
+  const gbm_matrix* m = nullptr;
+  int64_t T = 0;
+  int k_eff = 0, model = 0, flags = 0;
+  std::vector<std::unique_ptr<gbm::Pass>> passes;
+  std::vector<double*> rec;  // one record buffer per pass, kept for the plan's lifetime
+  std::unique_ptr<OutTargets> out;
+};
+
+extern "C" {
+
+int gbm_scan_plan_create(const gbm_matrix* m, const double* Y, int64_t T, int64_t ldy, const double* C, int64_t k,
+                         int64_t ldc, int model, int flags, gbm_scan_plan** plan_out) {
   GBM_API_BEGIN
   require_ready();
-  if (!m) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_scan: null handle");
+  if (!m || !plan_out) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_scan_plan_create: null pointer");
   check_scan_args(m->n, Y, T, ldy, C, k, ldc, model);
   State& st = state();
-  reset_timing();
-  const int64_t p = m->p;
   SideVectors sv = prepare_side_vectors(Y, m->n, T, ldy, C, k, ldc);
   for (int64_t t = 0; t < T; ++t)
     if (!(sv.yMy[t] > 0.0)) GBM_THROW(GBM_ERR_ARGUMENT, "No variance in the trait after removing the covariates.");
-  DevOutputs out(p, T, beta, se, stat, neglog10p, mean, sd, keep, st.stream);
-  auto passes = build_passes(sv, m->n, T);
+  std::unique_ptr<gbm_scan_plan> pl(new gbm_scan_plan);
+  pl->m = m;
+  pl->T = T;
+  pl->k_eff = sv.k_eff;
+  pl->model = model;
+  pl->flags = flags;
+  pl->passes = build_passes(sv, m->n, T);
+  for (const auto& ps : pl->passes) {
+    double* r = nullptr;
+    GBM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r), sizeof(double) * m->p * ps->stride));
+    pl->rec.push_back(r);
+  }
+  pl->out.reset(new OutTargets(st.stream));
+  *plan_out = pl.release();
+  GBM_API_END
+}
+
+int gbm_scan_plan_run(gbm_scan_plan* pl, double* beta, double* se, double* stat, double* neglog10p, double* mean,
+                      double* sd, uint8_t* keep) {
+  GBM_API_BEGIN
+  require_ready();
+  if (!pl) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_scan_plan_run: null plan");
+  State& st = state();
+  reset_timing();
+  const gbm_matrix* m = pl->m;
+  const int64_t p = m->p;
+  pl->out->s = st.stream;
+  pl->out->bind_all(p, pl->T, beta, se, stat, neglog10p, mean, sd, keep);
   Span all(st.stream), mainsp(st.stream);
   all.start();
-  scan_block(m->d, m->n, p, m->lda, passes, sv.k_eff, model, flags, out.view(), p, 0, &mainsp);
+  scan_block(m->d, m->n, p, m->lda, pl->passes, pl->rec, pl->k_eff, pl->model, pl->flags, pl->out->view(), p, 0,
+             &mainsp);
   all.stop();
   Span d2h(st.stream);
   d2h.start();
-  copy_out(beta, out.beta.p, sizeof(double) * p * T, st.stream);
-  copy_out(se, out.se.p, sizeof(double) * p * T, st.stream);
-  copy_out(stat, out.stat.p, sizeof(double) * p * T, st.stream);
-  copy_out(neglog10p, out.nlp.p, sizeof(double) * p * T, st.stream);
-  copy_out(mean, out.mean.p, sizeof(double) * p, st.stream);
-  copy_out(sd, out.sd.p, sizeof(double) * p, st.stream);
-  copy_out(keep, out.keep.p, p, st.stream);
+  pl->out->copy_back(p, pl->T);
   d2h.stop();
   GBM_CUDA(cudaStreamSynchronize(st.stream));
   st.kernel_ms = all.ms();
   st.main_ms = mainsp.ms();
   st.d2h_ms = d2h.ms();
   GBM_API_END
+}
+
+int gbm_scan_plan_free(gbm_scan_plan* pl) {
+  GBM_API_BEGIN
+  if (pl) {
+    if (state().ready) cudaStreamSynchronize(state().stream);
+    for (double* r : pl->rec) cudaFree(r);
+    delete pl;
+  }
+  GBM_API_END
+}
+
+int gbm_scan(const gbm_matrix* m, const double* Y, int64_t T, int64_t ldy, const double* C, int64_t k, int64_t ldc,
+             int model, int flags, double* beta, double* se, double* stat, double* neglog10p, double* mean,
+             double* sd, uint8_t* keep) {
+  gbm_scan_plan* pl = nullptr;
+  int rc = gbm_scan_plan_create(m, Y, T, ldy, C, k, ldc, model, flags, &pl);
+  if (rc != GBM_OK) return rc;
+  rc = gbm_scan_plan_run(pl, beta, se, stat, neglog10p, mean, sd, keep);
+  std::string keep_msg = rc != GBM_OK ? std::string(gbm_last_error()) : std::string();
+  gbm_scan_plan_free(pl);
+  if (rc != GBM_OK) set_error(keep_msg);
+  return rc;
 }
 
 int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const double* Y, int64_t T, int64_t ldy,
@@ -889,8 +1005,10 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
   SideVectors sv = prepare_side_vectors(Y, n, T, ldy, C, k, ldc);
   for (int64_t t = 0; t < T; ++t)
     if (!(sv.yMy[t] > 0.0)) GBM_THROW(GBM_ERR_ARGUMENT, "No variance in the trait after removing the covariates.");
-  DevOutputs out(p, T, beta, se, stat, neglog10p, mean, sd, keep, st.stream);
+  OutTargets out(st.stream);
+  out.bind_all(p, T, beta, se, stat, neglog10p, mean, sd, keep);
   auto passes = build_passes(sv, n, T);
+  const std::vector<double*> no_rec;
   // column blocks of ~256 MB, double-buffered: the copy engine fills one buffer while the
   // scan kernel streams the other
   const int64_t ldd = round_up(n, 16);
@@ -916,17 +1034,11 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
                                pc, cudaMemcpyDefault, st.copy_stream));
     GBM_CUDA(cudaEventRecord(copied[b], st.copy_stream));
     GBM_CUDA(cudaStreamWaitEvent(st.stream, copied[b], 0));
-    scan_block(buf[b], n, pc, ldd, passes, sv.k_eff, model, flags, out.view(), p, j0, nullptr);
+    scan_block(buf[b], n, pc, ldd, passes, no_rec, sv.k_eff, model, flags, out.view(), p, j0, nullptr);
     GBM_CUDA(cudaEventRecord(consumed[b], st.stream));
   }
   all.stop();
-  copy_out(beta, out.beta.p, sizeof(double) * p * T, st.stream);
-  copy_out(se, out.se.p, sizeof(double) * p * T, st.stream);
-  copy_out(stat, out.stat.p, sizeof(double) * p * T, st.stream);
-  copy_out(neglog10p, out.nlp.p, sizeof(double) * p * T, st.stream);
-  copy_out(mean, out.mean.p, sizeof(double) * p, st.stream);
-  copy_out(sd, out.sd.p, sizeof(double) * p, st.stream);
-  copy_out(keep, out.keep.p, p, st.stream);
+  out.copy_back(p, T);
   GBM_CUDA(cudaStreamSynchronize(st.stream));
   GBM_CUDA(cudaStreamSynchronize(st.copy_stream));
   st.kernel_ms = all.ms();  // copy + compute overlapped: wall time of the pipeline on the device

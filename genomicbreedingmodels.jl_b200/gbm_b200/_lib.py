@@ -71,6 +71,9 @@ SIGNATURES = {
     "gbm_grm_finalize": (c_int, [_P, c_int64, c_double]),
     "gbm_kstd_pc1": (c_int, [_P, c_int64, _P, _P, POINTER(c_double)]),
     "gbm_scan": (c_int, [c_void_p, _P, c_int64, c_int64, _P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "gbm_scan_plan_create": (c_int, [c_void_p, _P, c_int64, c_int64, _P, c_int64, c_int64, c_int, c_int, POINTER(c_void_p)]),
+    "gbm_scan_plan_run": (c_int, [c_void_p, _P, _P, _P, _P, _P, _P, _P]),
+    "gbm_scan_plan_free": (c_int, [c_void_p]),
     "gbm_scan_host": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int64, c_int64, c_int, c_int,
                               _P, _P, _P, _P, _P, _P, _P]),
     "gbm_neglog10_sf": (c_int, [_P, c_int64, c_int, c_double, _P]),

@@ -142,6 +142,39 @@ class DeviceMatrix:
         return out
 
 
+class ScanPlan:
+    """Prepared scan over a resident DeviceMatrix (``gbm_scan_plan``): run() is just the two
+    kernel launches.  Outputs may be NumPy arrays (copied out) or CUDA tensors (written in place)."""
+
+    def __init__(self, dm: DeviceMatrix, Y, C=None, model: int = _lib.MODEL_OLS, flags: int = 0):
+        Y = np.asarray(Y, dtype=np.float64)
+        if Y.shape[0] != dm.n:
+            raise _lib.ArgumentError("phenotype length does not match the number of entries")
+        Y = _f64(Y.reshape(dm.n, -1))
+        Cm = None if C is None else _f64(np.asarray(C, dtype=np.float64).reshape(dm.n, -1))
+        self.dm, self.T = dm, Y.shape[1]
+        h = c_void_p()
+        check(_lib.load().gbm_scan_plan_create(dm._h, ptr(Y), self.T, dm.n, ptr(Cm), 0 if Cm is None else Cm.shape[1],
+                                               dm.n, model, flags, byref(h)))
+        self._h = h
+
+    def run(self, beta=None, se=None, stat=None, neglog10p=None, mean=None, sd=None, keep=None):
+        check(_lib.load().gbm_scan_plan_run(self._h, ptr(beta), ptr(se), ptr(stat), ptr(neglog10p), ptr(mean),
+                                            ptr(sd), ptr(keep)))
+        return _lib.last_timing()
+
+    def free(self):
+        if self._h is not None:
+            check(_lib.load().gbm_scan_plan_free(self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 def grm_finalize(dK_ptr: int, n: int, scale: float):
     check(_lib.lib().gbm_grm_finalize(c_void_p(dK_ptr), n, scale))
 

@@ -1,0 +1,262 @@
+# GenomicBreedingModelsB200.jl -- Julia shim over libgbm_b200.so (include/gbm_b200.h).
+#
+# Drop-in for the GWAS hot path of GenomicBreedingModels.jl v0.3.0: same function names,
+# keyword arguments, return types and exceptions as
+#     gwasprep  src/gwas.jl:77-142      gwasols  src/gwas.jl:206-259      gwaslmm  src/gwas.jl:329-399
+# and GenomicBreedingCore's grmsimple / grmploidyaware (call sites src/gwas.jl:120, :124).
+# Genomes / Phenomes in, Fit out.  One blocking `ccall` per phase from one Julia thread; the
+# library never calls back into Julia and never keeps a host pointer after it returns.
+#
+# NOT EXECUTED IN THE BUILD IMAGE (no Julia there): the Python ctypes harness
+# (../gbm_b200) binds the same symbols with the same call sequence and is what the tests run.
+module GenomicBreedingModelsB200
+
+using GenomicBreedingCore
+using Statistics
+
+export gwasprep, gwasols, gwaslmm, grmsimple_b200, grmploidyaware_b200
+
+const LIBGBM = get(ENV, "GBM_B200_LIB", joinpath(@__DIR__, "..", "libgbm_b200.so"))
+
+const GBM_OK = Cint(0)
+const GBM_ERR_ARGUMENT = Cint(1)
+const GBM_ERR_RUNTIME = Cint(2)
+const GBM_GRM_SIMPLE = Cint(0)
+const GBM_GRM_PLOIDY_AWARE = Cint(1)
+const GBM_MODEL_OLS = Cint(0)
+const GBM_MODEL_LMM = Cint(1)
+
+function check(code::Cint)
+    code == GBM_OK && return nothing
+    msg = unsafe_string(ccall((:gbm_last_error, LIBGBM), Cstring, ()))
+    code == GBM_ERR_ARGUMENT && throw(ArgumentError(msg))
+    throw(ErrorException(msg))
+end
+
+const INITIALISED = Ref(false)
+function init(device::Integer = parse(Int, get(ENV, "GBM_DEVICE", "0")))
+    if !INITIALISED[]
+        check(ccall((:gbm_init, LIBGBM), Cint, (Cint,), device))
+        INITIALISED[] = true
+    end
+    nothing
+end
+
+# ---- device matrix handle (library-owned HBM, freed by finalizer) --------------------
+mutable struct DeviceMatrix
+    handle::Ptr{Cvoid}
+    n::Int64
+    p::Int64
+    function DeviceMatrix(h::Ptr{Cvoid}, n, p)
+        m = new(h, n, p)
+        finalizer(free!, m)
+        m
+    end
+end
+function free!(m::DeviceMatrix)
+    if m.handle != C_NULL
+        ccall((:gbm_matrix_free, LIBGBM), Cint, (Ptr{Cvoid},), m.handle)
+        m.handle = C_NULL
+    end
+    nothing
+end
+
+# G = genomes.allele_frequencies[rows, cols]  (src/prediction.jl:129) without the host copy
+function upload(A::Matrix{Float64}, rows::Union{Nothing,Vector{Int64}}, cols::Union{Nothing,Vector{Int64}})
+    init()
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    n0, p0 = size(A)
+    if isnothing(rows) && isnothing(cols)
+        check(ccall((:gbm_matrix_upload, LIBGBM), Cint, (Ptr{Float64}, Int64, Int64, Int64, Ref{Ptr{Cvoid}}),
+                    A, n0, p0, n0, h))
+        return DeviceMatrix(h[], n0, p0)
+    end
+    n = isnothing(rows) ? n0 : length(rows)
+    p = isnothing(cols) ? p0 : length(cols)
+    check(ccall((:gbm_matrix_upload_indexed, LIBGBM), Cint,
+                (Ptr{Float64}, Int64, Int64, Int64, Ptr{Int64}, Int64, Ptr{Int64}, Int64, Ref{Ptr{Cvoid}}),
+                A, n0, p0, n0, isnothing(rows) ? C_NULL : pointer(rows), n,
+                isnothing(cols) ? C_NULL : pointer(cols), p, h))
+    DeviceMatrix(h[], n, p)
+end
+
+function colstats(m::DeviceMatrix)
+    mean = Vector{Float64}(undef, m.p); sd = similar(mean); mnz = similar(mean)
+    keep = Vector{UInt8}(undef, m.p); idx = Vector{Int64}(undef, m.p)
+    nk = Ref{Int64}(0); mk = Ref{Float64}(0.0)
+    check(ccall((:gbm_colstats, LIBGBM), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}, Ptr{Int64}, Ref{Int64}, Ref{Float64}),
+                m.handle, mean, sd, mnz, keep, idx, nk, mk))
+    (mean = mean, sd = sd, idx_cols = idx[1:nk[]], min_nonzero_kept = mk[])
+end
+
+function grm(m::DeviceMatrix, grm_type::Cint, ploidy::Integer; flags::Integer = 0)
+    K = Matrix{Float64}(undef, m.n, m.n)
+    tf = Ref{Float64}(0.0)
+    check(ccall((:gbm_grm, LIBGBM), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Float64}, Ref{Float64}),
+                m.handle, grm_type, ploidy, flags, K, tf))
+    K
+end
+
+function kstd_pc1(K::Matrix{Float64}; want_kstd::Bool = true, want_pc1::Bool = true)
+    n = size(K, 1)
+    Ks = want_kstd ? Matrix{Float64}(undef, n, n) : nothing
+    pc = want_pc1 ? Vector{Float64}(undef, n) : nothing
+    ms = Ref{Float64}(0.0)
+    check(ccall((:gbm_kstd_pc1, LIBGBM), Cint, (Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
+                K, n, want_kstd ? pointer(Ks) : C_NULL, want_pc1 ? pointer(pc) : C_NULL, ms))
+    (Ks, pc)
+end
+
+function scan(m::DeviceMatrix, y::Vector{Float64}, pc::Vector{Float64}, model::Cint)
+    stat = Vector{Float64}(undef, m.p); beta = similar(stat); se = similar(stat); nlp = similar(stat)
+    check(ccall((:gbm_scan, LIBGBM), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Float64}, Int64, Int64, Cint, Cint, Ptr{Float64},
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}),
+                m.handle, y, 1, m.n, pc, 1, m.n, model, 0, beta, se, stat, nlp, C_NULL, C_NULL, C_NULL))
+    (stat = stat, beta = beta, se = se, neglog10p = nlp)
+end
+
+# ---- the reference's row filter and validation (src/prediction.jl:67-127), host side ----
+function selectrows(genomes::Genomes, phenomes::Phenomes, idx_entries, idx_loci_alleles, idx_trait::Int64)
+    if !checkdims(genomes) && !checkdims(phenomes)
+        throw(ArgumentError("The Genomes and Phenomes structs are corrupted ☹."))
+    end
+    !checkdims(genomes) && throw(ArgumentError("The Genomes struct is corrupted ☹."))
+    !checkdims(phenomes) && throw(ArgumentError("The Phenomes struct is corrupted ☹."))
+    if genomes.entries != phenomes.entries
+        throw(ArgumentError("The genomes and phenomes input need to have been merged to have consitent entries."))
+    end
+    allrows = isnothing(idx_entries)
+    idx_entries = allrows ? collect(1:length(genomes.entries)) : idx_entries
+    if minimum(idx_entries) < 1 || maximum(idx_entries) > length(genomes.entries)
+        throw(ArgumentError("The indexes of the entries, `idx_entries` are out of bounds."))
+    end
+    if !isnothing(idx_loci_alleles) &&
+       (minimum(idx_loci_alleles) < 1 || maximum(idx_loci_alleles) > length(genomes.loci_alleles))
+        throw(ArgumentError("The indexes of the loci_alleles, `idx_loci_alleles` are out of bounds."))
+    end
+    ϕ = phenomes.phenotypes[idx_entries, idx_trait]
+    idx = findall(.!ismissing.(ϕ) .&& .!isnan.(ϕ) .&& .!isinf.(ϕ))
+    if length(idx) < 2
+        throw(ArgumentError("There are less than 2 entries with non-missing phenotype data after merging with the genotype data."))
+    end
+    y::Vector{Float64} = ϕ[idx]
+    if var(y) < 1e-20
+        throw(ErrorException("Very low or zero variance in trait: `" * phenomes.traits[idx_trait] * "`."))
+    end
+    rows = (allrows && length(idx) == length(idx_entries)) ? nothing : idx_entries[idx]
+    (rows, idx_loci_alleles, y)
+end
+
+struct Prepared
+    dm::DeviceMatrix
+    y::Vector{Float64}
+    K::Union{Nothing,Matrix{Float64}}
+    pc1::Union{Nothing,Vector{Float64}}
+    stats::NamedTuple
+    entries::Vector{String}
+    populations::Vector{String}
+    loci_alleles::Vector{String}
+    trait::String
+end
+
+function prepare(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type, standardise; need_kstd, need_pc1)
+    rows, cols, y = selectrows(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait)   # src/gwas.jl:93-100
+    if sum(["simple", "ploidy-aware"] .== GRM_type) == 0                                       # :101-107
+        throw(ArgumentError("Unrecognised `GRM_type`. Please select from:\n\t‣ simple\n\t‣ ploidy-aware"))
+    end
+    var(y) < eps(Float64) && throw(ArgumentError("No variance in the trait: " * phenomes.traits[idx_trait] * "."))  # :109-111
+    A = Matrix{Float64}(genomes.allele_frequencies)   # throws on `missing`, as src/prediction.jl:129 does
+    dm = upload(A, rows, cols)
+    stats = colstats(dm)                               # :112-113
+    r = isnothing(rows) ? collect(1:size(A, 1)) : rows
+    c = isnothing(cols) ? collect(1:size(A, 2)) : cols
+    loci = genomes.loci_alleles[c][stats.idx_cols]     # :115
+    full = (isnothing(rows) && isnothing(cols)) ? dm : upload(A, nothing, nothing)   # GRM on the FULL genomes (:120, :124)
+    K = if GRM_type == "ploidy-aware"
+        ploidy = Int(round(1 / stats.min_nonzero_kept))                              # :119
+        grm(full, GBM_GRM_PLOIDY_AWARE, ploidy)
+    else
+        grm(full, GBM_GRM_SIMPLE, 2)
+    end
+    full === dm || free!(full)
+    pc1 = nothing
+    if standardise                                      # :127-131
+        y = (y .- mean(y)) ./ std(y)
+        Ks, pc1 = kstd_pc1(K; want_kstd = need_kstd, want_pc1 = need_pc1)
+        K = Ks
+    end
+    Prepared(dm, y, K, pc1, stats, genomes.entries[r], genomes.populations[r], loci, phenomes.traits[idx_trait])
+end
+
+function newfit(pr::Prepared)::Fit
+    n, l = length(pr.entries), length(pr.loci_alleles)
+    fit = Fit(n = n, l = l)                              # src/gwas.jl:133-140
+    fit.model = ""
+    fit.trait = pr.trait
+    fit.b_hat_labels = pr.loci_alleles
+    fit.entries = pr.entries
+    fit.populations = pr.populations
+    fit.metrics = Dict("" => 0.0)
+    fit
+end
+
+function gwasprep(;
+    genomes::Genomes, phenomes::Phenomes,
+    idx_entries::Union{Nothing,Vector{Int64}} = nothing, idx_loci_alleles::Union{Nothing,Vector{Int64}} = nothing,
+    idx_trait::Int64 = 1, GRM_type::String = "simple", standardise::Bool = true, verbose::Bool = false,
+)::Tuple{Matrix{Float64},Vector{Float64},Matrix{Float64},Fit}
+    pr = prepare(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type, standardise; need_kstd = true, need_pc1 = false)
+    G = Matrix{Float64}(undef, pr.dm.n, pr.dm.p)
+    check(ccall((:gbm_matrix_download, LIBGBM), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64), pr.dm.handle, 0, pr.dm.p, G, pr.dm.n))
+    G = G[:, pr.stats.idx_cols]
+    if standardise
+        G = (G .- pr.stats.mean[pr.stats.idx_cols]') ./ pr.stats.sd[pr.stats.idx_cols]'
+    end
+    fit = newfit(pr)
+    free!(pr.dm)
+    (G, pr.y, pr.K, fit)
+end
+
+function gwas(model_name::String, model::Cint, genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type)::Fit
+    pr = prepare(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type, true; need_kstd = false, need_pc1 = true)
+    if length(pr.entries) != length(pr.pc1)
+        free!(pr.dm)
+        throw(ArgumentError("The GRM is computed on all entries of `genomes` but some entries were dropped: PC1 and G have different numbers of rows."))
+    end
+    fit = newfit(pr)
+    fit.model = model_name                                # src/gwas.jl:231 / :354
+    res = scan(pr.dm, pr.y, pr.pc1, model)                # marker loop, src/gwas.jl:239-249 / :363-389
+    b = res.stat[pr.stats.idx_cols]
+    if model == GBM_MODEL_LMM
+        b[isnan.(b)] .= 0.0                               # failed fits leave 0.0 (src/gwas.jl:367-382)
+    end
+    fit.b_hat = b
+    free!(pr.dm)
+    if !checkdims(fit)                                    # src/gwas.jl:255-257 / :395-397
+        throw(ErrorException("Error performing GWAS using the " * GRM_type * " GRM."))
+    end
+    fit
+end
+
+gwasols(; genomes::Genomes, phenomes::Phenomes, idx_entries::Union{Nothing,Vector{Int64}} = nothing,
+    idx_loci_alleles::Union{Nothing,Vector{Int64}} = nothing, idx_trait::Int64 = 1, GRM_type::String = "simple",
+    verbose::Bool = false)::Fit = gwas("GWAS_OLS", GBM_MODEL_OLS, genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type)
+
+gwaslmm(; genomes::Genomes, phenomes::Phenomes, idx_entries::Union{Nothing,Vector{Int64}} = nothing,
+    idx_loci_alleles::Union{Nothing,Vector{Int64}} = nothing, idx_trait::Int64 = 1, GRM_type::String = "simple",
+    verbose::Bool = false)::Fit = gwas("GWAS_LMM", GBM_MODEL_LMM, genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type)
+
+# GRM entry points with the GenomicBreedingCore signatures (returning the bare matrix; wrap in
+# GenomicBreedingCore.GRM as needed)
+function grmsimple_b200(genomes::Genomes; idx_entries = nothing, idx_loci_alleles = nothing, verbose::Bool = false)
+    dm = upload(Matrix{Float64}(genomes.allele_frequencies), idx_entries, idx_loci_alleles)
+    K = grm(dm, GBM_GRM_SIMPLE, 2); free!(dm); K
+end
+function grmploidyaware_b200(genomes::Genomes; ploidy::Int64 = 2, idx_entries = nothing, idx_loci_alleles = nothing, verbose::Bool = false)
+    dm = upload(Matrix{Float64}(genomes.allele_frequencies), idx_entries, idx_loci_alleles)
+    K = grm(dm, GBM_GRM_PLOIDY_AWARE, ploidy); free!(dm); K
+end
+
+end # module

@@ -140,6 +140,18 @@ int gbm_scan(const gbm_matrix* m, const double* Y, int64_t T, int64_t ldy, const
              int64_t ldc, int model, int flags, double* beta, double* se, double* stat, double* neglog10p,
              double* mean, double* sd, uint8_t* keep);
 
+/* Reusable scan: side vectors (covariates orthonormalised, traits residualised) and
+ * scratch are prepared once; every gbm_scan_plan_run is then the two kernel launches of one
+ * pass over the resident matrix (streaming sums + finalisation).  Device output pointers are
+ * written by the kernels in place, host ones are copied out.  The matrix handle must outlive
+ * the plan.  gbm_scan == create + run + free. */
+typedef struct gbm_scan_plan gbm_scan_plan;
+int gbm_scan_plan_create(const gbm_matrix* m, const double* Y, int64_t T, int64_t ldy, const double* C, int64_t k,
+                         int64_t ldc, int model, int flags, gbm_scan_plan** plan);
+int gbm_scan_plan_run(gbm_scan_plan* plan, double* beta, double* se, double* stat, double* neglog10p, double* mean,
+                      double* sd, uint8_t* keep);
+int gbm_scan_plan_free(gbm_scan_plan* plan);
+
 /* One call from host memory to results (the end-to-end path): uploads A in column blocks
  * through pinned staging while the previous block is scanned. Same outputs as gbm_scan. */
 int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const double* Y, int64_t T, int64_t ldy,

@@ -1,0 +1,171 @@
+"""CPU suite, part 2: the C-ABI library loads and exports every symbol include/gbm_b200.h
+declares; the host-side mirror validates arguments like the reference; compute calls fail
+loudly (no fallback) when there is no GPU."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "gbm_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gbm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    import gbm_b200
+
+    path = gbm_b200.build()
+    assert os.path.exists(path)
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (gbm_[a-z0-9_]+)", out))
+    decl = declared_symbols()
+    assert len(decl) >= 20
+    assert set(decl) <= exported, sorted(set(decl) - exported)
+    # the ctypes harness binds exactly the header's symbols
+    assert sorted(gbm_b200._lib.SIGNATURES) == decl
+    lib = gbm_b200.load()
+    assert lib.gbm_abi_version() == 1
+
+
+def test_library_is_sm100a_with_tma_and_dmma():
+    import gbm_b200
+
+    sass = subprocess.run(["cuobjdump", "-sass", gbm_b200.build()], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert "UTMALDG" in sass and "DMMA" in sass and "SYNCS" in sass
+
+
+def _has_gpu():
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_compute_fails_loudly_without_gpu():
+    import gbm_b200
+
+    with pytest.raises(gbm_b200.CudaError):
+        gbm_b200.init(0)
+    A = np.asfortranarray(np.random.default_rng(0).random((10, 5)))
+    with pytest.raises(gbm_b200.CudaError):
+        gbm_b200.DeviceMatrix.upload(A)
+    g = gbm_b200.Genomes.from_matrix(A)
+    ph = gbm_b200.Phenomes.from_matrix(np.arange(10.0), entries=g.entries)
+    with pytest.raises(gbm_b200.CudaError):
+        gbm_b200.gwasols(genomes=g, phenomes=ph)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "genomicbreedingmodels.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "liboracle" not in txt, f
+
+
+def test_host_validation_mirrors_reference_errors():
+    """Errors of extractxyetc / gwasprep raised before any device work
+    (/root/reference/src/prediction.jl:67-127, /root/reference/src/gwas.jl:101-111)."""
+    import gbm_b200
+    from gbm_b200.gwas import _validate_and_select
+
+    rng = np.random.default_rng(1)
+    A = np.asfortranarray(rng.random((12, 7)))
+    y = rng.normal(size=12)
+    g = gbm_b200.Genomes.from_matrix(A)
+    ph = gbm_b200.Phenomes.from_matrix(y, entries=g.entries)
+    rows, cols, yy = _validate_and_select(g, ph, None, None, 1)
+    assert rows is None and cols is None and np.array_equal(yy, y)
+    # missing / NaN / Inf phenotypes are dropped (prediction.jl:116)
+    y2 = y.copy()
+    y2[[2, 5]] = np.nan
+    y2[7] = -np.inf
+    ph2 = gbm_b200.Phenomes.from_matrix(y2, entries=g.entries)
+    rows, _, yy = _validate_and_select(g, ph2, None, None, 1)
+    assert list(rows) == [1, 2, 4, 5, 7, 9, 10, 11, 12] and yy.size == 9
+    rows, _, _ = _validate_and_select(g, ph2, [12, 3, 1, 6], None, 1)
+    assert list(rows) == [12, 1]
+    bad = gbm_b200.Phenomes.from_matrix(y, entries=g.entries[::-1])
+    with pytest.raises(gbm_b200.ArgumentError, match="merged"):
+        _validate_and_select(g, bad, None, None, 1)
+    with pytest.raises(gbm_b200.ArgumentError, match="idx_entries"):
+        _validate_and_select(g, ph, [0, 3], None, 1)
+    with pytest.raises(gbm_b200.ArgumentError, match="idx_loci_alleles"):
+        _validate_and_select(g, ph, None, [1, 8], 1)
+    with pytest.raises(gbm_b200.ArgumentError, match="less than 2"):
+        _validate_and_select(g, gbm_b200.Phenomes.from_matrix(np.full(12, np.nan), entries=g.entries), None, None, 1)
+    with pytest.raises(gbm_b200.ErrorException, match="variance"):
+        _validate_and_select(g, gbm_b200.Phenomes.from_matrix(np.ones(12), entries=g.entries), None, None, 1)
+    corrupt = gbm_b200.Genomes.from_matrix(A)
+    corrupt.entries = corrupt.entries[:-1]
+    with pytest.raises(gbm_b200.ArgumentError, match="corrupted"):
+        _validate_and_select(corrupt, ph, None, None, 1)
+    # GRM_type is validated before the device is touched too (gwas.jl:101-107)
+    with pytest.raises((gbm_b200.ArgumentError, gbm_b200.CudaError)):
+        gbm_b200.gwasols(genomes=g, phenomes=ph, GRM_type="fancy")
+
+
+def test_extractxyetc_mirror_identity():
+    import gbm_b200
+
+    rng = np.random.default_rng(2)
+    A = np.asfortranarray(rng.random((9, 4)))
+    y = rng.normal(size=9)
+    g = gbm_b200.Genomes.from_matrix(A)
+    ph = gbm_b200.Phenomes.from_matrix(y, entries=g.entries)
+    X, yy, ent, pops, loci = gbm_b200.extractxyetc(g, ph)
+    assert np.array_equal(X, np.hstack([np.ones((9, 1)), A])) and np.array_equal(yy, y)  # prediction.jl:46-50
+    assert ent == g.entries and loci == g.loci_alleles and len(pops) == 9
+    f = gbm_b200.Fit.new(9, 4)
+    assert f.checkdims() and f.b_hat.shape == (4,) and np.all(f.b_hat == 0)
+
+
+def test_pvalue_device_functions_on_host():
+    """pvalue.cuh is __host__ __device__: compile it for the host and check the log-space
+    tails against the oracle (mpmath) -- the same code the finalisation kernel runs."""
+    import tempfile
+
+    from oracle import gwas_oracle as go
+
+    csrc = os.path.join(ROOT, "genomicbreedingmodels.jl_b200", "csrc")
+    src = r"""
+#include <cstdio>
+#include <cstdlib>
+#include "pvalue.cuh"
+int main(int argc, char** argv) {
+  double df = atof(argv[1]);
+  for (int i = 2; i < argc; ++i) {
+    double t = atof(argv[i]);
+    printf("%.17g %.17g\n", -gbm::log_sf_t(t, df) / log(10.0), -gbm::log_sf_normal(t) / log(10.0));
+  }
+  return 0;
+}
+"""
+    with tempfile.TemporaryDirectory() as td:
+        cu = os.path.join(td, "pv.cu")
+        open(cu, "w").write(src)
+        exe = os.path.join(td, "pv")
+        subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-ccbin", "/usr/bin/g++", "-O2", "-I", csrc, "-o", exe, cu])
+        t = [0.0, 0.1, 0.5, 1.0, 1.7, 1.75, 2.0, 3.0, 5.0, 8.3, 12.0, 19.9, 20.1, 37.0, 40.0, 100.0, 300.0]
+        for df in (1.0, 4.0, 99.0, 299.0, 9999.0, 19999.0):
+            out = subprocess.run([exe, repr(df)] + [repr(x) for x in t], capture_output=True, text=True, check=True)
+            got = np.array([[float(v) for v in line.split()] for line in out.stdout.strip().splitlines()])
+            want_t = go.neglog10_sf_t(t, df)
+            want_z = go.neglog10_sf_normal(t)
+            assert np.max(np.abs(got[:, 0] - want_t)) < 1e-6, (df, np.abs(got[:, 0] - want_t).max())
+            assert np.max(np.abs(got[:, 1] - want_z)) < 1e-6
+            ok = want_t < 300
+            assert np.max(np.abs(10.0 ** (want_t[ok] - got[ok, 0]) - 1.0)) < 1e-9, df

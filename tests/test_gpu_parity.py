@@ -324,3 +324,91 @@ def test_grm_sharded_accumulate_equals_single(gbm):
     gbm.grm_finalize(dK.data_ptr(), n, 1.0 / p)
     K2 = dK.cpu().numpy().reshape(n, n).T
     assert np.max(np.abs(K1 - K2)) < 1e-12 * np.abs(K1).max()
+
+
+# ---------------------------------------------------------------------------------------
+import glob
+import os
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_cuda_path_against_golden_fixtures(gbm, path):
+    """tests/golden/*.npz (made by tests/golden/make_golden.py from the oracle)."""
+    g = np.load(path)
+    A, y = g["A"], g["y"]
+    n, p = A.shape
+    ge = gbm.Genomes.from_matrix(A)
+    ph = gbm.Phenomes.from_matrix(y, entries=ge.entries)
+    for grm_type, tag in (("simple", "s"), ("ploidy-aware", "p")):
+        f1 = gbm.gwasols(genomes=ge, phenomes=ph, GRM_type=grm_type)
+        f2 = gbm.gwaslmm(genomes=ge, phenomes=ph, GRM_type=grm_type)
+        assert np.array_equal(f1.extras["idx_cols"], g[f"idx_cols_{tag}"])
+        assert rel_err(f1.b_hat, g[f"b_ols_{tag}"]) < RTOL
+        assert rel_err(f1.b_hat, g[f"b_ols_literal_{tag}"]) < 1e-8
+        assert rel_err(f2.b_hat, g[f"z_lmm_{tag}"]) < RTOL
+        assert rel_err(f1.extras["beta"], g[f"beta_{tag}"]) < RTOL
+        assert rel_err(f1.extras["se"], g[f"se_ols_{tag}"], floor=0) < RTOL
+        assert np.max(np.abs(f1.extras["neglog10p"] - g[f"nlp_t_{tag}"])) < 1e-6
+        assert np.max(np.abs(f2.extras["neglog10p"] - g[f"nlp_z_{tag}"])) < 1e-6
+        sgn = np.sign(f1.extras["pc1"] @ g[f"pc1_{tag}"])
+        assert np.max(np.abs(sgn * f1.extras["pc1"] - g[f"pc1_{tag}"])) < 1e-9
+    if "ploidy" in g:
+        assert f1.extras["ploidy"] == int(g["ploidy"])
+    G, ys, K, _ = gbm.gwasprep(genomes=ge, phenomes=ph, GRM_type="ploidy-aware")
+    np.testing.assert_allclose(K, g["K_p"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(ys, g["ys"], rtol=1e-13)
+    Ks = gbm.grmsimple(ge).genomic_relationship_matrix
+    Ku = gbm.grmsimple(ge, centre=False).genomic_relationship_matrix
+    Kp = gbm.grmploidyaware(ge, ploidy=4).genomic_relationship_matrix
+    for got, want in ((Ks, g["grm_simple"]), (Ku, g["grm_simple_uncentred"]), (Kp, g["grm_ploidy4"])):
+        assert np.max(np.abs(got - want)) < RTOL * np.abs(want).max()
+
+
+def test_scan_plan_reuse_and_device_outputs(gbm):
+    import torch
+
+    n, p = 1200, 2500
+    A, ys, pc = _problem(23, n, p, synth.KIND_DIPLOID)
+    dm = gbm.DeviceMatrix.upload(A)
+    ref = dm.scan(ys, pc[:, None], model=1)
+    plan = gbm.ScanPlan(dm, ys, pc[:, None], model=1)
+    stat_d = torch.full((p,), -7.0, dtype=torch.float64, device="cuda:0")
+    nlp_h = np.empty(p)
+    keep_d = torch.zeros(p, dtype=torch.uint8, device="cuda:0")
+    for _ in range(3):
+        tm = plan.run(stat=stat_d, neglog10p=nlp_h, keep=keep_d)
+        assert tm["launches"] == 2
+        assert np.array_equal(stat_d.cpu().numpy(), ref["stat"][:, 0], equal_nan=True)
+        assert np.array_equal(nlp_h, ref["neglog10p"][:, 0], equal_nan=True)
+        assert np.array_equal(keep_d.cpu().numpy().astype(bool), ref["keep"])
+    plan.free()
+    dm.free()
+
+
+def test_large_shape_properties(gbm):
+    """BASELINE-size rows (n = 10,000) on a column block: size-independent properties --
+    the generator block regenerated on the CPU bit-exactly, sampled columns against the
+    oracle, and linearity of the statistic's numerator in y."""
+    n, p, col0 = 10000, 4096, 777_000
+    dm = gbm.DeviceMatrix.generate(42, n, p, synth.KIND_DIPLOID, col0)
+    sample = [0, 1, 17, 1000, 4095]
+    for j in sample:
+        assert np.array_equal(dm.download(j, 1)[:, 0], synth.block(42, n, col0 + j, 1, synth.KIND_DIPLOID)[:, 0])
+    rng = np.random.default_rng(0)
+    y1, y2 = rng.normal(size=n), rng.normal(size=n)
+    pc = rng.normal(size=n)
+    r1 = dm.scan(y1, pc[:, None], model=0)
+    r2 = dm.scan(y2, pc[:, None], model=0)
+    r12 = dm.scan(y1 + 2.0 * y2, pc[:, None], model=0)
+    keep = r1["keep"]
+    # stat_ols = x'My / sqrt(x'Mx) is linear in y
+    lin = r1["stat"][keep, 0] + 2.0 * r2["stat"][keep, 0]
+    assert np.max(np.abs(r12["stat"][keep, 0] - lin)) < 1e-9 * np.abs(lin).max()
+    A = np.asfortranarray(np.hstack([synth.block(42, n, col0 + j, 1, synth.KIND_DIPLOID) for j in sample]))
+    pcn = pc - pc.mean()
+    ref = go.scan_closed_form(A, y1, pcn / np.linalg.norm(pcn))
+    ok = np.array([keep[j] for j in sample])
+    assert rel_err(r1["stat"][sample, 0][ok], ref["stat_ols"][ok]) < RTOL
+    dm.free()

@@ -1,0 +1,155 @@
+"""CPU suite, part 1: the oracle itself -- against the invariants the reference's doctests
+pin, against its own golden fixtures, and its routes against each other."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cbind, gwas_oracle as go, synth
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def _ent(n):
+    return [f"entry_{i + 1}" for i in range(n)]
+
+
+def test_golden_fixtures_exist():
+    assert len(GOLDEN) >= 3
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_oracle_reproduces_golden(path):
+    g = np.load(path)
+    A, y = g["A"], g["y"]
+    n, p = A.shape
+    assert np.array_equal(A, synth.block(int(g["seed"]), n, 0, p, int(g["kind"])))
+    for grm_type, tag in (("simple", "s"), ("ploidy-aware", "p")):
+        b, prep, pc = go.gwasols(A, _ent(n), y[:, None], _ent(n), GRM_type=grm_type)
+        z, _, _ = go.gwaslmm(A, _ent(n), y[:, None], _ent(n), GRM_type=grm_type)
+        assert np.array_equal(prep.idx_cols, g[f"idx_cols_{tag}"])
+        np.testing.assert_allclose(b, g[f"b_ols_literal_{tag}"], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(z, g[f"z_lmm_{tag}"], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(prep.K, g[f"K_{tag}"], rtol=1e-10, atol=1e-12)
+        sgn = np.sign(pc @ g[f"pc1_{tag}"])
+        np.testing.assert_allclose(sgn * pc, g[f"pc1_{tag}"], atol=1e-9)
+        # literal pinv route vs closed form
+        np.testing.assert_allclose(g[f"b_ols_literal_{tag}"], g[f"b_ols_{tag}"], rtol=1e-8, atol=1e-9)
+
+
+def test_gwasprep_doctest_invariants_on_oracle():
+    """/root/reference/src/gwas.jl:55-74."""
+    n, p = 100, 1200
+    A = synth.block(42, n, 0, p, synth.KIND_TETRAPLOID)
+    y = synth.phenotype(42, n, p, synth.KIND_TETRAPLOID)
+    prep = go.gwasprep(A, _ent(n), y[:, None], _ent(n))
+    assert np.all(np.abs(prep.G.mean(axis=0)) < 1e-10)
+    assert np.all(np.abs(prep.G.std(axis=0, ddof=1) - 1) < 1e-10)
+    assert abs(prep.y.mean()) < 1e-10 and abs(prep.y.std(ddof=1) - 1) < 1e-10
+    assert prep.G.shape[0] == prep.y.shape[0] and prep.K.shape == (n, n)
+    assert prep.idx_cols.size == prep.G.shape[1]
+    assert not np.allclose(prep.K, prep.K.T)  # standardised K is not symmetric
+
+
+def test_extractxyetc_identity_doctest():
+    """/root/reference/src/prediction.jl:46-50."""
+    n, p = 40, 60
+    A = synth.block(1, n, 0, p, synth.KIND_CONTINUOUS)
+    y = synth.phenotype(1, n, p, synth.KIND_CONTINUOUS)
+    X, yy, rows0, cols0 = go.extractxyetc(A, _ent(n), y[:, None], _ent(n))
+    assert np.array_equal(X, np.hstack([np.ones((n, 1)), A]))
+    assert np.array_equal(yy, y)
+
+
+def test_extractxyetc_filters_and_errors():
+    n, p = 30, 20
+    A = synth.block(2, n, 0, p, synth.KIND_DIPLOID)
+    y = synth.phenotype(2, n, p, synth.KIND_DIPLOID)
+    y[[3, 7]] = np.nan
+    y[9] = np.inf
+    X, yy, rows0, _ = go.extractxyetc(A, _ent(n), y[:, None], _ent(n), add_intercept=False)
+    assert X.shape == (n - 3, p) and not set(rows0) & {3, 7, 9}
+    with pytest.raises(go.ArgumentError):
+        go.extractxyetc(A, _ent(n), y[:, None], _ent(n)[::-1])
+    with pytest.raises(go.ArgumentError):
+        go.extractxyetc(A, _ent(n), y[:, None], _ent(n), idx_entries=[0, 1])
+    with pytest.raises(go.ArgumentError):
+        go.extractxyetc(A, _ent(n), y[:, None], _ent(n), idx_loci_alleles=[1, p + 1])
+    with pytest.raises(go.ArgumentError):
+        go.extractxyetc(A, _ent(n), np.full((n, 1), np.nan), _ent(n))
+    with pytest.raises(go.ErrorException):
+        go.extractxyetc(A, _ent(n), np.ones((n, 1)), _ent(n))
+    with pytest.raises(go.ArgumentError):
+        go.gwasprep(A, _ent(n), y[:, None], _ent(n), GRM_type="other")
+
+
+def test_lmm_reml_is_flat_in_theta_and_z_matches_closed_form():
+    """with (1|entries) and one observation per level the profiled
+    REML objective does not depend on theta and z equals the closed form."""
+    n, p = 60, 40
+    A = synth.block(5, n, 0, p, synth.KIND_CONTINUOUS)
+    y = synth.phenotype(5, n, p, synth.KIND_CONTINUOUS)
+    z, prep, pc = go.gwaslmm(A, _ent(n), y[:, None], _ent(n))
+    for j in (0, 5, 17):
+        X = np.stack([np.ones(n), pc, prep.G[:, j]], axis=1)
+        objs, zs = [], []
+        for th in (0.0, 0.1, 0.7, 1.0, 3.0):
+            o, _, zz = go.lmm_profiled_reml(prep.y, X, th)
+            objs.append(o)
+            zs.append(zz[-1])
+        assert np.ptp(objs) < 1e-8 * abs(objs[0])
+        np.testing.assert_allclose(zs, z[j], rtol=1e-10)
+
+
+@pytest.mark.parametrize("kind", [synth.KIND_DIPLOID, synth.KIND_TETRAPLOID])
+def test_c_twin_matches_numpy_oracle(kind):
+    n, p = 200, 1500
+    A = synth.block(42, n, 0, p, kind)
+    y = synth.phenotype(42, n, p, kind)
+    b, prep, pc = go.gwasols(A, _ent(n), y[:, None], _ent(n))
+    z, _, _ = go.gwaslmm(A, _ent(n), y[:, None], _ent(n))
+    so, sl, keep = cbind.gwasols_raw(A, prep.y, pc)
+    assert np.array_equal(np.flatnonzero(keep) + 1, prep.idx_cols)
+    np.testing.assert_allclose(so[keep], b, rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(sl[keep], z, rtol=1e-8, atol=1e-9)
+    mu, sd = cbind.colstats(A)
+    mu2, sd2 = go.column_std(A)
+    np.testing.assert_allclose(mu, mu2, rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(sd, sd2, rtol=1e-12, atol=1e-15)
+
+
+def test_ploidy_inference_and_grm_properties():
+    A = synth.block(8, 50, 0, 400, synth.KIND_TETRAPLOID)
+    mu, v = go.column_std(A)
+    G = A[:, v > go.EPS]
+    assert go.infer_ploidy(G) == 4  # gwas.jl:119
+    assert go.infer_ploidy(synth.block(8, 50, 0, 400, synth.KIND_DIPLOID)) == 2
+    K = go.grm_simple(A)
+    assert np.allclose(K, K.T) and np.allclose(K.sum(axis=0), 0, atol=1e-12)  # centred => rows sum to 0
+    Kp = go.grm_ploidy_aware(A, 4)
+    q = A.mean(axis=0)
+    np.testing.assert_allclose(Kp, 4 * K * A.shape[1] / np.sum(q * (1 - q)), rtol=1e-12)
+
+
+def test_pvalue_oracle_against_scipy():
+    from scipy import stats
+
+    t = np.array([0.0, 0.3, 1.0, 2.5, 5.0, 8.0])
+    for df in (5.0, 299.0, 9999.0):
+        np.testing.assert_allclose(go.neglog10_sf_t(t, df), -np.log10(stats.t.sf(t, df)), rtol=1e-10)
+    np.testing.assert_allclose(go.neglog10_sf_normal(t), -np.log10(stats.norm.sf(t)), rtol=1e-10)
+    # large-df quadrature route agrees with the beta route where both work
+    a = go.neglog10_sf_t([0.5, 4.0, 30.0], 20000.0)
+    b = go.neglog10_sf_t([0.5, 4.0, 30.0], 20000.0001)
+    np.testing.assert_allclose(a, b, rtol=1e-8)
+
+
+def test_synth_properties():
+    A = synth.block(42, 500, 0, 970, synth.KIND_DIPLOID)
+    assert set(np.unique(A)) <= {0.0, 0.5, 1.0}
+    _, v = go.column_std(A)
+    assert 3 <= (v <= go.EPS).sum() <= 30  # ~1 % fixed columns for the filter
+    # blocks are consistent whatever the chunking
+    B = np.hstack([synth.block(42, 500, 0, 400, 0), synth.block(42, 500, 400, 570, 0)])
+    assert np.array_equal(A, B)
