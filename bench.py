@@ -151,6 +151,7 @@ def cpu_sample_rate(n: int, p: int, markers: int, reps: int = 1):
     /root/reference/src/gwas.jl:112-115, :129, :241-245) on all host cores."""
     from oracle import cbind
 
+    cbind.use_all_cores()
     A = synth_block_chunked(n, markers)
     ys, pc = cpu_inputs(n, p)
     cbind.gwasols_raw(A[:, :64], ys, pc)  # warm-up (thread pool, page faults)
@@ -168,6 +169,7 @@ def run_reference(args):
         return 0
     from oracle import cbind
 
+    cbind.use_all_cores()
     n = args.n
     # bounded sample: ~1 s of CPU work per step, at most 2 GB of genotypes
     rate0, _, cores = cpu_sample_rate(n, args.p, 512)
@@ -202,6 +204,10 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    # NCCL / libraries may print banners on stdout; keep stdout for the one JSON line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -274,8 +280,15 @@ def main():
     peak, peak_src = measured_peaks()
     algo_bytes = 8.0 * n * p_loc  # 8n bytes per marker, each genotype read once
     achieved = algo_bytes / (main_avg_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "scan_traffic.json")
+    if os.path.exists(tpath):  # dram__bytes_read+write of this kernel from the committed ncu --set full capture
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get("n") == n:
+            traffic = tj["dram_bytes_per_marker"] * p_loc
     roofline = {"bound": "hbm", "kernel": "scan_sums_kernel<16,2>", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": main_avg_ms}
     keep_count = int(keep.sum().item())
 
@@ -317,6 +330,17 @@ def main():
                                          _lib.ptr(hkeep)))
 
         e2e_step()
+        # the link itself: plain pinned H2D copy of the same buffer (reference point for e2e)
+        dev = torch.empty((pe, n), dtype=torch.float64, device="cuda")
+        dev.copy_(host, non_blocking=True)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        dev.copy_(host, non_blocking=True)
+        ev1.record()
+        torch.cuda.synchronize()
+        h2d_peak = 8.0 * n * pe / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+        del dev
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
@@ -330,7 +354,8 @@ def main():
         line["e2e"] = {"value": pe * world * args.e2e_steps / dt, "unit": "markers/s",
                        "h2d_bytes_per_step": 8 * n * pe + 16 * n, "d2h_bytes_per_step": pe * (6 * 8 + 1),
                        "sample": f"{pe} host-resident (pinned) markers per GPU per step through gbm_scan_host",
-                       "h2d_gbps": 8.0 * n * pe * args.e2e_steps / dt / 1e9}
+                       "h2d_gbps": 8.0 * n * pe * args.e2e_steps / dt / 1e9, "h2d_link_gbps_plain_copy": h2d_peak,
+                       "bound": "PCIe host->device link: 8n bytes per marker must cross it"}
         del host
 
     plan.free()
@@ -368,7 +393,7 @@ def main():
     if rank == 0 and args.pipeline:
         line["pipeline"] = run_pipeline(gbm_b200, _lib, n, p_loc, j0, ys)
 
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:  # reported at N=1 only
         rate0, _, cores = cpu_sample_rate(n, p, 512)
         markers = args.cpu_markers or int(max(1024, min(40_000, rate0 * 12.0)))  # ~12 s, <= 3.2 GB of genotypes
         rate, secs, cores = cpu_sample_rate(n, p, markers)
@@ -377,8 +402,11 @@ def main():
                                           "the reference's per-marker loop (gwas.jl:112-115,:129,:241-245); the "
                                           "reference is Julia and cannot run in this image"}
 
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -391,6 +419,11 @@ def run_pipeline(gbm_b200, _lib, n, p_loc, j0, ys):
     import torch
 
     out = {}
+    # one-off library initialisation (cuSOLVER/cuBLAS handles, kernel images) on a toy problem
+    wm = gbm_b200.DeviceMatrix.generate(SEED, 256, 512, KIND_DIPLOID)
+    wK, _ = wm.grm(_lib.GRM_SIMPLE, 2, 0)
+    gbm_b200.kstd_pc1(wK, want_kstd=False)
+    wm.free()
     dm = gbm_b200.DeviceMatrix.generate(SEED, n, p_loc, KIND_DIPLOID, col0=j0)
     t0 = time.perf_counter()
     st = dm.colstats()

@@ -34,6 +34,9 @@ struct State {
   cudaStream_t copy_stream = nullptr;
   void* cusolver = nullptr;
   cudaEvent_t ev[8] = {};
+  void* stage_buf[2] = {nullptr, nullptr};  // cached H2D staging for gbm_scan_host
+  size_t stage_bytes = 0;
+  cudaEvent_t stage_copied[2] = {nullptr, nullptr}, stage_consumed[2] = {nullptr, nullptr};
   double h2d_ms = 0, kernel_ms = 0, main_ms = 0, d2h_ms = 0;
   int64_t launches = 0;
 };

@@ -344,6 +344,14 @@ int gbm_shutdown(void) {
     cusolverDnDestroy(reinterpret_cast<cusolverDnHandle_t>(st.cusolver));
     st.cusolver = nullptr;
   }
+  for (int b = 0; b < 2; ++b) {
+    if (st.stage_buf[b]) cudaFree(st.stage_buf[b]);
+    st.stage_buf[b] = nullptr;
+    if (st.stage_copied[b]) cudaEventDestroy(st.stage_copied[b]);
+    if (st.stage_consumed[b]) cudaEventDestroy(st.stage_consumed[b]);
+    st.stage_copied[b] = st.stage_consumed[b] = nullptr;
+  }
+  st.stage_bytes = 0;
   if (st.own_stream) cudaStreamDestroy(st.own_stream);
   if (st.copy_stream) cudaStreamDestroy(st.copy_stream);
   st.own_stream = st.copy_stream = st.stream = nullptr;
@@ -1014,14 +1022,26 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
   const int64_t ldd = round_up(n, 16);
   int64_t blk = std::max<int64_t>(16, ((int64_t(256) << 20) / (8 * ldd)) / 16 * 16);
   blk = std::min(blk, round_up(p, 16));
-  double* buf[2] = {nullptr, nullptr};
-  cudaEvent_t copied[2], consumed[2];
-  for (int b = 0; b < 2; ++b) {
-    GBM_CUDA(cudaMalloc(reinterpret_cast<void**>(&buf[b]), sizeof(double) * ldd * blk));
-    if (ldd != n) GBM_CUDA(cudaMemsetAsync(buf[b], 0, sizeof(double) * ldd * blk, st.copy_stream));
-    GBM_CUDA(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
-    GBM_CUDA(cudaEventCreateWithFlags(&consumed[b], cudaEventDisableTiming));
+  // staging buffers and events are cached across calls (cudaMalloc/cudaFree of 2 x 256 MB per
+  // call would cost milliseconds)
+  const size_t need = sizeof(double) * ldd * blk;
+  if (st.stage_bytes < need) {
+    for (int b = 0; b < 2; ++b) {
+      if (st.stage_buf[b]) cudaFree(st.stage_buf[b]);
+      st.stage_buf[b] = nullptr;
+      GBM_CUDA(cudaMalloc(&st.stage_buf[b], need));
+    }
+    st.stage_bytes = need;
   }
+  double* buf[2] = {static_cast<double*>(st.stage_buf[0]), static_cast<double*>(st.stage_buf[1])};
+  cudaEvent_t* copied = st.stage_copied;
+  cudaEvent_t* consumed = st.stage_consumed;
+  for (int b = 0; b < 2; ++b) {
+    if (!copied[b]) GBM_CUDA(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+    if (!consumed[b]) GBM_CUDA(cudaEventCreateWithFlags(&consumed[b], cudaEventDisableTiming));
+    if (ldd != n) GBM_CUDA(cudaMemsetAsync(buf[b], 0, need, st.copy_stream));
+  }
+  const bool contiguous = (lda == n && ldd == n);
   Span all(st.stream);
   all.start();
   GBM_CUDA(cudaEventRecord(consumed[0], st.stream));
@@ -1030,8 +1050,11 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
   for (int64_t j0 = 0; j0 < p; j0 += blk, b ^= 1) {
     const int64_t pc = std::min(blk, p - j0);
     GBM_CUDA(cudaStreamWaitEvent(st.copy_stream, consumed[b], 0));
-    GBM_CUDA(cudaMemcpy2DAsync(buf[b], ldd * sizeof(double), A + j0 * lda, lda * sizeof(double), n * sizeof(double),
-                               pc, cudaMemcpyDefault, st.copy_stream));
+    if (contiguous)
+      GBM_CUDA(cudaMemcpyAsync(buf[b], A + j0 * lda, sizeof(double) * n * pc, cudaMemcpyDefault, st.copy_stream));
+    else
+      GBM_CUDA(cudaMemcpy2DAsync(buf[b], ldd * sizeof(double), A + j0 * lda, lda * sizeof(double),
+                                 n * sizeof(double), pc, cudaMemcpyDefault, st.copy_stream));
     GBM_CUDA(cudaEventRecord(copied[b], st.copy_stream));
     GBM_CUDA(cudaStreamWaitEvent(st.stream, copied[b], 0));
     scan_block(buf[b], n, pc, ldd, passes, no_rec, sv.k_eff, model, flags, out.view(), p, j0, nullptr);
@@ -1042,11 +1065,6 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
   GBM_CUDA(cudaStreamSynchronize(st.stream));
   GBM_CUDA(cudaStreamSynchronize(st.copy_stream));
   st.kernel_ms = all.ms();  // copy + compute overlapped: wall time of the pipeline on the device
-  for (int i = 0; i < 2; ++i) {
-    cudaFree(buf[i]);
-    cudaEventDestroy(copied[i]);
-    cudaEventDestroy(consumed[i]);
-  }
   GBM_API_END
 }
 

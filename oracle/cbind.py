@@ -26,6 +26,7 @@ def lib():
         dp = ctypes.POINTER(ctypes.c_double)
         i64 = ctypes.c_int64
         L.oracle_num_threads.restype = ctypes.c_int
+        L.oracle_set_num_threads.argtypes = [ctypes.c_int]
         L.oracle_colstats.argtypes = [dp, i64, i64, i64, dp, dp]
         L.oracle_gwasols_raw.argtypes = [dp, i64, i64, i64, dp, dp, dp, dp, ctypes.POINTER(ctypes.c_uint8)]
         _LIB = L
@@ -34,6 +35,13 @@ def lib():
 
 def _dp(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def use_all_cores() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().oracle_set_num_threads(n)
+    return n
 
 
 def num_threads() -> int:
