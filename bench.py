@@ -55,6 +55,9 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-markers", type=int, default=0, help="markers in the CPU sample (0: sized for ~10-20 s)")
     ap.add_argument("--pipeline", action="store_true", help="also time the whole gwaslmm pipeline (GRM + PC1) once")
+    ap.add_argument("--lmm-markers", type=int, default=0,
+                    help="also run the GRM-covariance LMM engine (eigen-rotation GEMM + per-marker delta search) "
+                         "on this many markers")
     return ap.parse_args()
 
 
@@ -393,6 +396,9 @@ def main():
     if rank == 0 and args.pipeline:
         line["pipeline"] = run_pipeline(gbm_b200, _lib, n, p_loc, j0, ys)
 
+    if rank == 0 and args.lmm_markers > 0:
+        line["lmm_rotation_engine"] = run_lmm(gbm_b200, _lib, n, args.lmm_markers)
+
     if rank == 0 and world == 1 and not args.no_cpu:  # reported at N=1 only
         rate0, _, cores = cpu_sample_rate(n, p, 512)
         markers = args.cpu_markers or int(max(1024, min(40_000, rate0 * 12.0)))  # ~12 s, <= 3.2 GB of genotypes
@@ -446,6 +452,45 @@ def run_pipeline(gbm_b200, _lib, n, p_loc, j0, ys):
     tot = out["colstats_s"] + out["grm_s"] + out["kstd_pc1_s"] + out["scan_s"]
     out["total_s"] = tot
     out["markers_per_s_whole_gwaslmm"] = p_loc / tot
+    dm.free()
+    return out
+
+
+def run_lmm(gbm_b200, _lib, n, pm):
+    """GRM-covariance LMM engine (model of gwasreml): GRM on the sample, syevd (cuSOLVER, timed
+    separately), rotation U'A by the DMMA GEMM, per-marker REML delta search."""
+    import torch
+
+    out = {"n": n, "markers": pm}
+    dm = gbm_b200.DeviceMatrix.generate(SEED, n, pm, KIND_DIPLOID)
+    dK = torch.empty(n * n, dtype=torch.float64, device="cuda")
+    dm.grm(_lib.GRM_SIMPLE, 2, 0, out=dK)
+    # polygenic phenotype (h2 = 0.5) so that delta is interior: y = g + e with g ~ N(0, K)-like
+    rng = np.random.default_rng(3)
+    cols = rng.choice(pm, size=min(pm, 2000), replace=False)
+    g = np.zeros(n)
+    for j in cols:
+        c = dm.download(int(j), 1)[:, 0]
+        g += rng.normal() * (c - c.mean())
+    g /= g.std()
+    y = np.sqrt(0.5) * g + np.sqrt(0.5) * rng.normal(size=n)
+    t0 = time.perf_counter()
+    plan = gbm_b200.LmmPlan(dK, y)
+    out["plan_create_s"] = time.perf_counter() - t0
+    out["cusolver_syevd_s"] = plan.eig_ms * 1e-3
+    out["null_log_delta"] = plan.null_log_delta
+    plan.run(dm)  # warm-up
+    t0 = time.perf_counter()
+    res = plan.run(dm)
+    out["run_s"] = time.perf_counter() - t0
+    out["rotation_gemm_tflops"] = res["gemm_tflops"]
+    out["rotation_gemm_ms"] = res["timing"]["main_ms"]
+    out["delta_search_ms"] = res["search_ms"]
+    out["markers_per_s"] = pm / out["run_s"]
+    ld = res["log_delta"]
+    out["log_delta_range"] = [float(np.nanmin(ld)), float(np.nanmax(ld))]
+    out["max_neglog10p"] = float(np.nanmax(res["neglog10p"]))
+    plan.free()
     dm.free()
     return out
 

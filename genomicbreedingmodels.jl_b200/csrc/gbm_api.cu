@@ -1068,6 +1068,202 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
   GBM_API_END
 }
 
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------
+// GRM-covariance LMM scan (rotation + per-marker delta search)
+// ------------------------------------------------------------------------------------
+struct gbm_lmm_plan {
+  int64_t n = 0, ldu = 0;
+  int Q0 = 1;
+  double* dU = nullptr;   // eigenvectors, n x n (ldu)
+  double* dS = nullptr;   // eigenvalues ascending
+  double* dYr = nullptr;  // U'y
+  double* dCr = nullptr;  // U'[1, C], n x Q0 (ld n)
+  double lam0 = 0.0;
+};
+
+extern "C" {
+
+int gbm_lmm_plan_create(const double* K, int64_t n, const double* y, const double* C, int64_t k, int64_t ldc,
+                        gbm_lmm_plan** plan_out, double* eig_ms, double* null_log_delta) {
+  GBM_API_BEGIN
+  require_ready();
+  if (!K || !y || !plan_out || n < 4) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_lmm_plan_create: bad arguments");
+  if (k < 0 || k > 2 || (k > 0 && (!C || ldc < n)))
+    GBM_THROW(GBM_ERR_ARGUMENT, "gbm_lmm_plan_create: 0..2 covariates besides the intercept are supported");
+  if (n > 2147483647) GBM_THROW(GBM_ERR_ARGUMENT, "n too large for cuSOLVER");
+  State& st = state();
+  reset_timing();
+  std::unique_ptr<gbm_lmm_plan> pl(new gbm_lmm_plan);
+  pl->n = n;
+  pl->ldu = round_up(n, 16);
+  pl->Q0 = static_cast<int>(k) + 1;
+  const int Q0 = pl->Q0;
+  auto dalloc = [&](double** p, size_t count) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), sizeof(double) * count);
+    if (e != cudaSuccess) GBM_THROW(GBM_ERR_CUDA, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+  };
+  struct Guard {
+    gbm_lmm_plan* p;
+    ~Guard() {
+      if (p) {
+        cudaFree(p->dU); cudaFree(p->dS); cudaFree(p->dYr); cudaFree(p->dCr);
+      }
+    }
+  } guard{pl.get()};
+  dalloc(&pl->dU, static_cast<size_t>(pl->ldu) * n);
+  dalloc(&pl->dS, n);
+  dalloc(&pl->dYr, n);
+  dalloc(&pl->dCr, static_cast<size_t>(n) * Q0);
+  if (pl->ldu != n) GBM_CUDA(cudaMemsetAsync(pl->dU, 0, sizeof(double) * pl->ldu * n, st.stream));
+  GBM_CUDA(cudaMemcpy2DAsync(pl->dU, pl->ldu * sizeof(double), K, n * sizeof(double), n * sizeof(double), n,
+                             cudaMemcpyDefault, st.stream));
+  // K = U S U' through cuSOLVER (lower triangle), timed separately
+  if (!st.cusolver) {
+    cusolverDnHandle_t h;
+    if (cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS) GBM_THROW(GBM_ERR_CUDA, "cusolverDnCreate failed");
+    st.cusolver = h;
+  }
+  cusolverDnHandle_t h = reinterpret_cast<cusolverDnHandle_t>(st.cusolver);
+  if (cusolverDnSetStream(h, st.stream) != CUSOLVER_STATUS_SUCCESS) GBM_THROW(GBM_ERR_CUDA, "cusolverDnSetStream failed");
+  const int ni = static_cast<int>(n), ldi = static_cast<int>(pl->ldu);
+  int lwork = 0;
+  if (cusolverDnDsyevd_bufferSize(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, ni, pl->dU, ldi, pl->dS,
+                                  &lwork) != CUSOLVER_STATUS_SUCCESS)
+    GBM_THROW(GBM_ERR_CUDA, "cusolverDnDsyevd_bufferSize failed");
+  {
+    DevBuf<double> dwork(static_cast<size_t>(lwork), st.stream);
+    DevBuf<int> dinfo(1, st.stream);
+    Span eig(st.stream);
+    eig.start();
+    cusolverStatus_t cs = cusolverDnDsyevd(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, ni, pl->dU, ldi,
+                                           pl->dS, dwork.p, lwork, dinfo.p);
+    eig.stop();
+    if (cs != CUSOLVER_STATUS_SUCCESS) GBM_THROW(GBM_ERR_CUDA, "cusolverDnDsyevd failed, status " + std::to_string((int)cs));
+    int info = 0;
+    GBM_CUDA(cudaMemcpyAsync(&info, dinfo.p, sizeof(int), cudaMemcpyDeviceToHost, st.stream));
+    GBM_CUDA(cudaStreamSynchronize(st.stream));
+    if (info != 0) GBM_THROW(GBM_ERR_RUNTIME, "eigendecomposition of the GRM failed (syevd info " + std::to_string(info) + ")");
+    if (eig_ms) *eig_ms = eig.ms();
+  }
+  // rotate [1, C, y] with the DMMA GEMM
+  const int64_t ldb = round_up(n, 16);
+  std::vector<double> hB(static_cast<size_t>(ldb) * (Q0 + 1), 0.0);
+  for (int64_t i = 0; i < n; ++i) hB[i] = 1.0;
+  if (k > 0)
+    GBM_CUDA(cudaMemcpy2D(hB.data() + ldb, ldb * sizeof(double), C, ldc * sizeof(double), n * sizeof(double), k,
+                          cudaMemcpyDefault));
+  GBM_CUDA(cudaMemcpy(hB.data() + static_cast<size_t>(ldb) * Q0, y, n * sizeof(double), cudaMemcpyDefault));
+  {
+    DevBuf<double> dB(hB.size(), st.stream), dOut(static_cast<size_t>(n) * (Q0 + 1), st.stream);
+    GBM_CUDA(cudaMemcpyAsync(dB.p, hB.data(), sizeof(double) * hB.size(), cudaMemcpyHostToDevice, st.stream));
+    launch_gemm_tn(pl->dU, pl->ldu, dB.p, ldb, dOut.p, n, n, Q0 + 1, n, st.sm_count, st.stream);
+    GBM_CUDA(cudaMemcpyAsync(pl->dCr, dOut.p, sizeof(double) * n * Q0, cudaMemcpyDeviceToDevice, st.stream));
+    GBM_CUDA(cudaMemcpyAsync(pl->dYr, dOut.p + static_cast<size_t>(n) * Q0, sizeof(double) * n,
+                             cudaMemcpyDeviceToDevice, st.stream));
+    st.launches++;
+    GBM_CUDA(cudaStreamSynchronize(st.stream));
+  }
+  // null model on the host (n-vector work)
+  std::vector<double> hS(n), hY(n), hC(static_cast<size_t>(n) * Q0);
+  GBM_CUDA(cudaMemcpy(hS.data(), pl->dS, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  GBM_CUDA(cudaMemcpy(hY.data(), pl->dYr, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  GBM_CUDA(cudaMemcpy(hC.data(), pl->dCr, sizeof(double) * n * Q0, cudaMemcpyDeviceToHost));
+  pl->lam0 = lmm_null_lam0(Q0, hS.data(), hC.data(), n, hY.data(), n);
+  if (null_log_delta) *null_log_delta = pl->lam0;
+  guard.p = nullptr;
+  *plan_out = pl.release();
+  GBM_API_END
+}
+
+int gbm_lmm_plan_run(gbm_lmm_plan* pl, const gbm_matrix* m, int flags, double* beta, double* se, double* stat,
+                     double* neglog10p, double* log_delta, double* gemm_tflops, double* search_ms) {
+  GBM_API_BEGIN
+  require_ready();
+  if (!pl || !m) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_lmm_plan_run: null pointer");
+  if (m->n != pl->n) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_lmm_plan_run: the matrix and the GRM have different numbers of entries");
+  State& st = state();
+  reset_timing();
+  const int64_t n = pl->n, p = m->p;
+  // fixed-locus filter + column sd (beta / se are reported for the standardised column)
+  const int stride = scan_record_stride(0, true);
+  DevBuf<double> rec(static_cast<size_t>(p) * stride, st.stream), dsd(p, st.stream);
+  DevBuf<uint8_t> dkeep(p, st.stream);
+  launch_scan_sums(m->d, n, p, m->lda, nullptr, 0, 0, true, rec.p, st.sm_count, st.stream);
+  launch_colstats_finalize(rec.p, stride, n, p, nullptr, dsd.p, nullptr, dkeep.p, st.stream);
+  st.launches += 2;
+  OutTargets out(st.stream);
+  out.bind(0, beta, sizeof(double) * p);
+  out.bind(1, se, sizeof(double) * p);
+  out.bind(2, stat, sizeof(double) * p);
+  out.bind(3, neglog10p, sizeof(double) * p);
+  out.bind(4, log_delta, sizeof(double) * p);
+  const int64_t ldr = round_up(n, 16);
+  int64_t PB = std::max<int64_t>(128, ((int64_t(1) << 30) / (8 * ldr)) / 128 * 128);
+  PB = std::min<int64_t>(PB, round_up(p, 128));
+  DevBuf<double> dAr(static_cast<size_t>(ldr) * PB, st.stream);
+  double gemm_total = 0.0, search_total = 0.0;
+  std::vector<std::unique_ptr<Span>> gs, ss;
+  for (int64_t j0 = 0; j0 < p; j0 += PB) {
+    const int64_t pb = std::min(PB, p - j0);
+    gs.emplace_back(new Span(st.stream));
+    gs.back()->start();
+    launch_gemm_tn(pl->dU, pl->ldu, m->d + j0 * m->lda, m->lda, dAr.p, ldr, n, pb, n, st.sm_count, st.stream);
+    gs.back()->stop();
+    ss.emplace_back(new Span(st.stream));
+    ss.back()->start();
+    auto off = [&](int i) { return out.slot[i].dev ? static_cast<double*>(out.slot[i].dev) + j0 : nullptr; };
+    launch_lmm_delta(pl->Q0, dAr.p, n, pb, ldr, pl->dS, pl->dYr, pl->dCr, n, pl->lam0, dsd.p + j0, dkeep.p + j0,
+                     off(0), off(1), off(2), off(3), off(4), flags, st.sm_count, st.stream);
+    ss.back()->stop();
+    st.launches += 2;
+  }
+  const size_t sz = sizeof(double) * p;
+  for (int i = 0; i < 5; ++i)
+    if (out.slot[i].user && out.slot[i].dev != out.slot[i].user) copy_out(out.slot[i].user, out.slot[i].dev, sz, st.stream);
+  GBM_CUDA(cudaStreamSynchronize(st.stream));
+  for (auto& s : gs) gemm_total += s->ms();
+  for (auto& s : ss) search_total += s->ms();
+  st.main_ms = gemm_total;
+  st.kernel_ms = gemm_total + search_total;
+  if (gemm_tflops) *gemm_tflops = 2.0 * n * n * static_cast<double>(p) / (gemm_total * 1e-3) / 1e12;
+  if (search_ms) *search_ms = search_total;
+  GBM_API_END
+}
+
+int gbm_lmm_plan_free(gbm_lmm_plan* pl) {
+  GBM_API_BEGIN
+  if (pl) {
+    if (state().ready) cudaStreamSynchronize(state().stream);
+    cudaFree(pl->dU);
+    cudaFree(pl->dS);
+    cudaFree(pl->dYr);
+    cudaFree(pl->dCr);
+    delete pl;
+  }
+  GBM_API_END
+}
+
+/* plain C = A'B on the DMMA GEMM (device pointers), exposed for tests and for rotating extra vectors */
+int gbm_gemm_tn(const double* dA, int64_t lda, const double* dB, int64_t ldb, double* dC, int64_t ldc, int64_t M,
+                int64_t N, int64_t K, double* tflops) {
+  GBM_API_BEGIN
+  require_ready();
+  if (!dA || !dB || !dC || M < 1 || N < 1 || K < 1 || lda < K || ldb < K || ldc < M)
+    GBM_THROW(GBM_ERR_ARGUMENT, "gbm_gemm_tn: bad arguments");
+  if (!is_device_ptr(dA) || !is_device_ptr(dB) || !is_device_ptr(dC))
+    GBM_THROW(GBM_ERR_ARGUMENT, "gbm_gemm_tn: device pointers required");
+  State& st = state();
+  Span sp(st.stream);
+  sp.start();
+  launch_gemm_tn(dA, lda, dB, ldb, dC, ldc, M, N, K, st.sm_count, st.stream);
+  sp.stop();
+  GBM_CUDA(cudaStreamSynchronize(st.stream));
+  if (tflops) *tflops = 2.0 * M * static_cast<double>(N) * K / (sp.ms() * 1e-3) / 1e12;
+  GBM_API_END
+}
+
 int gbm_neglog10_sf(const double* stat, int64_t len, int dist, double df, double* out) {
   GBM_API_BEGIN
   require_ready();

@@ -66,4 +66,18 @@ void launch_row_centre(const double* Ks, double* Z, int64_t n, int64_t ld, cudaS
 void launch_gather(const double* src, int64_t lds, const int64_t* rows, int64_t n, const int64_t* cols, int64_t p,
                    double* dst, int64_t ldd, cudaStream_t stream);
 
+// gemm_tn.cu --------------------------------------------------------------------------
+// C (M x N, ldc) = A' B with A: K x M (lda), B: K x N (ldb), all column-major, device; lda, ldb even.
+void launch_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M,
+                    int64_t N, int64_t K, int sm_count, cudaStream_t stream);
+
+// lmm.cu ------------------------------------------------------------------------------
+// Per-marker REML delta search on a rotated block (one warp per marker). Q0 = fixed covariates incl. intercept.
+void launch_lmm_delta(int Q0, const double* Ar, int64_t n, int64_t pb, int64_t ld, const double* S, const double* Yr,
+                      const double* Cr, int64_t ldcr, double lam0, const double* col_sd, const uint8_t* keep,
+                      double* beta, double* se, double* stat, double* nlp, double* log_delta, int flags,
+                      int sm_count, cudaStream_t stream);
+// null-model log(delta) on the host from rotated vectors
+double lmm_null_lam0(int Q0, const double* S, const double* Cr, int64_t ldcr, const double* Yr, int64_t n);
+
 }  // namespace gbm

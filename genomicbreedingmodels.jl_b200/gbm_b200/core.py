@@ -175,6 +175,56 @@ class ScanPlan:
             pass
 
 
+class LmmPlan:
+    """GRM-covariance LMM scan (``gbm_lmm_plan``): eigendecomposition of the symmetric GRM,
+    rotation of y / covariates, null-model delta; run() rotates a resident DeviceMatrix in
+    column blocks (DMMA GEMM) and searches delta per marker.  Model of the reference's
+    gwasreml (/root/reference/src/gwas.jl:549-613), see oracle/lmm_oracle.py for the definition."""
+
+    def __init__(self, K, y, C=None):
+        n = int(np.asarray(y).shape[0])
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        Cm = None if C is None else _f64(np.asarray(C, dtype=np.float64).reshape(n, -1))
+        if isinstance(K, np.ndarray):
+            K = _f64(K)
+            if K.shape != (n, n):
+                raise _lib.ArgumentError("GRM must be n x n")
+        h = c_void_p()
+        eig, lam0 = c_double(), c_double()
+        check(_lib.lib().gbm_lmm_plan_create(ptr(K), n, ptr(y), ptr(Cm), 0 if Cm is None else Cm.shape[1], n, byref(h),
+                                             byref(eig), byref(lam0)))
+        self._h, self.n = h, n
+        self.eig_ms, self.null_log_delta = eig.value, lam0.value
+
+    def run(self, dm: DeviceMatrix, flags: int = 0):
+        p = dm.p
+        out = {k: np.empty(p) for k in ("beta", "se", "stat", "neglog10p", "log_delta")}
+        tf, sms = c_double(), c_double()
+        check(_lib.load().gbm_lmm_plan_run(self._h, dm._h, flags, ptr(out["beta"]), ptr(out["se"]), ptr(out["stat"]),
+                                           ptr(out["neglog10p"]), ptr(out["log_delta"]), byref(tf), byref(sms)))
+        out["gemm_tflops"], out["search_ms"] = tf.value, sms.value
+        out["timing"] = _lib.last_timing()
+        return out
+
+    def free(self):
+        if self._h is not None:
+            check(_lib.load().gbm_lmm_plan_free(self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def gemm_tn(dA_ptr: int, lda: int, dB_ptr: int, ldb: int, dC_ptr: int, ldc: int, M: int, N: int, K: int) -> float:
+    """C = A'B on the DMMA rotation GEMM (device pointers); returns TFLOP/s."""
+    tf = c_double()
+    check(_lib.lib().gbm_gemm_tn(c_void_p(dA_ptr), lda, c_void_p(dB_ptr), ldb, c_void_p(dC_ptr), ldc, M, N, K, byref(tf)))
+    return tf.value
+
+
 def grm_finalize(dK_ptr: int, n: int, scale: float):
     check(_lib.lib().gbm_grm_finalize(c_void_p(dK_ptr), n, scale))
 

@@ -18,7 +18,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import ArgumentError, ErrorException
-from .core import DeviceMatrix, kstd_pc1
+from .core import DeviceMatrix, LmmPlan, kstd_pc1
 from .structs import GRM, Fit, Genomes, Phenomes
 
 GRM_TYPES = ("simple", "ploidy-aware")
@@ -272,3 +272,43 @@ def gwaslmm(*, genomes: Genomes, phenomes: Phenomes, idx_entries=None, idx_loci_
     y ~ 1 + PC1 + x + (1|entries) fitted by REML (closed form)."""
     return _gwas("GWAS_LMM", _lib.MODEL_LMM, genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type,
                  verbose)
+
+
+def gwasreml(*, genomes: Genomes, phenomes: Phenomes, idx_entries=None, idx_loci_alleles=None, idx_trait: int = 1,
+             GRM_type: str = "simple", verbose: bool = False) -> Fit:
+    """gwasreml (/root/reference/src/gwas.jl:549-613): per-marker LMM with the GRM as the
+    covariance of the random genotype effect, variance components re-estimated for every
+    marker, fit.b_hat[j] = b[end]/sqrt(inv(X'V^-1 X)[end]) with X = [1, g_j] (:586, :596-599).
+
+    Engine: eigen-rotation (cuSOLVER + FP64 DMMA GEMM) and a per-marker REML delta search on
+    the device.  Differences from the reference's code, by design (oracle/lmm_oracle.py):
+    the symmetric un-standardised GRM is the covariance (the reference passes the
+    column-standardised, non-symmetric K of gwas.jl:130) and the objective is the standard
+    REML log-likelihood (the reference's `0.5 log det V + y'Py + log det X'V^-1X`, :478, is
+    minimised by L-BFGS to g_tol 1e-4).  PARITY UNPINNED."""
+    pr = _prepare(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type, False, need_kstd=False,
+                  need_pc1=False)  # gwas.jl:564-573 (K stays symmetric: standardise=False)
+    try:
+        if len(pr.entries) != pr.K.shape[0]:
+            raise ArgumentError(
+                "The GRM is computed on all entries of `genomes` (gwas.jl:120,:124) but some entries were dropped: "
+                "y and the GRM have different sizes.")
+        fit = _new_fit(pr)
+        fit.model = "GWAS_REML"  # :574
+        y = (pr.y - pr.y.mean()) / np.std(pr.y, ddof=1)  # :128 (z is invariant to it)
+        plan = LmmPlan(pr.K, y)
+        try:
+            res = plan.run(pr.dm)
+        finally:
+            plan.free()
+        sel = pr.idx_cols - 1
+        fit.b_hat = np.ascontiguousarray(res["stat"][sel])
+        fit.extras = {"beta": res["beta"][sel], "se": res["se"][sel], "neglog10p": res["neglog10p"][sel],
+                      "log_delta": res["log_delta"][sel], "null_log_delta": plan.null_log_delta,
+                      "idx_cols": pr.idx_cols, "eig_ms": plan.eig_ms, "gemm_tflops": res["gemm_tflops"],
+                      "search_ms": res["search_ms"], "ploidy": pr.ploidy}
+        if not fit.checkdims():  # :609-611
+            raise ErrorException("Error performing GWAS via REML using the " + GRM_type + " GRM.")
+        return fit
+    finally:
+        pr.dm.free()

@@ -158,6 +158,29 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
                   const double* C, int64_t k, int64_t ldc, int model, int flags, double* beta, double* se,
                   double* stat, double* neglog10p, double* mean, double* sd, uint8_t* keep);
 
+/* ---- GRM-covariance LMM scan: the model of gwasreml / loglikreml ----------------------
+ * (/root/reference/src/gwas.jl:450-483, :549-613: V = s2u*GRM + s2e*I, variance components
+ * re-estimated for every marker, statistic b[end]/sqrt(inv(X'V^-1 X)[end]); restated as the
+ * standard REML on the SYMMETRIC GRM -- oracle/lmm_oracle.py lists the differences.)
+ * create: K = U S U' (cuSOLVER syevd, eig_ms), rotation of [1, C, y] by the DMMA GEMM,
+ *         null-model log(delta) (returned in *null_log_delta).  K: n x n, host or device,
+ *         lower triangle used; y: n; C: n x k, k <= 2 extra covariates (intercept implied).
+ * run   : for the resident matrix m (n rows): U'A in column blocks by the FP64 DMMA GEMM,
+ *         then one warp per marker searches delta = s2e/s2g (bracket marched from the null
+ *         estimate, safeguarded Newton on dLL/dlog(delta)), and emits beta, se (of the
+ *         standardised column), z, -log10 P(N(0,1) > |z|) and log(delta).  Outputs length p,
+ *         host or device, nullable.  gemm_tflops: 2 n^2 p / DMMA GEMM time. */
+typedef struct gbm_lmm_plan gbm_lmm_plan;
+int gbm_lmm_plan_create(const double* K, int64_t n, const double* y, const double* C, int64_t k, int64_t ldc,
+                        gbm_lmm_plan** plan, double* eig_ms, double* null_log_delta);
+int gbm_lmm_plan_run(gbm_lmm_plan* plan, const gbm_matrix* m, int flags, double* beta, double* se, double* stat,
+                     double* neglog10p, double* log_delta, double* gemm_tflops, double* search_ms);
+int gbm_lmm_plan_free(gbm_lmm_plan* plan);
+/* C (M x N, ldc) = A' B, A: K x M (lda), B: K x N (ldb); column-major DEVICE buffers, lda and
+ * ldb even, 16-byte aligned.  The rotation GEMM on its own. */
+int gbm_gemm_tn(const double* dA, int64_t lda, const double* dB, int64_t ldb, double* dC, int64_t ldc, int64_t M,
+                int64_t N, int64_t K, double* tflops);
+
 /* -log10 upper-tail probabilities on the device (log-space; finite where 1 - cdf saturates) */
 int gbm_neglog10_sf(const double* stat, int64_t len, int dist /*0: TDist(df), 1: Normal*/, double df, double* out);
 
