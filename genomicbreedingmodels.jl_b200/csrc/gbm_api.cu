@@ -669,7 +669,7 @@ static void grm_accumulate_impl(const gbm_matrix* m, int centre, double* dK, dou
   }
   if (!centre) GBM_CUDA(cudaMemsetAsync(dmu.p, 0, sizeof(double) * ppad, st.stream));
   mainsp.start();
-  launch_grm_accumulate(m->d, m->n, m->p, m->lda, dmu.p, dK, st.sm_count, st.stream);
+  launch_grm_accumulate(m->d, m->n, m->p, m->lda, dmu.p, dK, st.sm_count, st.stream, centre != 0);
   mainsp.stop();
   all.stop();
   st.launches++;
@@ -797,7 +797,7 @@ int gbm_kstd_pc1(const double* K, int64_t n, double* Kstd, double* pc1, double* 
     const int64_t npad = round_up(n, 16);
     DevBuf<double> dzero(npad, st.stream);
     GBM_CUDA(cudaMemsetAsync(dzero.p, 0, sizeof(double) * npad, st.stream));
-    launch_grm_accumulate(dZ.p, n, n, ld, dzero.p, dB.p, st.sm_count, st.stream);
+    launch_grm_accumulate(dZ.p, n, n, ld, dzero.p, dB.p, st.sm_count, st.stream, false);
     launch_grm_finalize(dB.p, n, 1.0, st.stream);
     st.launches += 3;
     // largest eigenpair of B through cuSOLVER (timed separately, as BASELINE.json asks)

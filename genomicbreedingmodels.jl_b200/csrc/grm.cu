@@ -123,10 +123,14 @@ __global__ void __launch_bounds__(kGrmThreads, 1)
       const double* pb = sJ + t * kTilePad + wn * 32 + g;
 #pragma unroll
       for (int kk = 0; kk < kKT / 4; ++kk) {
+        // Only the column-block operand is centred: sum_j a_ij (a_i'j - mu_j) = Kc[i,i'] + w_i'
+        // with w = (A - 1 mu')mu, removed by grm_wcorrect_kernel.  w has the magnitude of the
+        // centred entries themselves, so nothing cancels (unlike A A' - ...), and the MMA loop
+        // carries 4 DADD instead of 12 per 32 DMMA.
         const double mu = sMu[kk * 4 + t];
         double a[8], b[4];
 #pragma unroll
-        for (int mt = 0; mt < 8; ++mt) a[mt] = pa[kk * 4 * kTilePad + mt * 8] - mu;
+        for (int mt = 0; mt < 8; ++mt) a[mt] = pa[kk * 4 * kTilePad + mt * 8];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) b[nt] = pb[kk * 4 * kTilePad + nt * 8] - mu;
 #pragma unroll
@@ -167,8 +171,78 @@ __global__ void __launch_bounds__(kGrmThreads, 1)
   }
 }
 
+// w_partial[slab][i] = sum_{j in slab} (a_ij - mu_j) mu_j : thread = row (coalesced down the
+// column), the slab's means staged in shared memory.
+constexpr int kWSlab = 1024;
+__global__ void __launch_bounds__(256)
+    grm_wpartial_kernel(const double* __restrict__ A, int64_t n, int64_t p, int64_t lda,
+                        const double* __restrict__ mu, double* __restrict__ wpart) {
+  __shared__ double smu[kWSlab];
+  const int64_t j0 = static_cast<int64_t>(blockIdx.y) * kWSlab;
+  const int cnt = static_cast<int>((p - j0) < kWSlab ? (p - j0) : kWSlab);
+  for (int c = threadIdx.x; c < cnt; c += blockDim.x) smu[c] = mu[j0 + c];
+  __syncthreads();
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* col = A + j0 * lda + i;
+  double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+  int c = 0;
+  for (; c + 3 < cnt; c += 4) {
+    acc0 = fma(col[(c + 0) * lda] - smu[c + 0], smu[c + 0], acc0);
+    acc1 = fma(col[(c + 1) * lda] - smu[c + 1], smu[c + 1], acc1);
+    acc2 = fma(col[(c + 2) * lda] - smu[c + 2], smu[c + 2], acc2);
+    acc3 = fma(col[(c + 3) * lda] - smu[c + 3], smu[c + 3], acc3);
+  }
+  for (; c < cnt; ++c) acc0 = fma(col[c * lda] - smu[c], smu[c], acc0);
+  wpart[static_cast<int64_t>(blockIdx.y) * n + i] = (acc0 + acc1) + (acc2 + acc3);
+}
+
+// w[i] = sum over slabs in a fixed order (deterministic)
+__global__ void __launch_bounds__(256)
+    grm_wreduce_kernel(const double* __restrict__ wpart, int64_t n, int slabs, double* __restrict__ w) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int b = 0; b < slabs; ++b) s += wpart[static_cast<int64_t>(b) * n + i];
+  w[i] = s;
+}
+
+// dK[i, i'] -= w[i'] on the lower triangle (i >= i')
+__global__ void __launch_bounds__(256)
+    grm_wcorrect_kernel(double* __restrict__ K, int64_t ld, int64_t rows, const double* __restrict__ w) {
+  // K points at the diagonal element of the first column handled by this launch
+  const int64_t col = blockIdx.y;
+  const double wc = w[col];
+  for (int64_t i = col + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < rows;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    K[col * ld + i] -= wc;
+}
+
+static void launch_grm_wcorrection(const double* A, int64_t n, int64_t p, int64_t lda, const double* mu, double* dK,
+                                   cudaStream_t stream) {
+  const int slabs = static_cast<int>((p + kWSlab - 1) / kWSlab);
+  double *wpart = nullptr, *w = nullptr;
+  GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&wpart), sizeof(double) * n * slabs, stream));
+  GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&w), sizeof(double) * n, stream));
+  const unsigned gx = static_cast<unsigned>((n + 255) / 256);
+  for (int s0 = 0; s0 < slabs; s0 += 65535) {
+    const int sc = slabs - s0 < 65535 ? slabs - s0 : 65535;
+    grm_wpartial_kernel<<<dim3(gx, static_cast<unsigned>(sc)), 256, 0, stream>>>(
+        A + static_cast<int64_t>(s0) * kWSlab * lda, n, p - static_cast<int64_t>(s0) * kWSlab, lda,
+        mu + static_cast<int64_t>(s0) * kWSlab, wpart + static_cast<int64_t>(s0) * n);
+  }
+  grm_wreduce_kernel<<<gx, 256, 0, stream>>>(wpart, n, slabs, w);
+  for (int64_t c0 = 0; c0 < n; c0 += 65535) {
+    const unsigned gy = static_cast<unsigned>(n - c0 < 65535 ? n - c0 : 65535);
+    grm_wcorrect_kernel<<<dim3(4, gy), 256, 0, stream>>>(dK + c0 * n + c0, n, n - c0, w + c0);
+  }
+  GBM_CUDA(cudaGetLastError());
+  GBM_CUDA(cudaFreeAsync(wpart, stream));
+  GBM_CUDA(cudaFreeAsync(w, stream));
+}
+
 void launch_grm_accumulate(const double* A, int64_t n, int64_t p, int64_t lda, const double* mu, double* dK,
-                           int sm_count, cudaStream_t stream) {
+                           int sm_count, cudaStream_t stream, bool centred) {
   if (n <= 0 || p <= 0) return;
   const int nb = static_cast<int>((n + kTile - 1) / kTile);
   const int num_tiles = nb * (nb + 1) / 2;
@@ -219,6 +293,7 @@ void launch_grm_accumulate(const double* A, int64_t n, int64_t p, int64_t lda, c
   const int grid = static_cast<int>(items < sm_count ? items : sm_count);
   grm_dmma_kernel<<<grid, kGrmThreads, kGrmSmemBytes, stream>>>(tmA, prm);
   GBM_CUDA(cudaGetLastError());
+  if (centred) launch_grm_wcorrection(A, n, p, lda, mu, dK, stream);
   GBM_CUDA(cudaFreeAsync(d_ij, stream));
   GBM_CUDA(cudaStreamSynchronize(stream));  // h_ij must outlive the async copy
   GBM_CUDA(cudaFreeHost(h_ij));

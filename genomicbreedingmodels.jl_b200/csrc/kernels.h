@@ -50,8 +50,9 @@ void launch_neglog10_sf(const double* stat, int64_t len, int dist, double df, do
 // grm.cu -------------------------------------------------------------------------------
 // dK (n x n col-major, ld n) += lower-triangle tiles of sum_j (a_j - mu_j)(a_j - mu_j)'.
 // mu: device, length >= round_up(p, 16), zero padded (all zeros = uncentred).
+// centred = false: mu must be all zeros and no correction pass is run.
 void launch_grm_accumulate(const double* A, int64_t n, int64_t p, int64_t lda, const double* mu, double* dK,
-                           int sm_count, cudaStream_t stream);
+                           int sm_count, cudaStream_t stream, bool centred);
 // scale the lower triangle and mirror it into the upper one
 void launch_grm_finalize(double* dK, int64_t n, double scale, cudaStream_t stream);
 // out[0] += sum_j mu_j (1 - mu_j)

@@ -14,7 +14,7 @@ module GenomicBreedingModelsB200
 using GenomicBreedingCore
 using Statistics
 
-export gwasprep, gwasols, gwaslmm, grmsimple_b200, grmploidyaware_b200
+export gwasprep, gwasols, gwaslmm, gwasreml, grmsimple_b200, grmploidyaware_b200
 
 const LIBGBM = get(ENV, "GBM_B200_LIB", joinpath(@__DIR__, "..", "libgbm_b200.so"))
 
@@ -247,6 +247,40 @@ gwasols(; genomes::Genomes, phenomes::Phenomes, idx_entries::Union{Nothing,Vecto
 gwaslmm(; genomes::Genomes, phenomes::Phenomes, idx_entries::Union{Nothing,Vector{Int64}} = nothing,
     idx_loci_alleles::Union{Nothing,Vector{Int64}} = nothing, idx_trait::Int64 = 1, GRM_type::String = "simple",
     verbose::Bool = false)::Fit = gwas("GWAS_LMM", GBM_MODEL_LMM, genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type)
+
+# gwasreml (src/gwas.jl:549-613): GRM-covariance LMM, variance components re-estimated per marker.
+# Engine: K = U S U' (cuSOLVER), U'A by the FP64 DMMA GEMM, per-marker REML delta search on the
+# device.  Uses the symmetric un-standardised GRM and the standard REML likelihood (the reference
+# passes the column-standardised K and minimises a non-standard objective; see oracle/lmm_oracle.py).
+function gwasreml(; genomes::Genomes, phenomes::Phenomes, idx_entries::Union{Nothing,Vector{Int64}} = nothing,
+    idx_loci_alleles::Union{Nothing,Vector{Int64}} = nothing, idx_trait::Int64 = 1, GRM_type::String = "simple",
+    verbose::Bool = false)::Fit
+    pr = prepare(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type, false; need_kstd = false, need_pc1 = false)
+    if length(pr.entries) != size(pr.K, 1)
+        free!(pr.dm)
+        throw(ArgumentError("The GRM is computed on all entries of `genomes` but some entries were dropped: y and the GRM have different sizes."))
+    end
+    fit = newfit(pr)
+    fit.model = "GWAS_REML"                               # src/gwas.jl:574
+    y = (pr.y .- mean(pr.y)) ./ std(pr.y)
+    plan = Ref{Ptr{Cvoid}}(C_NULL); eig_ms = Ref{Float64}(0.0); lam0 = Ref{Float64}(0.0)
+    check(ccall((:gbm_lmm_plan_create, LIBGBM), Cint,
+                (Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Ref{Ptr{Cvoid}}, Ref{Float64}, Ref{Float64}),
+                pr.K, pr.dm.n, y, C_NULL, 0, pr.dm.n, plan, eig_ms, lam0))
+    stat = Vector{Float64}(undef, pr.dm.p)
+    tf = Ref{Float64}(0.0); sms = Ref{Float64}(0.0)
+    rc = ccall((:gbm_lmm_plan_run, LIBGBM), Cint,
+               (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ref{Float64}),
+               plan[], pr.dm.handle, 0, C_NULL, C_NULL, stat, C_NULL, C_NULL, tf, sms)
+    ccall((:gbm_lmm_plan_free, LIBGBM), Cint, (Ptr{Cvoid},), plan[])
+    free!(pr.dm)
+    check(rc)
+    fit.b_hat = stat[pr.stats.idx_cols]                   # src/gwas.jl:599
+    if !checkdims(fit)                                    # src/gwas.jl:609-611
+        throw(ErrorException("Error performing GWAS via REML using the " * GRM_type * " GRM."))
+    end
+    fit
+end
 
 # GRM entry points with the GenomicBreedingCore signatures (returning the bare matrix; wrap in
 # GenomicBreedingCore.GRM as needed)
