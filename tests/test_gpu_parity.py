@@ -412,3 +412,55 @@ def test_large_shape_properties(gbm):
     ok = np.array([keep[j] for j in sample])
     assert rel_err(r1["stat"][sample, 0][ok], ref["stat_ols"][ok]) < RTOL
     dm.free()
+
+
+def test_c_abi_error_codes(gbm):
+    """The C ABI reports argument errors as GBM_ERR_ARGUMENT (-> Julia ArgumentError) with a
+    message, never crashes, and stays usable afterwards."""
+    from ctypes import byref, c_double, c_int64, c_void_p
+
+    from gbm_b200 import _lib
+
+    lib = _lib.load()
+    h = c_void_p()
+    A = np.asfortranarray(np.random.default_rng(0).random((10, 4)))
+    assert lib.gbm_matrix_upload(None, 10, 4, 10, byref(h)) == _lib.GBM_ERR_ARGUMENT
+    assert lib.gbm_matrix_upload(_lib.ptr(A), 1, 4, 10, byref(h)) == _lib.GBM_ERR_ARGUMENT      # < 2 entries
+    assert lib.gbm_matrix_upload(_lib.ptr(A), 10, 4, 5, byref(h)) == _lib.GBM_ERR_ARGUMENT      # lda < n
+    assert b"leading dimension" in lib.gbm_last_error()
+    assert lib.gbm_matrix_upload(_lib.ptr(A), 10, 4, 10, byref(h)) == _lib.GBM_OK
+    K = np.empty((10, 10), order="F")
+    tf = c_double()
+    assert lib.gbm_grm(h, 7, 2, 0, _lib.ptr(K), byref(tf)) == _lib.GBM_ERR_ARGUMENT             # GRM_type (gwas.jl:101-107)
+    assert b"GRM_type" in lib.gbm_last_error()
+    assert lib.gbm_grm(h, 1, 0, 0, _lib.ptr(K), byref(tf)) == _lib.GBM_ERR_ARGUMENT             # ploidy
+    y = np.ones(10)
+    stat = np.empty(4)
+    args = (None,) * 2 + (_lib.ptr(stat),) + (None,) * 4
+    assert lib.gbm_scan(h, _lib.ptr(y), 1, 10, None, 0, 10, 0, 0, *args) == _lib.GBM_ERR_ARGUMENT  # no trait variance
+    assert b"variance" in lib.gbm_last_error()
+    assert lib.gbm_scan(h, _lib.ptr(y), 0, 10, None, 0, 10, 0, 0, *args) == _lib.GBM_ERR_ARGUMENT
+    assert lib.gbm_scan(h, _lib.ptr(y), 1, 10, None, 0, 10, 9, 0, *args) == _lib.GBM_ERR_ARGUMENT  # model
+    y = np.arange(10.0)
+    assert lib.gbm_scan(h, _lib.ptr(y), 1, 10, None, 0, 10, 0, 0, *args) == _lib.GBM_OK
+    assert np.all(np.isfinite(stat))
+    idx = np.array([1, 2, 99], dtype=np.int64)
+    h2 = c_void_p()
+    assert lib.gbm_matrix_upload_indexed(_lib.ptr(A), 10, 4, 10, None, 10, _lib.ptr(idx), 3, byref(h2)) == _lib.GBM_ERR_ARGUMENT
+    assert b"idx_loci_alleles" in lib.gbm_last_error()
+    n, p, lda, d = c_int64(), c_int64(), c_int64(), c_void_p()
+    assert lib.gbm_matrix_info(h, byref(n), byref(p), byref(lda), byref(d)) == 0 and (n.value, p.value) == (10, 4)
+    assert lda.value % 16 == 0
+    assert lib.gbm_matrix_free(h) == _lib.GBM_OK
+
+
+def test_config4_tetraploid_pipeline_reduced(gbm):
+    """BASELINE configs[3] shape (grmploidyaware + gwaslmm on tetraploid frequencies), n = 2,000,
+    p reduced to what the oracle finishes in seconds; ploidy inference must return 4."""
+    n, p = 2000, 3000
+    A, y, g, ph = _structs(gbm, n, p, synth.KIND_TETRAPLOID, seed=4)
+    f = gbm.gwaslmm(genomes=g, phenomes=ph, GRM_type="ploidy-aware")
+    z_ref, prep, _ = go.gwaslmm(A, g.entries, y[:, None], ph.entries, GRM_type="ploidy-aware")
+    assert f.extras["ploidy"] == 4 == prep.ploidy
+    assert np.array_equal(f.extras["idx_cols"], prep.idx_cols)
+    assert rel_err(f.b_hat, z_ref) < RTOL
