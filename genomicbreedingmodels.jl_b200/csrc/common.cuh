@@ -36,6 +36,8 @@ struct State {
   cudaEvent_t ev[8] = {};
   void* stage_buf[2] = {nullptr, nullptr};  // cached H2D staging for gbm_scan_host
   size_t stage_bytes = 0;
+  void* pack_host[2] = {nullptr, nullptr};  // pinned host staging for packed blocks
+  size_t pack_bytes = 0;
   cudaEvent_t stage_copied[2] = {nullptr, nullptr}, stage_consumed[2] = {nullptr, nullptr};
   double h2d_ms = 0, kernel_ms = 0, main_ms = 0, d2h_ms = 0;
   int64_t launches = 0;
@@ -46,6 +48,9 @@ void require_ready();
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed)
 void make_tensor_map_2d_f64(CUtensorMap* map, const double* base, uint64_t rows, uint64_t cols,
                             uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols);
+// byte matrix viewed as uint64 words: rows64 words per column, column pitch ld_bytes (multiple of 16)
+void make_tensor_map_2d_u64(CUtensorMap* map, const void* base, uint64_t rows64, uint64_t cols, uint64_t ld_bytes,
+                            uint32_t box_rows64, uint32_t box_cols);
 
 // ------------------------------------------------------------------------------------
 // device-side PTX wrappers: mbarrier + TMA (cp.async.bulk[.tensor])

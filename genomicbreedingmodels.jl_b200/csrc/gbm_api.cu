@@ -10,15 +10,22 @@
 #include <algorithm>
 #include <memory>
 #include <mutex>
+#include <thread>
+#ifdef __linux__
+#include <sched.h>
+#endif
 #include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
 
 struct gbm_matrix {
-  double* d = nullptr;
+  double* d = nullptr;      // Float64 slab (dtype 0)
   int64_t n = 0, p = 0, lda = 0;
   bool owned = false;
+  int dtype = 0;            // 0: Float64, 1: one-byte dosage codes (a = code / 240)
+  uint8_t* d8 = nullptr;    // code slab (dtype 1), column pitch ld8 bytes
+  int64_t ld8 = 0;
 };
 
 namespace gbm {
@@ -63,6 +70,20 @@ void make_tensor_map_2d_f64(CUtensorMap* map, const double* base, uint64_t rows,
   if (r != CUDA_SUCCESS) GBM_THROW(GBM_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
 }
 
+void make_tensor_map_2d_u64(CUtensorMap* map, const void* base, uint64_t rows64, uint64_t cols, uint64_t ld_bytes,
+                            uint32_t box_rows64, uint32_t box_cols) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (ld_bytes & 15u) != 0)
+    GBM_THROW(GBM_ERR_ARGUMENT, "packed matrix must be 16-byte aligned with a pitch that is a multiple of 16");
+  cuuint64_t gdim[2] = {rows64, cols};
+  cuuint64_t gstride[1] = {ld_bytes};
+  cuuint32_t box[2] = {box_rows64, box_cols};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_tiled()(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) GBM_THROW(GBM_ERR_CUDA, "cuTensorMapEncodeTiled (u64) failed with code " + std::to_string((int)r));
+}
+
 static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 static bool is_device_ptr(const void* p) {
@@ -89,6 +110,32 @@ struct DevBuf {
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
 };
+
+// streaming sums over a resident matrix of either storage type
+static void scan_sums_any(const gbm_matrix* m, int64_t j0, int64_t pb, const double* Q, int M, int64_t ldq,
+                          double* rec) {
+  State& st = state();
+  if (m->dtype == 0) {
+    launch_scan_sums(m->d + j0 * m->lda, m->n, pb, m->lda, Q, M, ldq, M == 0, rec, st.sm_count, st.stream);
+  } else {
+    const int stride = scan_record_stride(M, false);
+    const int Mp = stride - 2 - (M == 0 ? 1 : 0);
+    if (Mp <= 2) {
+      launch_scan_sums_u8(m->d8 + j0 * m->ld8, m->n, pb, m->ld8, Q, Mp, ldq, rec, st.sm_count, st.stream);
+    } else {
+      // many side vectors (multi-trait) on packed codes: decode column blocks, Float64 kernel
+      const int64_t ldt = round_up(m->n, 16);
+      int64_t PB = std::max<int64_t>(16, ((int64_t(1) << 30) / (8 * ldt)) / 16 * 16);
+      PB = std::min(PB, round_up(pb, 16));
+      DevBuf<double> tmp(static_cast<size_t>(ldt) * PB, st.stream);
+      for (int64_t b0 = 0; b0 < pb; b0 += PB) {
+        const int64_t pc = std::min(PB, pb - b0);
+        launch_decode_u8(m->d8 + (j0 + b0) * m->ld8, m->n, pc, m->ld8, tmp.p, ldt, st.stream);
+        launch_scan_sums(tmp.p, m->n, pc, ldt, Q, M, ldq, false, rec + b0 * stride, st.sm_count, st.stream);
+      }
+    }
+  }
+}
 
 // event-pair timing on the library stream
 struct Span {
@@ -243,10 +290,10 @@ struct ScanOutputs {
   uint8_t* keep;
 };
 
-static void scan_block(const double* dA, int64_t n, int64_t p_blk, int64_t lda,
-                       const std::vector<std::unique_ptr<Pass>>& passes, const std::vector<double*>& rec_bufs,
-                       int k_eff, int model, int flags, const ScanOutputs& dev_out, int64_t ld_out, int64_t col0,
-                       Span* main_span) {
+static void scan_block(const gbm_matrix& mat, int64_t p_blk, const std::vector<std::unique_ptr<Pass>>& passes,
+                       const std::vector<double*>& rec_bufs, int k_eff, int model, int flags,
+                       const ScanOutputs& dev_out, int64_t ld_out, int64_t col0, Span* main_span) {
+  const int64_t n = mat.n;
   State& st = state();
   const int64_t ldq = round_up(n, 2);
   for (size_t pi = 0; pi < passes.size(); ++pi) {
@@ -255,7 +302,7 @@ static void scan_block(const double* dA, int64_t n, int64_t p_blk, int64_t lda,
     DevBuf<double> rec_tmp(own_rec ? static_cast<size_t>(p_blk) * ps->stride : 0, st.stream);
     struct { double* p; } rec{own_rec ? rec_tmp.p : rec_bufs[pi]};
     if (main_span) main_span->start();
-    launch_scan_sums(dA, n, p_blk, lda, ps->dQ.p, ps->M, ldq, false, rec.p, st.sm_count, st.stream);
+    scan_sums_any(&mat, 0, p_blk, ps->dQ.p, ps->M, ldq, rec.p);
     if (main_span) main_span->stop();
     FinalizeParams fp;
     fp.n = n;
@@ -352,6 +399,11 @@ int gbm_shutdown(void) {
     st.stage_copied[b] = st.stage_consumed[b] = nullptr;
   }
   st.stage_bytes = 0;
+  for (int b = 0; b < 2; ++b) {
+    if (st.pack_host[b]) cudaFreeHost(st.pack_host[b]);
+    st.pack_host[b] = nullptr;
+  }
+  st.pack_bytes = 0;
   if (st.own_stream) cudaStreamDestroy(st.own_stream);
   if (st.copy_stream) cudaStreamDestroy(st.copy_stream);
   st.own_stream = st.copy_stream = st.stream = nullptr;
@@ -557,6 +609,57 @@ int gbm_matrix_generate(uint64_t seed, int64_t n, int64_t p, int64_t col0, int k
   GBM_API_END
 }
 
+int gbm_matrix_pack(const gbm_matrix* m, gbm_matrix** out, int64_t* n_inexact) {
+  GBM_API_BEGIN
+  require_ready();
+  if (!m || !out || !n_inexact) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_matrix_pack: null pointer");
+  if (m->dtype != 0) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_matrix_pack: the matrix is already packed");
+  State& st = state();
+  *out = nullptr;
+  std::unique_ptr<gbm_matrix> q(new gbm_matrix);
+  q->n = m->n;
+  q->p = m->p;
+  q->dtype = 1;
+  q->owned = true;
+  q->ld8 = round_up(m->n, 128);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&q->d8), static_cast<size_t>(q->ld8) * m->p);
+  if (e != cudaSuccess) GBM_THROW(GBM_ERR_CUDA, std::string("cudaMalloc of the code slab failed: ") + cudaGetErrorString(e));
+  DevBuf<unsigned long long> bad(1, st.stream);
+  GBM_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(unsigned long long), st.stream));
+  launch_pack_u8(m->d, m->n, m->p, m->lda, q->d8, q->ld8, bad.p, st.stream);
+  unsigned long long h = 0;
+  GBM_CUDA(cudaMemcpyAsync(&h, bad.p, sizeof(h), cudaMemcpyDeviceToHost, st.stream));
+  GBM_CUDA(cudaStreamSynchronize(st.stream));
+  *n_inexact = static_cast<int64_t>(h);
+  if (h != 0) {
+    cudaFree(q->d8);  // not every element is a dosage code: the Float64 path must be used
+    return GBM_OK;
+  }
+  *out = q.release();
+  GBM_API_END
+}
+
+int gbm_matrix_upload_packed(const uint8_t* codes, int64_t n, int64_t p, int64_t ld, gbm_matrix** out) {
+  GBM_API_BEGIN
+  require_ready();
+  if (!codes || !out) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_matrix_upload_packed: null pointer");
+  check_dims(n, p, ld);
+  State& st = state();
+  std::unique_ptr<gbm_matrix> q(new gbm_matrix);
+  q->n = n;
+  q->p = p;
+  q->dtype = 1;
+  q->owned = true;
+  q->ld8 = round_up(n, 128);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&q->d8), static_cast<size_t>(q->ld8) * p);
+  if (e != cudaSuccess) GBM_THROW(GBM_ERR_CUDA, std::string("cudaMalloc of the code slab failed: ") + cudaGetErrorString(e));
+  GBM_CUDA(cudaMemsetAsync(q->d8, 0, static_cast<size_t>(q->ld8) * p, st.stream));
+  GBM_CUDA(cudaMemcpy2DAsync(q->d8, q->ld8, codes, ld, n, p, cudaMemcpyDefault, st.stream));
+  GBM_CUDA(cudaStreamSynchronize(st.stream));
+  *out = q.release();
+  GBM_API_END
+}
+
 int gbm_matrix_download(const gbm_matrix* m, int64_t j0, int64_t ncols, double* dst, int64_t ldd) {
   GBM_API_BEGIN
   require_ready();
@@ -564,6 +667,15 @@ int gbm_matrix_download(const gbm_matrix* m, int64_t j0, int64_t ncols, double* 
   if (j0 < 0 || ncols < 0 || j0 + ncols > m->p || ldd < m->n)
     GBM_THROW(GBM_ERR_ARGUMENT, "gbm_matrix_download: range out of bounds");
   State& st = state();
+  if (m->dtype == 1) {
+    const int64_t ldt = round_up(m->n, 16);
+    DevBuf<double> tmp(static_cast<size_t>(ldt) * std::max<int64_t>(ncols, 1), st.stream);
+    launch_decode_u8(m->d8 + j0 * m->ld8, m->n, ncols, m->ld8, tmp.p, ldt, st.stream);
+    GBM_CUDA(cudaMemcpy2DAsync(dst, ldd * sizeof(double), tmp.p, ldt * sizeof(double), m->n * sizeof(double), ncols,
+                               cudaMemcpyDefault, st.stream));
+    GBM_CUDA(cudaStreamSynchronize(st.stream));
+    return GBM_OK;
+  }
   GBM_CUDA(cudaMemcpy2DAsync(dst, ldd * sizeof(double), m->d + j0 * m->lda, m->lda * sizeof(double),
                              m->n * sizeof(double), ncols, cudaMemcpyDefault, st.stream));
   GBM_CUDA(cudaStreamSynchronize(st.stream));
@@ -576,16 +688,18 @@ int gbm_matrix_info(const gbm_matrix* m, int64_t* n, int64_t* p, int64_t* lda, d
   if (n) *n = m->n;
   if (p) *p = m->p;
   if (lda) *lda = m->lda;
-  if (device_ptr) *device_ptr = m->d;
+  if (lda && m->dtype == 1) *lda = m->ld8;
+  if (device_ptr) *device_ptr = m->dtype == 1 ? reinterpret_cast<double*>(m->d8) : m->d;
   GBM_API_END
 }
 
 int gbm_matrix_free(gbm_matrix* m) {
   GBM_API_BEGIN
   if (m) {
-    if (m->owned && m->d) {
+    if (m->owned && (m->d || m->d8)) {
       cudaStreamSynchronize(state().stream);
-      cudaFree(m->d);
+      if (m->d) cudaFree(m->d);
+      if (m->d8) cudaFree(m->d8);
     }
     delete m;
   }
@@ -611,7 +725,7 @@ int gbm_colstats(const gbm_matrix* m, double* mean, double* sd, double* min_nonz
   Span all(st.stream), mainsp(st.stream);
   all.start();
   mainsp.start();
-  launch_scan_sums(m->d, m->n, p, m->lda, nullptr, 0, 0, true, rec.p, st.sm_count, st.stream);
+  scan_sums_any(m, 0, p, nullptr, 0, 0, rec.p);
   mainsp.stop();
   launch_colstats_finalize(rec.p, stride, m->n, p, dmean.p, dsd.p, dmin.p, dkeep.p, st.stream);
   launch_compact_keep(dkeep.p, dmin.p, p, didx.p, dcount.p, dminkept.p, st.stream);
@@ -649,7 +763,7 @@ static void column_means_padded(const gbm_matrix* m, double* dmu_pad /* round_up
   State& st = state();
   const int stride = scan_record_stride(0, true);
   DevBuf<double> rec(static_cast<size_t>(m->p) * stride, st.stream);
-  launch_scan_sums(m->d, m->n, m->p, m->lda, nullptr, 0, 0, true, rec.p, st.sm_count, st.stream);
+  scan_sums_any(m, 0, m->p, nullptr, 0, 0, rec.p);
   launch_colstats_finalize(rec.p, stride, m->n, m->p, dmu_pad, nullptr, nullptr, nullptr, st.stream);
   st.launches += 2;
 }
@@ -669,7 +783,21 @@ static void grm_accumulate_impl(const gbm_matrix* m, int centre, double* dK, dou
   }
   if (!centre) GBM_CUDA(cudaMemsetAsync(dmu.p, 0, sizeof(double) * ppad, st.stream));
   mainsp.start();
-  launch_grm_accumulate(m->d, m->n, m->p, m->lda, dmu.p, dK, st.sm_count, st.stream, centre != 0);
+  if (m->dtype == 0) {
+    launch_grm_accumulate(m->d, m->n, m->p, m->lda, dmu.p, dK, st.sm_count, st.stream, centre != 0);
+  } else {
+    // packed codes: decode column blocks (<= 1 GB of Float64) and accumulate block by block
+    const int64_t ldt = round_up(m->n, 16);
+    int64_t PB = std::max<int64_t>(16, ((int64_t(1) << 30) / (8 * ldt)) / 16 * 16);
+    PB = std::min(PB, ppad);
+    DevBuf<double> tmp(static_cast<size_t>(ldt) * PB, st.stream);
+    for (int64_t j0 = 0; j0 < m->p; j0 += PB) {
+      const int64_t pb = std::min(PB, m->p - j0);
+      launch_decode_u8(m->d8 + j0 * m->ld8, m->n, pb, m->ld8, tmp.p, ldt, st.stream);
+      launch_grm_accumulate(tmp.p, m->n, pb, ldt, dmu.p + j0, dK, st.sm_count, st.stream, centre != 0);
+      st.launches += 2;
+    }
+  }
   mainsp.stop();
   all.stop();
   st.launches++;
@@ -963,8 +1091,7 @@ int gbm_scan_plan_run(gbm_scan_plan* pl, double* beta, double* se, double* stat,
   pl->out->bind_all(p, pl->T, beta, se, stat, neglog10p, mean, sd, keep);
   Span all(st.stream), mainsp(st.stream);
   all.start();
-  scan_block(m->d, m->n, p, m->lda, pl->passes, pl->rec, pl->k_eff, pl->model, pl->flags, pl->out->view(), p, 0,
-             &mainsp);
+  scan_block(*m, p, pl->passes, pl->rec, pl->k_eff, pl->model, pl->flags, pl->out->view(), p, 0, &mainsp);
   all.stop();
   Span d2h(st.stream);
   d2h.start();
@@ -1000,6 +1127,28 @@ int gbm_scan(const gbm_matrix* m, const double* Y, int64_t T, int64_t ldy, const
   return rc;
 }
 
+// ---- host-side packer (host_pack.cpp): Float64 -> dosage codes with the exactness check ----
+}  // extern "C"
+
+namespace gbm {
+bool pack_block_host(const double* A, int64_t n, int64_t lda, int64_t pc, uint8_t* out, int64_t ldo);
+int64_t count_inexact_host(const double* A, int64_t n, int64_t lda, int64_t pc);
+int host_threads();
+}  // namespace gbm
+
+extern "C" {
+
+int gbm_pack_host(const double* A, int64_t n, int64_t p, int64_t lda, uint8_t* out, int64_t ldo, int64_t* n_inexact) {
+  GBM_API_BEGIN
+  if (!A || !out || !n_inexact || n < 1 || p < 1 || lda < n || ldo < n)
+    GBM_THROW(GBM_ERR_ARGUMENT, "gbm_pack_host: bad arguments");
+  if (pack_block_host(A, n, lda, p, out, ldo))
+    *n_inexact = 0;
+  else
+    *n_inexact = count_inexact_host(A, n, lda, p);
+  GBM_API_END
+}
+
 int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const double* Y, int64_t T, int64_t ldy,
                   const double* C, int64_t k, int64_t ldc, int model, int flags, double* beta, double* se,
                   double* stat, double* neglog10p, double* mean, double* sd, uint8_t* keep) {
@@ -1017,13 +1166,15 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
   out.bind_all(p, T, beta, se, stat, neglog10p, mean, sd, keep);
   auto passes = build_passes(sv, n, T);
   const std::vector<double*> no_rec;
-  // column blocks of ~256 MB, double-buffered: the copy engine fills one buffer while the
+  bool pack = (flags & GBM_SCAN_HOST_NO_PACK) == 0 && !is_device_ptr(A);  // auto: pack blocks that are all dosage codes
+  const int kflags = flags & GBM_PVALUE_TWO_SIDED;
+  // column blocks of ~256 MB of Float64, double-buffered: the copy engine fills one buffer while the
   // scan kernel streams the other
   const int64_t ldd = round_up(n, 16);
+  const int64_t ld8 = round_up(n, 128);
   int64_t blk = std::max<int64_t>(16, ((int64_t(256) << 20) / (8 * ldd)) / 16 * 16);
   blk = std::min(blk, round_up(p, 16));
-  // staging buffers and events are cached across calls (cudaMalloc/cudaFree of 2 x 256 MB per
-  // call would cost milliseconds)
+  // staging buffers and events are cached across calls
   const size_t need = sizeof(double) * ldd * blk;
   if (st.stage_bytes < need) {
     for (int b = 0; b < 2; ++b) {
@@ -1033,15 +1184,25 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
     }
     st.stage_bytes = need;
   }
+  const size_t need8 = static_cast<size_t>(ld8) * blk;
+  if (pack && st.pack_bytes < need8) {
+    for (int b = 0; b < 2; ++b) {
+      if (st.pack_host[b]) cudaFreeHost(st.pack_host[b]);
+      st.pack_host[b] = nullptr;
+      GBM_CUDA(cudaMallocHost(&st.pack_host[b], need8));
+    }
+    st.pack_bytes = need8;
+  }
   double* buf[2] = {static_cast<double*>(st.stage_buf[0]), static_cast<double*>(st.stage_buf[1])};
   cudaEvent_t* copied = st.stage_copied;
   cudaEvent_t* consumed = st.stage_consumed;
   for (int b = 0; b < 2; ++b) {
     if (!copied[b]) GBM_CUDA(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
     if (!consumed[b]) GBM_CUDA(cudaEventCreateWithFlags(&consumed[b], cudaEventDisableTiming));
-    if (ldd != n) GBM_CUDA(cudaMemsetAsync(buf[b], 0, need, st.copy_stream));
+    if (ldd != n && !pack) GBM_CUDA(cudaMemsetAsync(buf[b], 0, need, st.copy_stream));
   }
   const bool contiguous = (lda == n && ldd == n);
+  int64_t packed_blocks = 0, total_blocks = 0;
   Span all(st.stream);
   all.start();
   GBM_CUDA(cudaEventRecord(consumed[0], st.stream));
@@ -1049,15 +1210,41 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
   int b = 0;
   for (int64_t j0 = 0; j0 < p; j0 += blk, b ^= 1) {
     const int64_t pc = std::min(blk, p - j0);
-    GBM_CUDA(cudaStreamWaitEvent(st.copy_stream, consumed[b], 0));
-    if (contiguous)
-      GBM_CUDA(cudaMemcpyAsync(buf[b], A + j0 * lda, sizeof(double) * n * pc, cudaMemcpyDefault, st.copy_stream));
-    else
-      GBM_CUDA(cudaMemcpy2DAsync(buf[b], ldd * sizeof(double), A + j0 * lda, lda * sizeof(double),
-                                 n * sizeof(double), pc, cudaMemcpyDefault, st.copy_stream));
+    ++total_blocks;
+    gbm_matrix view;
+    view.n = n;
+    view.p = pc;
+    bool packed_ok = false;
+    if (pack) {
+      // the pinned pack buffer b was handed to the copy engine two blocks ago: wait for that copy
+      GBM_CUDA(cudaEventSynchronize(copied[b]));
+      uint8_t* hp = static_cast<uint8_t*>(st.pack_host[b]);
+      packed_ok = pack_block_host(A + j0 * lda, n, lda, pc, hp, ld8);
+      if (!packed_ok) pack = false;  // not dosage data: stop trying, the rest travels as Float64
+      if (packed_ok) {
+        GBM_CUDA(cudaStreamWaitEvent(st.copy_stream, consumed[b], 0));
+        GBM_CUDA(cudaMemcpyAsync(buf[b], hp, static_cast<size_t>(ld8) * pc, cudaMemcpyHostToDevice, st.copy_stream));
+        view.dtype = 1;
+        view.d8 = reinterpret_cast<uint8_t*>(buf[b]);
+        view.ld8 = ld8;
+        ++packed_blocks;
+      }
+    }
+    if (!packed_ok) {
+      GBM_CUDA(cudaStreamWaitEvent(st.copy_stream, consumed[b], 0));
+      if (pack && ldd != n) GBM_CUDA(cudaMemsetAsync(buf[b], 0, sizeof(double) * ldd * pc, st.copy_stream));
+      if (contiguous)
+        GBM_CUDA(cudaMemcpyAsync(buf[b], A + j0 * lda, sizeof(double) * n * pc, cudaMemcpyDefault, st.copy_stream));
+      else
+        GBM_CUDA(cudaMemcpy2DAsync(buf[b], ldd * sizeof(double), A + j0 * lda, lda * sizeof(double),
+                                   n * sizeof(double), pc, cudaMemcpyDefault, st.copy_stream));
+      view.dtype = 0;
+      view.d = buf[b];
+      view.lda = ldd;
+    }
     GBM_CUDA(cudaEventRecord(copied[b], st.copy_stream));
     GBM_CUDA(cudaStreamWaitEvent(st.stream, copied[b], 0));
-    scan_block(buf[b], n, pc, ldd, passes, no_rec, sv.k_eff, model, flags, out.view(), p, j0, nullptr);
+    scan_block(view, pc, passes, no_rec, sv.k_eff, model, kflags, out.view(), p, j0, nullptr);
     GBM_CUDA(cudaEventRecord(consumed[b], st.stream));
   }
   all.stop();
@@ -1065,6 +1252,8 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
   GBM_CUDA(cudaStreamSynchronize(st.stream));
   GBM_CUDA(cudaStreamSynchronize(st.copy_stream));
   st.kernel_ms = all.ms();  // copy + compute overlapped: wall time of the pipeline on the device
+  st.launches = packed_blocks;  // reported through gbm_last_timing: blocks that went down the packed path
+  (void)total_blocks;
   GBM_API_END
 }
 
@@ -1190,7 +1379,7 @@ int gbm_lmm_plan_run(gbm_lmm_plan* pl, const gbm_matrix* m, int flags, double* b
   const int stride = scan_record_stride(0, true);
   DevBuf<double> rec(static_cast<size_t>(p) * stride, st.stream), dsd(p, st.stream);
   DevBuf<uint8_t> dkeep(p, st.stream);
-  launch_scan_sums(m->d, n, p, m->lda, nullptr, 0, 0, true, rec.p, st.sm_count, st.stream);
+  scan_sums_any(m, 0, p, nullptr, 0, 0, rec.p);
   launch_colstats_finalize(rec.p, stride, n, p, nullptr, dsd.p, nullptr, dkeep.p, st.stream);
   st.launches += 2;
   OutTargets out(st.stream);
@@ -1203,13 +1392,19 @@ int gbm_lmm_plan_run(gbm_lmm_plan* pl, const gbm_matrix* m, int flags, double* b
   int64_t PB = std::max<int64_t>(128, ((int64_t(1) << 30) / (8 * ldr)) / 128 * 128);
   PB = std::min<int64_t>(PB, round_up(p, 128));
   DevBuf<double> dAr(static_cast<size_t>(ldr) * PB, st.stream);
+  DevBuf<double> dDec(m->dtype == 1 ? static_cast<size_t>(ldr) * PB : 0, st.stream);
   double gemm_total = 0.0, search_total = 0.0;
   std::vector<std::unique_ptr<Span>> gs, ss;
   for (int64_t j0 = 0; j0 < p; j0 += PB) {
     const int64_t pb = std::min(PB, p - j0);
     gs.emplace_back(new Span(st.stream));
     gs.back()->start();
-    launch_gemm_tn(pl->dU, pl->ldu, m->d + j0 * m->lda, m->lda, dAr.p, ldr, n, pb, n, st.sm_count, st.stream);
+    if (m->dtype == 0) {
+      launch_gemm_tn(pl->dU, pl->ldu, m->d + j0 * m->lda, m->lda, dAr.p, ldr, n, pb, n, st.sm_count, st.stream);
+    } else {
+      launch_decode_u8(m->d8 + j0 * m->ld8, n, pb, m->ld8, dDec.p, ldr, st.stream);
+      launch_gemm_tn(pl->dU, pl->ldu, dDec.p, ldr, dAr.p, ldr, n, pb, n, st.sm_count, st.stream);
+    }
     gs.back()->stop();
     ss.emplace_back(new Span(st.stream));
     ss.back()->start();

@@ -47,6 +47,16 @@ void launch_compact_keep(const uint8_t* keep, const double* minnz, int64_t p, in
 
 void launch_neglog10_sf(const double* stat, int64_t len, int dist, double df, double* out, cudaStream_t stream);
 
+// scan_u8.cu --------------------------------------------------------------------------
+// Compact dosage codes (1 byte per genotype, a = code/240).  Mp = padded side-vector count as in scan.cu;
+// records have the same meaning and stride as the Float64 kernel's (Mp = 0 tracks min-nonzero).
+void launch_scan_sums_u8(const uint8_t* A8, int64_t n, int64_t p, int64_t ld8, const double* Q, int Mp, int64_t ldq,
+                         double* rec, int sm_count, cudaStream_t stream);
+void launch_pack_u8(const double* A, int64_t n, int64_t p, int64_t lda, uint8_t* out, int64_t ld8,
+                    unsigned long long* inexact, cudaStream_t stream);
+void launch_decode_u8(const uint8_t* A8, int64_t n, int64_t p, int64_t ld8, double* out, int64_t ldo,
+                      cudaStream_t stream);
+
 // grm.cu -------------------------------------------------------------------------------
 // dK (n x n col-major, ld n) += lower-triangle tiles of sum_j (a_j - mu_j)(a_j - mu_j)'.
 // mu: device, length >= round_up(p, 16), zero padded (all zeros = uncentred).

@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "pvalue.cuh"
+#include "reduce.cuh"
 
 namespace gbm {
 
@@ -47,22 +48,6 @@ struct ScanParams {
   int num_tiles, chunks;
   double inv_n;
   double* rec;
-};
-
-// Halving butterfly: N values per lane in, N/32 fully reduced values per lane out.  All
-// register indices are compile-time.
-template <int CNT, int MASK, int N>
-struct HalvingStep {
-  static __device__ __forceinline__ void run(double (&v)[N], int lane) {
-    const bool upper = (lane & MASK) != 0;
-#pragma unroll
-    for (int i = 0; i < CNT; ++i) {
-      const double send = upper ? v[i] : v[i + CNT];
-      const double keep = upper ? v[i + CNT] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, MASK);
-    }
-    if constexpr (MASK > 1) HalvingStep<CNT / 2, MASK / 2, N>::run(v, lane);
-  }
 };
 
 template <int C, int M, bool MINNZ>

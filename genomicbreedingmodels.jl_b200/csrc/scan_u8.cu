@@ -1,0 +1,368 @@
+// Compact-dosage marker scan ("compact integer dosage encodings,
+// 1 B/genotype => 8x fewer bytes, fused with the scan").
+//
+// Storage: one byte per genotype, code c in [0, 240], allele frequency a = c / 240 (240 is
+// divisible by 1..6, 8, 10, 12, 15, 16 so every ploidy level of those ploidies is a code).
+// A Float64 matrix is packed only if EVERY element satisfies fl(code/240) == a bit-exactly
+// (pack kernel / host packer); otherwise the Float64 path is used.  The doctests' data
+// (round.(af .* ploidy) ./ ploidy, /root/reference/src/gwas.jl:43-45) and the BASELINE
+// dosage configurations pack.
+//
+// Kernel: same persistent producer/consumer structure as scan.cu.  The byte matrix is
+// addressed through a UINT64 tensor map (8 codes per element), a stage is 1024 rows x C
+// markers of codes (one TMA box) plus the matching slice of the side vectors (2048 rows with
+// eight consumer warps).  A consumer
+// lane owns 8 consecutive rows: one LDS.64 per marker brings its 8 codes; sum(c) and sum(c^2)
+// are integer dot products (dp4a); the M dots sum(c*q) run in FP64 with the codes converted
+// by the 2^52 trick (one DADD, no I2F).  Per-marker records are identical in meaning to the
+// Float64 kernel's: [mean, SS, dots.. (, min nonzero)], so the finalisation kernel is shared.
+// sum(c), sum(c^2) are exact integers: SS of a constant column is exactly 0.
+//
+// Algorithmic bytes: n per marker.
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "reduce.cuh"
+
+namespace gbm {
+
+constexpr int kU8ConsumerWarps = 4;
+constexpr int kU8Rows = kU8ConsumerWarps * 32 * 8;  // rows per stage: every consumer lane owns 8 rows
+constexpr int kU8ConsumerThreads = kU8ConsumerWarps * 32;
+constexpr int kU8Threads = kU8ConsumerThreads + 32;
+constexpr int kU8SmemBudget = 200 * 1024;
+constexpr double kLevels = 240.0;
+
+template <int C, int M, bool MINNZ>
+struct U8Cfg {
+  static constexpr int NSUM = 2 + M;
+  static constexpr int NV = C * NSUM;
+  static constexpr int NVP = ((NV + 31) / 32) * 32;
+  static constexpr int NS = NSUM + (MINNZ ? 1 : 0);
+  static constexpr int A_BYTES = kU8Rows * C;          // bytes of codes
+  static constexpr int Q_BYTES = kU8Rows * M * 8;
+  static constexpr int STAGE_BYTES = A_BYTES + Q_BYTES;
+  static constexpr int STAGES_RAW = kU8SmemBudget / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int RED_BYTES = 2 * kU8ConsumerWarps * NVP * 8 + 2 * kU8ConsumerWarps * C * 8 + 2 * C * 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RED_BYTES + 2 * STAGES * 8 + 128;
+};
+
+struct U8Params {
+  int64_t n, p;
+  int num_tiles, chunks;
+  double inv_n;
+  double* rec;
+};
+
+__device__ __forceinline__ double code_to_double(uint32_t c) {
+  // 2^52 + c is exactly representable; subtracting 2^52 leaves c
+  return __hiloint2double(0x43300000, static_cast<int>(c)) - 4503599627370496.0;
+}
+
+template <int C, int M, bool MINNZ>
+__global__ void __launch_bounds__(kU8Threads, 1)
+    scan_sums_u8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmQ,
+                        const U8Params prm) {
+  using Cfg = U8Cfg<C, M, MINNZ>;
+  constexpr int NSUM = Cfg::NSUM, NV = Cfg::NV, NVP = Cfg::NVP, NS = Cfg::NS, STAGES = Cfg::STAGES;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* ring = smem;
+  double* red = reinterpret_cast<double*>(smem + STAGES * Cfg::STAGE_BYTES);
+  double* redmin = red + 2 * kU8ConsumerWarps * NVP;
+  double* shift_s = redmin + 2 * kU8ConsumerWarps * C;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(shift_s + 2 * C);
+  uint64_t* empty_bar = full_bar + STAGES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kU8ConsumerWarps);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == kU8ConsumerWarps) {
+    if (lane == 0) {
+      prefetch_tensormap(&tmA);
+      if (M > 0) prefetch_tensormap(&tmQ);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
+        for (int chunk = 0; chunk < prm.chunks; ++chunk) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* dst = ring + stage * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(dst, &tmA, chunk * (kU8Rows / 8), tile * C, &full_bar[stage], kEvictFirst);
+          if (M > 0) {
+#pragma unroll
+            for (int b = 0; b < kU8Rows / 256; ++b)  // Q boxes are 256 rows x M, laid out [b][m][256]
+              tma_load_2d(dst + Cfg::A_BYTES + b * 256 * M * 8, &tmQ, chunk * kU8Rows + b * 256, 0,
+                          &full_bar[stage], kEvictLast);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  int stage = 0;
+  uint32_t phase = 0;
+  int parity = 0;
+  const int r = 8 * tid;  // this lane's 8 rows inside a 1024-row chunk
+  for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, parity ^= 1) {
+    uint32_t s1[C], s2[C];
+    uint32_t mn[MINNZ ? C : 1];
+    double dots[M > 0 ? C * M : 1];
+#pragma unroll
+    for (int c = 0; c < C; ++c) s1[c] = s2[c] = 0;
+#pragma unroll
+    for (int i = 0; i < C * M; ++i) dots[i] = 0.0;
+    if (MINNZ) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) mn[c] = 0xFFu + 1u;
+    }
+
+    for (int chunk = 0; chunk < prm.chunks; ++chunk) {
+      mbar_wait(&full_bar[stage], phase);
+      const uint64_t* sA = reinterpret_cast<const uint64_t*>(ring + stage * Cfg::STAGE_BYTES);
+      const double* sQ = reinterpret_cast<const double*>(ring + stage * Cfg::STAGE_BYTES + Cfg::A_BYTES);
+      if (chunk == 0 && tid < C)
+        shift_s[parity * C + tid] = static_cast<double>(static_cast<uint32_t>(sA[tid * (kU8Rows / 8)] & 0xFFull));
+      const int64_t row0 = static_cast<int64_t>(chunk) * kU8Rows + r;
+      const int valid = static_cast<int>(prm.n - row0 < 8 ? (prm.n - row0 < 0 ? 0 : prm.n - row0) : 8);
+      // byte mask for the rows of this lane that exist (TMA zero-fills whole out-of-range
+      // words, the tail bytes of the last word are zero in our own buffer; the mask keeps the
+      // code independent of that)
+      const uint64_t bmask = valid >= 8 ? ~0ull : ((1ull << (8 * valid)) - 1ull);
+      double q[M > 0 ? M : 1][8];
+      if (M > 0) {
+        const int qb = r >> 8, qr = r & 255;  // box index and row inside the 256-row box
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+          const double* src = sQ + (qb * M + m) * 256 + qr;
+#pragma unroll
+          for (int k = 0; k < 8; k += 2) {
+            const double2 t2 = *reinterpret_cast<const double2*>(src + k);
+            q[m][k] = t2.x;
+            q[m][k + 1] = t2.y;
+          }
+        }
+      }
+      if (valid > 0) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const uint64_t w = sA[c * (kU8Rows / 8) + tid] & bmask;
+          const uint32_t lo = static_cast<uint32_t>(w), hi = static_cast<uint32_t>(w >> 32);
+          s1[c] = __dp4a(lo, 0x01010101u, __dp4a(hi, 0x01010101u, s1[c]));
+          s2[c] = __dp4a(lo, lo, __dp4a(hi, hi, s2[c]));
+          if (M > 0) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t code = (k < 4 ? (lo >> (8 * k)) : (hi >> (8 * (k - 4)))) & 0xFFu;
+              const double cd = code_to_double(code);
+#pragma unroll
+              for (int m = 0; m < M; ++m) dots[c * M + m] = fma(cd, q[m][k], dots[c * M + m]);
+            }
+          }
+          if (MINNZ) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t code = (k < 4 ? (lo >> (8 * k)) : (hi >> (8 * (k - 4)))) & 0xFFu;
+              mn[c] = (code != 0u && code < mn[c]) ? code : mn[c];
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+
+    // epilogue: exact integer sums -> doubles (< 2^53), then the same reduction tree
+    double v[NVP];
+#pragma unroll
+    for (int i = 0; i < NVP; ++i) v[i] = 0.0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      v[c * NSUM + 0] = static_cast<double>(s1[c]);
+      v[c * NSUM + 1] = static_cast<double>(s2[c]);
+#pragma unroll
+      for (int m = 0; m < M; ++m) v[c * NSUM + 2 + m] = dots[c * M + m];
+    }
+    HalvingStep<NVP / 2, 16, NVP>::run(v, lane);
+    {
+      double* dst = red + (parity * kU8ConsumerWarps + warp) * NVP + halving_base<NVP>(lane);
+#pragma unroll
+      for (int i = 0; i < NVP / 32; ++i) dst[i] = v[i];
+    }
+    if (MINNZ) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        uint32_t x = mn[c];
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) x = min(x, __shfl_xor_sync(0xffffffffu, x, o));
+        if (lane == 0) redmin[(parity * kU8ConsumerWarps + warp) * C + c] = static_cast<double>(x);
+      }
+    }
+    named_bar_sync(1, kU8ConsumerThreads);
+    if (tid < NV) {
+      const int c = tid / NSUM, kk = tid - c * NSUM;
+      const double* rp = red + parity * kU8ConsumerWarps * NVP;
+      double tot = 0.0, S1 = 0.0, S2 = 0.0;
+#pragma unroll
+      for (int w = 0; w < kU8ConsumerWarps; ++w) {
+        tot += rp[w * NVP + tid];
+        S1 += rp[w * NVP + c * NSUM];
+        S2 += rp[w * NVP + c * NSUM + 1];
+      }
+      double out;
+      if (kk <= 1) {
+        // shift by the first code in exact integer arithmetic: constant columns give SS == 0
+        const long long c0 = static_cast<long long>(shift_s[parity * C + c]);
+        const long long n = prm.n;
+        const long long i1 = static_cast<long long>(S1) - n * c0;
+        const long long i2 = static_cast<long long>(S2) - 2 * c0 * static_cast<long long>(S1) + n * c0 * c0;
+        if (kk == 0) {
+          out = (static_cast<double>(c0) + static_cast<double>(i1) * prm.inv_n) / kLevels;
+        } else {
+          const double d1 = static_cast<double>(i1);
+          out = fmax(static_cast<double>(i2) - d1 * d1 * prm.inv_n, 0.0) / (kLevels * kLevels);
+        }
+      } else {
+        out = tot / kLevels;
+      }
+      const int64_t col = static_cast<int64_t>(tile) * C + c;
+      if (col < prm.p) prm.rec[col * NS + kk] = out;
+    }
+    if (MINNZ && tid >= kU8ConsumerThreads - C) {
+      const int c = tid - (kU8ConsumerThreads - C);
+      const double* mp = redmin + parity * kU8ConsumerWarps * C;
+      double x = mp[c];
+#pragma unroll
+      for (int w = 1; w < kU8ConsumerWarps; ++w) x = fmin(x, mp[w * C + c]);
+      const int64_t col = static_cast<int64_t>(tile) * C + c;
+      if (col < prm.p) prm.rec[col * NS + NSUM] = (x > 255.0) ? INFINITY : x / kLevels;
+    }
+  }
+}
+
+template <int C, int M, bool MINNZ>
+static void launch_u8_cfg(const uint8_t* A8, int64_t n, int64_t p, int64_t ld8, const double* Q, int64_t ldq,
+                          double* rec, int sm_count, cudaStream_t stream) {
+  using Cfg = U8Cfg<C, M, MINNZ>;
+  static_assert(Cfg::STAGES >= 2, "ring too shallow");
+  alignas(64) CUtensorMap tmA, tmQ;
+  make_tensor_map_2d_u64(&tmA, A8, static_cast<uint64_t>((n + 7) / 8), static_cast<uint64_t>(p),
+                         static_cast<uint64_t>(ld8), kU8Rows / 8, C);
+  if (M > 0)
+    make_tensor_map_2d_f64(&tmQ, Q, static_cast<uint64_t>(n), static_cast<uint64_t>(M), static_cast<uint64_t>(ldq),
+                           256, M);
+  else
+    tmQ = tmA;
+  U8Params prm;
+  prm.n = n;
+  prm.p = p;
+  prm.num_tiles = static_cast<int>((p + C - 1) / C);
+  prm.chunks = static_cast<int>((n + kU8Rows - 1) / kU8Rows);
+  prm.inv_n = 1.0 / static_cast<double>(n);
+  prm.rec = rec;
+  auto kern = scan_sums_u8_kernel<C, M, MINNZ>;
+  GBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  const int grid = prm.num_tiles < sm_count ? prm.num_tiles : sm_count;
+  kern<<<grid, kU8Threads, Cfg::SMEM_BYTES, stream>>>(tmA, tmQ, prm);
+  GBM_CUDA(cudaGetLastError());
+}
+
+// Mp: the padded side-vector count the Float64 dispatcher also uses (0,1,2,4,6,10,14)
+void launch_scan_sums_u8(const uint8_t* A8, int64_t n, int64_t p, int64_t ld8, const double* Q, int Mp, int64_t ldq,
+                         double* rec, int sm_count, cudaStream_t stream) {
+  if (p <= 0 || n <= 0) return;
+  switch (Mp) {
+    case 0: launch_u8_cfg<16, 0, true>(A8, n, p, ld8, Q, ldq, rec, sm_count, stream); break;
+    case 1: launch_u8_cfg<16, 1, false>(A8, n, p, ld8, Q, ldq, rec, sm_count, stream); break;
+    case 2: launch_u8_cfg<16, 2, false>(A8, n, p, ld8, Q, ldq, rec, sm_count, stream); break;
+    // more side vectors (multi-trait): the caller decodes blocks and uses the Float64 kernel
+    default: GBM_THROW(1, "scan(u8): unsupported side-vector count");
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// pack (Float64 -> codes, with the exactness check) and decode (codes -> Float64)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    pack_u8_kernel(const double* __restrict__ A, int64_t n, int64_t lda, uint8_t* __restrict__ out, int64_t ld8,
+                   unsigned long long* __restrict__ inexact) {
+  __shared__ double lut[241];
+  for (int i = threadIdx.x; i < 241; i += blockDim.x) lut[i] = static_cast<double>(i) / kLevels;
+  __syncthreads();
+  const int64_t j = blockIdx.y;
+  const double* col = A + j * lda;
+  uint64_t* dst = reinterpret_cast<uint64_t*>(out + j * ld8);
+  unsigned bad = 0;
+  for (int64_t w = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; w * 8 < ld8;
+       w += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    uint64_t word = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int64_t i = w * 8 + k;
+      if (i < n) {
+        const double a = col[i];
+        const double s = rint(a * kLevels);
+        int code = (s >= 0.0 && s <= 240.0) ? static_cast<int>(s) : 0;
+        if (!(s >= 0.0 && s <= 240.0) || lut[code] != a) ++bad;
+        word |= static_cast<uint64_t>(code) << (8 * k);
+      }
+    }
+    dst[w] = word;
+  }
+  if (bad) atomicAdd(inexact, static_cast<unsigned long long>(bad));
+}
+
+void launch_pack_u8(const double* A, int64_t n, int64_t p, int64_t lda, uint8_t* out, int64_t ld8,
+                    unsigned long long* inexact, cudaStream_t stream) {
+  if (n <= 0 || p <= 0) return;
+  unsigned gx = static_cast<unsigned>((ld8 / 8 + 255) / 256);
+  if (gx > 8) gx = 8;
+  for (int64_t j0 = 0; j0 < p; j0 += 65535) {
+    const unsigned gy = static_cast<unsigned>(p - j0 < 65535 ? p - j0 : 65535);
+    pack_u8_kernel<<<dim3(gx, gy), 256, 0, stream>>>(A + j0 * lda, n, lda, out + j0 * ld8, ld8, inexact);
+  }
+  GBM_CUDA(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256)
+    decode_u8_kernel(const uint8_t* __restrict__ A8, int64_t n, int64_t ld8, double* __restrict__ out, int64_t ldo) {
+  __shared__ double lut[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = static_cast<double>(i) / kLevels;
+  __syncthreads();
+  const int64_t j = blockIdx.y;
+  const uint8_t* col = A8 + j * ld8;
+  double* dst = out + j * ldo;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < ldo;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = i < n ? lut[col[i]] : 0.0;
+}
+
+void launch_decode_u8(const uint8_t* A8, int64_t n, int64_t p, int64_t ld8, double* out, int64_t ldo,
+                      cudaStream_t stream) {
+  if (n <= 0 || p <= 0) return;
+  unsigned gx = static_cast<unsigned>((ldo + 255) / 256);
+  if (gx > 16) gx = 16;
+  for (int64_t j0 = 0; j0 < p; j0 += 65535) {
+    const unsigned gy = static_cast<unsigned>(p - j0 < 65535 ? p - j0 : 65535);
+    decode_u8_kernel<<<dim3(gx, gy), 256, 0, stream>>>(A8 + j0 * ld8, n, ld8, out + j0 * ldo, ldo);
+  }
+  GBM_CUDA(cudaGetLastError());
+}
+
+}  // namespace gbm

@@ -27,6 +27,7 @@ GRM_SIMPLE, GRM_PLOIDY_AWARE = 0, 1
 GRM_NO_CENTRE = 1
 MODEL_OLS, MODEL_LMM = 0, 1
 PVALUE_TWO_SIDED = 1
+SCAN_HOST_NO_PACK = 4
 KIND_DIPLOID, KIND_TETRAPLOID, KIND_CONTINUOUS = 0, 1, 2
 
 
@@ -62,6 +63,9 @@ SIGNATURES = {
     "gbm_matrix_upload_indexed": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, POINTER(c_void_p)]),
     "gbm_matrix_wrap": (c_int, [_P, c_int64, c_int64, c_int64, POINTER(c_void_p)]),
     "gbm_matrix_generate": (c_int, [c_uint64, c_int64, c_int64, c_int64, c_int, POINTER(c_void_p)]),
+    "gbm_matrix_pack": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int64)]),
+    "gbm_matrix_upload_packed": (c_int, [_P, c_int64, c_int64, c_int64, POINTER(c_void_p)]),
+    "gbm_pack_host": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int64, POINTER(c_int64)]),
     "gbm_matrix_download": (c_int, [c_void_p, c_int64, c_int64, _P, c_int64]),
     "gbm_matrix_info": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_void_p)]),
     "gbm_matrix_free": (c_int, [c_void_p]),

@@ -24,6 +24,7 @@ class DeviceMatrix:
         self._h = handle
         self.n, self.p = int(n), int(p)
         self._keepalive = keepalive
+        self.packed = False
 
     # ---- constructors ----------------------------------------------------------------
     @classmethod
@@ -62,6 +63,28 @@ class DeviceMatrix:
         h = c_void_p()
         check(_lib.lib().gbm_matrix_generate(seed, n, p, col0, kind, byref(h)))
         return cls(h, n, p)
+
+    @classmethod
+    def upload_packed(cls, codes: np.ndarray) -> "DeviceMatrix":
+        """From one-byte dosage codes already on the host (n x p, uint8, a = code / 240)."""
+        codes = np.require(codes, dtype=np.uint8, requirements=["F_CONTIGUOUS", "ALIGNED"])
+        n, p = codes.shape
+        h = c_void_p()
+        check(_lib.lib().gbm_matrix_upload_packed(ptr(codes), n, p, n, byref(h)))
+        m = cls(h, n, p)
+        m.packed = True
+        return m
+
+    def pack(self):
+        """One-byte-per-genotype copy of this matrix (``gbm_matrix_pack``), or None when some
+        element is not exactly a dosage code (then keep using the Float64 matrix)."""
+        h, bad = c_void_p(), c_int64()
+        check(_lib.load().gbm_matrix_pack(self._h, byref(h), byref(bad)))
+        if not h.value:
+            return None
+        m = DeviceMatrix(h, self.n, self.p)
+        m.packed = True
+        return m
 
     # ---- housekeeping ----------------------------------------------------------------
     def info(self):
@@ -251,9 +274,23 @@ def kstd_pc1_device(dK_ptr: int, n: int):
     return pc, ms.value
 
 
-def scan_host(A, Y, C=None, model: int = _lib.MODEL_OLS, flags: int = 0):
+def pack_host(A: np.ndarray):
+    """Host-side packer (all cores): returns (codes uint8 n x p, n_inexact)."""
+    A = _f64(A)
+    n, p = A.shape
+    out = np.empty((n, p), dtype=np.uint8, order="F")
+    bad = c_int64()
+    check(_lib.load().gbm_pack_host(ptr(A), n, p, n, ptr(out), n, byref(bad)))
+    return out, int(bad.value)
+
+
+def scan_host(A, Y, C=None, model: int = _lib.MODEL_OLS, flags: int = 0, pack: bool = True):
     """End-to-end scan from a HOST matrix (pinned or pageable): H2D in column blocks
-    overlapped with the scan kernel."""
+    overlapped with the scan kernel.  pack=True (default): blocks whose elements are all
+    dosage codes are packed to one byte per genotype by the host cores before crossing PCIe
+    (identical results); pack=False forces plain Float64 copies."""
+    if not pack:
+        flags |= _lib.SCAN_HOST_NO_PACK
     if isinstance(A, np.ndarray):
         A = _f64(A)
         n, p = A.shape

@@ -51,6 +51,7 @@ extern "C" {
 #define GBM_MODEL_LMM 1 /* gwaslmm z statistic, p-values from Normal()   (gwas.jl:385, :392) */
 /* scan flags */
 #define GBM_PVALUE_TWO_SIDED 1 /* default is the one-sided upper tail of |stat| */
+#define GBM_SCAN_HOST_NO_PACK 4 /* gbm_scan_host: never pack blocks to 1-byte codes on the host (default: auto) */
 
 /* synthetic generator kinds (oracle/synth.py defines the arithmetic) */
 #define GBM_KIND_DIPLOID 0
@@ -92,6 +93,16 @@ int gbm_matrix_upload_indexed(const double* A, int64_t n0, int64_t p0, int64_t l
 int gbm_matrix_wrap(double* dA, int64_t n, int64_t p, int64_t lda, gbm_matrix** out);
 /* synthetic columns col0 .. col0+p-1 of the counter-based generator, made on the device */
 int gbm_matrix_generate(uint64_t seed, int64_t n, int64_t p, int64_t col0, int kind, gbm_matrix** out);
+/* Compact storage: one byte per genotype, code c in [0,240], a = c/240.
+ * gbm_matrix_pack converts a resident Float64 matrix; *out is set only when EVERY element is
+ * exactly a code (fl(c/240) == a), otherwise *out = NULL and *n_inexact > 0 (use the Float64
+ * matrix).  Packed handles work with gbm_colstats, gbm_scan*, gbm_grm*, gbm_lmm_plan_run and
+ * gbm_matrix_download (which returns Float64); results equal the Float64 path's.
+ * gbm_matrix_upload_packed takes codes that are already compact on the host (n x p, pitch ld). */
+int gbm_matrix_pack(const gbm_matrix* m, gbm_matrix** out, int64_t* n_inexact);
+int gbm_matrix_upload_packed(const uint8_t* codes, int64_t n, int64_t p, int64_t ld, gbm_matrix** out);
+/* multi-threaded host packer (all cores of the calling process' affinity mask) */
+int gbm_pack_host(const double* A, int64_t n, int64_t p, int64_t lda, uint8_t* out, int64_t ldo, int64_t* n_inexact);
 int gbm_matrix_download(const gbm_matrix* m, int64_t j0, int64_t ncols, double* dst, int64_t ldd);
 int gbm_matrix_info(const gbm_matrix* m, int64_t* n, int64_t* p, int64_t* lda, double** device_ptr);
 int gbm_matrix_free(gbm_matrix* m);
@@ -153,7 +164,11 @@ int gbm_scan_plan_run(gbm_scan_plan* plan, double* beta, double* se, double* sta
 int gbm_scan_plan_free(gbm_scan_plan* plan);
 
 /* One call from host memory to results (the end-to-end path): uploads A in column blocks
- * through pinned staging while the previous block is scanned. Same outputs as gbm_scan. */
+ * through pinned staging while the previous block is scanned. Same outputs as gbm_scan.
+ * By default each block is first packed to 1-byte dosage codes by the host cores (exactness-
+ * checked; the first block that is not all codes switches the call to plain Float64 copies), so
+ * 8x fewer bytes cross PCIe for dosage data with identical results; GBM_SCAN_HOST_NO_PACK
+ * disables that. */
 int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const double* Y, int64_t T, int64_t ldy,
                   const double* C, int64_t k, int64_t ldc, int model, int flags, double* beta, double* se,
                   double* stat, double* neglog10p, double* mean, double* sd, uint8_t* keep);

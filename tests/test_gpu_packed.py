@@ -1,0 +1,121 @@
+"""GPU parity tests for the compact (one byte per genotype) storage path (SURVEY.md 8f
+rank 3): every result must equal the Float64 path's on the same data."""
+import numpy as np
+import pytest
+
+from oracle import gwas_oracle as go, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(seed, n, p, kind):
+    A = synth.block(seed, n, 0, p, kind)
+    y = synth.phenotype(seed, n, p, kind)
+    ys = (y - y.mean()) / y.std(ddof=1)
+    rng = np.random.default_rng(seed)
+    pc = rng.normal(size=n)
+    return A, ys, pc
+
+
+@pytest.mark.parametrize("n,p,kind", [(300, 1000, synth.KIND_TETRAPLOID), (1025, 333, synth.KIND_DIPLOID),
+                                      (7, 5, synth.KIND_DIPLOID), (2049, 64, synth.KIND_TETRAPLOID),
+                                      (10000, 257, synth.KIND_DIPLOID)])
+def test_packed_scan_equals_float64_scan(gbm, n, p, kind):
+    A, ys, pc = _problem(3, n, p, kind)
+    dm = gbm.DeviceMatrix.upload(A)
+    pk = dm.pack()
+    assert pk is not None and pk.packed
+    assert np.array_equal(pk.download(), A)  # decode is exact
+    st_f, st_p = dm.colstats(), pk.colstats()
+    assert np.array_equal(st_f["idx_cols"], st_p["idx_cols"])
+    assert np.array_equal(st_f["keep"], st_p["keep"])
+    assert st_f["min_nonzero_kept"] == st_p["min_nonzero_kept"]
+    np.testing.assert_allclose(st_p["mean"], st_f["mean"], rtol=1e-14, atol=1e-16)
+    np.testing.assert_allclose(st_p["sd"], st_f["sd"], rtol=1e-13, atol=1e-16)
+    for model in (0, 1):
+        a = dm.scan(ys, pc[:, None], model=model)
+        b = pk.scan(ys, pc[:, None], model=model)
+        keep = a["keep"]
+        assert np.array_equal(keep, b["keep"])
+        for key in ("beta", "se", "stat"):
+            scale = np.nanmax(np.abs(a[key][keep]))
+            assert np.nanmax(np.abs(a[key][keep] - b[key][keep])) < 1e-11 * max(scale, 1e-300), key
+        assert np.nanmax(np.abs(a["neglog10p"][keep] - b["neglog10p"][keep])) < 1e-9
+        assert np.all(np.isnan(b["stat"][~keep]))
+    # oracle, directly
+    mu, v = go.column_std(A)
+    keep = v > go.EPS
+    if n > 4:
+        pcn = pc - pc.mean()
+        ref = go.scan_closed_form(A[:, keep], ys, pcn / np.linalg.norm(pcn))
+        got = pk.scan(ys, pc[:, None], model=1)["stat"][keep, 0]
+        assert np.max(np.abs(got - ref["stat_lmm"]) / np.maximum(np.abs(ref["stat_lmm"]), 1e-3 * np.abs(ref["stat_lmm"]).max())) < 1e-9
+    dm.free()
+    pk.free()
+
+
+def test_pack_refuses_inexact_values(gbm):
+    A = synth.block(3, 200, 0, 50, synth.KIND_CONTINUOUS)  # k/4096 grid: not all multiples of 1/240
+    dm = gbm.DeviceMatrix.upload(A)
+    assert dm.pack() is None
+    dm.free()
+    B = synth.block(3, 200, 0, 50, synth.KIND_DIPLOID)
+    B[17, 3] = 0.3000000001
+    dm = gbm.DeviceMatrix.upload(B)
+    assert dm.pack() is None
+    dm.free()
+    codes, bad = gbm.pack_host(B)
+    assert bad == 1
+    codes, bad = gbm.pack_host(synth.block(3, 200, 0, 50, synth.KIND_TETRAPLOID))
+    assert bad == 0 and set(np.unique(codes)) <= {0, 60, 120, 180, 240}
+    # thirds and sixths are codes too (hexaploid levels), as the doubles k/6
+    H = np.asfortranarray(np.random.default_rng(0).integers(0, 7, size=(50, 20)) / 6.0)
+    codes, bad = gbm.pack_host(H)
+    assert bad == 0
+    pk = gbm.DeviceMatrix.upload_packed(codes)
+    assert np.array_equal(pk.download(), H)
+    pk.free()
+
+
+def test_packed_multi_trait_and_grm_and_lmm(gbm):
+    from oracle import lmm_oracle as lo
+
+    n, p = 300, 700
+    A = synth.block(9, n, 0, p, synth.KIND_TETRAPLOID)
+    rng = np.random.default_rng(1)
+    Y = rng.normal(size=(n, 5))
+    C = rng.normal(size=(n, 2))
+    dm = gbm.DeviceMatrix.upload(A)
+    pk = dm.pack()
+    a = dm.scan(Y, C, model=1)
+    b = pk.scan(Y, C, model=1)  # 7 side vectors: decoded blocks + Float64 kernel
+    keep = a["keep"]
+    assert np.nanmax(np.abs(a["stat"][keep] - b["stat"][keep])) < 1e-11
+    K1, _ = dm.grm(1, 4, 0)
+    K2, _ = pk.grm(1, 4, 0)
+    assert np.max(np.abs(K1 - K2)) < 1e-13 * np.abs(K1).max()
+    g = (A - A.mean(axis=0)) @ rng.normal(size=p)
+    y = g / g.std() + rng.normal(size=n)
+    plan = gbm.LmmPlan(go.grm_simple(A), y)
+    r1 = plan.run(dm)
+    r2 = plan.run(pk)
+    plan.free()
+    assert np.nanmax(np.abs(r1["stat"] - r2["stat"])) < 1e-10
+    dm.free()
+    pk.free()
+
+
+@pytest.mark.parametrize("kind,expect_packed", [(synth.KIND_DIPLOID, True), (synth.KIND_CONTINUOUS, False)])
+def test_scan_host_pack_flag(gbm, kind, expect_packed):
+    n, p = 1000, 9000
+    A, ys, pc = _problem(13, n, p, kind)
+    a = gbm.scan_host(A, ys, pc[:, None], model=1, pack=False)
+    b = gbm.scan_host(A, ys, pc[:, None], model=1)  # auto-pack is the default
+    packed_blocks = gbm.last_timing()["launches"]
+    assert (packed_blocks > 0) == expect_packed
+    keep = a["keep"]
+    assert np.array_equal(keep, b["keep"])
+    tol = 1e-11 if expect_packed else 0.0
+    for key in ("beta", "se", "stat", "mean", "sd"):
+        x, y = a[key][keep], b[key][keep]
+        assert np.nanmax(np.abs(x - y)) <= tol * max(1.0, np.nanmax(np.abs(x))), key
