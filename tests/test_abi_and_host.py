@@ -169,3 +169,33 @@ int main(int argc, char** argv) {
             assert np.max(np.abs(got[:, 1] - want_z)) < 1e-6
             ok = want_t < 300
             assert np.max(np.abs(10.0 ** (want_t[ok] - got[ok, 0]) - 1.0)) < 1e-9, df
+
+
+def test_host_packer_without_gpu():
+    """gbm_pack_host is pure host code (AVX2 / scalar, thread pool): exactness check and codes."""
+    import gbm_b200
+    from oracle import synth
+
+    for kind, levels in ((synth.KIND_DIPLOID, {0, 120, 240}), (synth.KIND_TETRAPLOID, {0, 60, 120, 180, 240})):
+        A = synth.block(5, 1037, 0, 203, kind)  # n not a multiple of 8: scalar tail after the AVX2 body
+        codes, bad = gbm_b200.pack_host(A)
+        assert bad == 0 and set(np.unique(codes)) <= levels
+        assert np.array_equal(codes.astype(np.float64) / 240.0, A)
+    rng = np.random.default_rng(0)
+    H = np.asfortranarray(rng.integers(0, 7, size=(333, 17)) / 6.0)  # hexaploid levels k/6 as doubles
+    codes, bad = gbm_b200.pack_host(H)
+    assert bad == 0 and np.array_equal(codes.astype(np.float64) / 240.0, H)
+    for k in (3, 5, 8, 10, 12):
+        L = np.asfortranarray(rng.integers(0, k + 1, size=(64, 9)) / float(k))
+        assert gbm_b200.pack_host(L)[1] == 0
+    # anything that is not exactly a code is counted
+    B = synth.block(5, 500, 0, 40, synth.KIND_DIPLOID)
+    B[3, 7] = 0.5000000000000001
+    B[499, 39] = np.nan
+    B[0, 0] = 1.5
+    B[10, 10] = -0.5
+    assert gbm_b200.pack_host(B)[1] == 4
+    C = synth.block(5, 100, 0, 30, synth.KIND_CONTINUOUS)
+    _, bad = gbm_b200.pack_host(C)
+    want = int(np.sum((np.rint(C * 240.0) / 240.0) != C))
+    assert bad == want and bad > 0
