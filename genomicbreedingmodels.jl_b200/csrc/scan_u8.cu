@@ -20,6 +20,7 @@
 //
 // Algorithmic bytes: n per marker.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -56,12 +57,43 @@ struct U8Params {
   double* rec;
 };
 
-__device__ __forceinline__ double code_to_double(uint32_t c) {
-  // 2^52 + c is exactly representable; subtracting 2^52 leaves c
-  return __hiloint2double(0x43300000, static_cast<int>(c)) - 4503599627370496.0;
+// byte k (0..3) of a 32-bit word as a double, two ways (the kernel mixes them to balance the
+// conversion pipe against the FP64 pipe; U8_I2F_BYTES of every 8 codes take the first route):
+//  - bfe + cvt: ptxas fuses the pair into ONE `I2F.F64.U8 Rd, Ra.Bk`
+//  - PRMT into the low word of 2^52 (exactly representable up to 2^52 + 255) and one DADD
+template <int K>
+__device__ __forceinline__ double byte_to_double_i2f(uint32_t x) {
+  uint32_t t;
+  double d;
+  asm("bfe.u32 %0, %1, %2, 8;" : "=r"(t) : "r"(x), "n"(8 * K));
+  asm("cvt.rn.f64.u32 %0, %1;" : "=d"(d) : "r"(t));
+  return d;
 }
+template <int K>
+__device__ __forceinline__ double byte_to_double_magic(uint32_t x) {
+  const uint32_t code = __byte_perm(x, 0, 0x4440 | K);
+  return __hiloint2double(0x43300000, static_cast<int>(code)) - 4503599627370496.0;
+}
+template <int K, int NI>  // K = 0..7: byte of the 64-bit word (lo, hi); NI bytes go through I2F
+__device__ __forceinline__ double code_as_double(uint32_t lo, uint32_t hi) {
+  const uint32_t x = K < 4 ? lo : hi;
+  if constexpr ((K % 8) * NI / 8 != ((K % 8) + 1) * NI / 8)  // spreads the NI I2F bytes evenly over the 8
+    return byte_to_double_i2f<(K & 3)>(x);
+  else
+    return byte_to_double_magic<(K & 3)>(x);
+}
+template <int K, int NI, int M_>
+struct DotBytes {
+  static __device__ __forceinline__ void run(uint32_t lo, uint32_t hi, const double (&q)[M_ > 0 ? M_ : 1][8],
+                                             double* dots) {
+    const double cd = code_as_double<K, NI>(lo, hi);
+#pragma unroll
+    for (int m = 0; m < M_; ++m) dots[m] = fma(cd, q[m][K], dots[m]);
+    if constexpr (K < 7) DotBytes<K + 1, NI, M_>::run(lo, hi, q, dots);
+  }
+};
 
-template <int C, int M, bool MINNZ>
+template <int C, int M, bool MINNZ, int NI>
 __global__ void __launch_bounds__(kU8Threads, 1)
     scan_sums_u8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmQ,
                         const U8Params prm) {
@@ -162,15 +194,7 @@ __global__ void __launch_bounds__(kU8Threads, 1)
           const uint32_t lo = static_cast<uint32_t>(w), hi = static_cast<uint32_t>(w >> 32);
           s1[c] = __dp4a(lo, 0x01010101u, __dp4a(hi, 0x01010101u, s1[c]));
           s2[c] = __dp4a(lo, lo, __dp4a(hi, hi, s2[c]));
-          if (M > 0) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint32_t code = (k < 4 ? (lo >> (8 * k)) : (hi >> (8 * (k - 4)))) & 0xFFu;
-              const double cd = code_to_double(code);
-#pragma unroll
-              for (int m = 0; m < M; ++m) dots[c * M + m] = fma(cd, q[m][k], dots[c * M + m]);
-            }
-          }
+          if (M > 0) DotBytes<0, NI, M>::run(lo, hi, q, &dots[c * M]);
           if (MINNZ) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -188,22 +212,33 @@ __global__ void __launch_bounds__(kU8Threads, 1)
       }
     }
 
-    // epilogue: exact integer sums -> doubles (< 2^53), then the same reduction tree
-    double v[NVP];
-#pragma unroll
-    for (int i = 0; i < NVP; ++i) v[i] = 0.0;
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      v[c * NSUM + 0] = static_cast<double>(s1[c]);
-      v[c * NSUM + 1] = static_cast<double>(s2[c]);
-#pragma unroll
-      for (int m = 0; m < M; ++m) v[c * NSUM + 2 + m] = dots[c * M + m];
-    }
-    HalvingStep<NVP / 2, 16, NVP>::run(v, lane);
+    // epilogue.  Integer sums: hardware warp reduction (REDUX), sum(c^2) in two 16-bit halves so
+    // the 32-lane total cannot overflow 32 bits whatever n is.  Dots: halving shuffle tree.
     {
-      double* dst = red + (parity * kU8ConsumerWarps + warp) * NVP + halving_base<NVP>(lane);
+      double* dst = red + (parity * kU8ConsumerWarps + warp) * NVP;
 #pragma unroll
-      for (int i = 0; i < NVP / 32; ++i) dst[i] = v[i];
+      for (int c = 0; c < C; ++c) {
+        const uint32_t t1 = __reduce_add_sync(0xffffffffu, s1[c]);
+        const uint32_t t2l = __reduce_add_sync(0xffffffffu, s2[c] & 0xFFFFu);
+        const uint32_t t2h = __reduce_add_sync(0xffffffffu, s2[c] >> 16);
+        if (lane == c) {
+          dst[c * NSUM + 0] = static_cast<double>(t1);
+          dst[c * NSUM + 1] = static_cast<double>(t2l) + 65536.0 * static_cast<double>(t2h);
+        }
+      }
+      if constexpr (M > 0) {
+        constexpr int ND = C * M, NDP = ((ND + 31) / 32) * 32;
+        double v[NDP];
+#pragma unroll
+        for (int i = 0; i < NDP; ++i) v[i] = i < ND ? dots[i < ND ? i : 0] : 0.0;  // ND <= NDP
+        HalvingStep<NDP / 2, 16, NDP>::run(v, lane);
+        const int base = halving_base<NDP>(lane);
+#pragma unroll
+        for (int i = 0; i < NDP / 32; ++i) {
+          const int idx = base + i;
+          if (idx < ND) dst[(idx / M) * NSUM + 2 + (idx % M)] = v[i];
+        }
+      }
     }
     if (MINNZ) {
 #pragma unroll
@@ -256,7 +291,7 @@ __global__ void __launch_bounds__(kU8Threads, 1)
   }
 }
 
-template <int C, int M, bool MINNZ>
+template <int C, int M, bool MINNZ, int NI = 4>
 static void launch_u8_cfg(const uint8_t* A8, int64_t n, int64_t p, int64_t ld8, const double* Q, int64_t ldq,
                           double* rec, int sm_count, cudaStream_t stream) {
   using Cfg = U8Cfg<C, M, MINNZ>;
@@ -276,7 +311,7 @@ static void launch_u8_cfg(const uint8_t* A8, int64_t n, int64_t p, int64_t ld8, 
   prm.chunks = static_cast<int>((n + kU8Rows - 1) / kU8Rows);
   prm.inv_n = 1.0 / static_cast<double>(n);
   prm.rec = rec;
-  auto kern = scan_sums_u8_kernel<C, M, MINNZ>;
+  auto kern = scan_sums_u8_kernel<C, M, MINNZ, NI>;
   GBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int grid = prm.num_tiles < sm_count ? prm.num_tiles : sm_count;
   kern<<<grid, kU8Threads, Cfg::SMEM_BYTES, stream>>>(tmA, tmQ, prm);
@@ -290,7 +325,16 @@ void launch_scan_sums_u8(const uint8_t* A8, int64_t n, int64_t p, int64_t ld8, c
   switch (Mp) {
     case 0: launch_u8_cfg<16, 0, true>(A8, n, p, ld8, Q, ldq, rec, sm_count, stream); break;
     case 1: launch_u8_cfg<16, 1, false>(A8, n, p, ld8, Q, ldq, rec, sm_count, stream); break;
-    case 2: launch_u8_cfg<16, 2, false>(A8, n, p, ld8, Q, ldq, rec, sm_count, stream); break;
+    case 2: {
+      // tuning knob (bytes of every 8 converted by I2F.F64.U8 instead of PRMT + DADD)
+      static const int ni = [] { const char* e = getenv("GBM_U8_I2F"); return e ? atoi(e) : 4; }();
+      if (ni <= 0) launch_u8_cfg<16, 2, false, 0>(A8, n, p, ld8, Q, ldq, rec, sm_count, stream);
+      else if (ni >= 8) launch_u8_cfg<16, 2, false, 8>(A8, n, p, ld8, Q, ldq, rec, sm_count, stream);
+      else if (ni == 2) launch_u8_cfg<16, 2, false, 2>(A8, n, p, ld8, Q, ldq, rec, sm_count, stream);
+      else if (ni == 6) launch_u8_cfg<16, 2, false, 6>(A8, n, p, ld8, Q, ldq, rec, sm_count, stream);
+      else launch_u8_cfg<16, 2, false, 4>(A8, n, p, ld8, Q, ldq, rec, sm_count, stream);
+      break;
+    }
     // more side vectors (multi-trait): the caller decodes blocks and uses the Float64 kernel
     default: GBM_THROW(1, "scan(u8): unsupported side-vector count");
   }
