@@ -7,7 +7,7 @@
 // FP64 tensor-core path of sm_100a: mma.sync m8n8k4.f64 (SASS DMMA.8x8x4; tcgen05 has no
 // FP64 kind).  Persistent CTAs; a producer lane TMA-loads, per 16-marker step, the two
 // 132-row x 16-marker boxes of A for the tile's row block and column block into a
-// 4-deep mbarrier ring.  Boxes are 132 rows (not 128) so that the shared-memory pitch
+// 5-slot mbarrier ring; each slot carries a small metadata word (tile, first/last step).  Boxes are 132 rows (not 128) so that the shared-memory pitch
 // between consecutive markers is 1056 B = 4 (mod 16) doubles: the m8n8k4 fragment
 // loads (lane -> k = lane&3, row = lane>>2) then hit 32 distinct banks per half-warp with
 // no swizzle.  Eight consumer warps (2 x 4) own 64x32 accumulator blocks (64 FP64
@@ -15,11 +15,14 @@
 // element, exact centring without a second copy of A) and issue 32 DMMA per k4 step.
 // Out-of-range rows / markers are zero-filled by TMA.
 //
-// Work items are (tile, marker-slice) pairs, dealt round-robin to the CTAs; the slice
-// count is chosen to keep the last wave full.  With more than one slice partial tiles
+// Work items are (tile, marker-slice) pairs fetched dynamically (atomic counter) by the
+// producer lanes, full tiles before the ragged edge tiles; the slice count is chosen to keep
+// the last wave full.  With more than one slice partial tiles
 // are combined with FP64 atomics (RED.ADD.F64), otherwise by a plain read-modify-write.
 //
 // Algorithmic flops (SYRK convention): n (n+1) p.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -33,17 +36,19 @@ constexpr int kGrmTileBytes = kTilePad * kKT * 8;               // 16896
 constexpr int kGrmStageBytes = 2 * kGrmTileBytes + kKT * 8;     // + mu slice (128 B)
 constexpr int kGrmConsumerWarps = 8;
 constexpr int kGrmThreads = (kGrmConsumerWarps + 1) * 32;
-constexpr int kGrmSmemBytes = kGrmStages * kGrmStageBytes + 2 * kGrmStages * 8 + 128;
+constexpr int kGrmSmemBytes = kGrmStages * kGrmStageBytes + 2 * kGrmStages * 8 + kGrmStages * 16 + 128;
 
 struct GrmParams {
   int64_t n, p;
   int num_tiles;    // lower-triangle tiles
+  int num_full_tiles;  // the first num_full_tiles entries of tile_ij are interior (non-ragged) tiles
   int num_slices;   // split of the marker dimension
   int steps_total;  // ceil(p / 16)
   int steps_per_slice;
   const int2* tile_ij;  // (row block, col block), row block >= col block
   const double* mu;     // zero-padded to steps_total * 16
   double* dK;
+  int* counter;         // dynamic work counter (zeroed before the launch)
 };
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -57,6 +62,7 @@ __global__ void __launch_bounds__(kGrmThreads, 1)
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kGrmStages * kGrmStageBytes);
   uint64_t* empty_bar = full_bar + kGrmStages;
+  int4* meta = reinterpret_cast<int4*>(empty_bar + kGrmStages);  // per slot: {row block, col block, flags, -}
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -71,18 +77,39 @@ __global__ void __launch_bounds__(kGrmThreads, 1)
   const int num_items = prm.num_tiles * prm.num_slices;
 
   if (warp == kGrmConsumerWarps) {
+    // ---- producer lane: dynamic work fetch (atomic counter; items are ordered full tiles
+    // first, ragged edge tiles last), TMA loads, per-slot metadata for the MMA warps ----
     if (lane == 0) {
       prefetch_tensormap(&tmA);
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int tile = item % prm.num_tiles, slice = item / prm.num_tiles;
+      for (;;) {
+        const int item = atomicAdd(prm.counter, 1);
+        if (item >= num_items) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          meta[stage] = make_int4(0, 0, -1, 0);  // sentinel: no more work
+          mbar_arrive(&full_bar[stage]);
+          break;
+        }
+        // all (full tile, slice) items first, slice-major so neighbours share the marker range
+        // in L2; then the (edge tile, slice) items
+        int tile, slice;
+        const int full_items = prm.num_full_tiles * prm.num_slices;
+        if (item < full_items) {
+          slice = item / prm.num_full_tiles;
+          tile = item - slice * prm.num_full_tiles;
+        } else {
+          const int r = item - full_items, n_edge = prm.num_tiles - prm.num_full_tiles;
+          slice = r / n_edge;
+          tile = prm.num_full_tiles + (r - slice * n_edge);
+        }
         const int2 ij = prm.tile_ij[tile];
         const int s0 = slice * prm.steps_per_slice;
         const int s1 = min(s0 + prm.steps_per_slice, prm.steps_total);
         for (int s = s0; s < s1; ++s) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* dst = smem + stage * kGrmStageBytes;
+          meta[stage] = make_int4(ij.x, ij.y, (s == s0 ? 1 : 0) | (s == s1 - 1 ? 2 : 0), 0);
           mbar_arrive_expect_tx(&full_bar[stage], kGrmStageBytes);
           tma_load_2d(dst, &tmA, ij.x * kTile, s * kKT, &full_bar[stage], kEvictNormal);
           tma_load_2d(dst + kGrmTileBytes, &tmA, ij.y * kTile, s * kKT, &full_bar[stage], kEvictNormal);
@@ -102,41 +129,66 @@ __global__ void __launch_bounds__(kGrmThreads, 1)
   const int g = lane >> 2, t = lane & 3;      // fragment row / k index
   int stage = 0;
   uint32_t phase = 0;
-  for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-    const int tile = item % prm.num_tiles, slice = item / prm.num_tiles;
-    const int2 ij = prm.tile_ij[tile];
-    const int s0 = slice * prm.steps_per_slice;
-    const int s1 = min(s0 + prm.steps_per_slice, prm.steps_total);
-
+  for (;;) {
+    // ---- first step of a work item (or the sentinel) ----
+    mbar_wait(&full_bar[stage], phase);
+    int4 md = meta[stage];
+    if (md.z < 0) break;
+    const int bi = md.x, bj = md.y;
     double acc[8][4][2];
 #pragma unroll
     for (int mt = 0; mt < 8; ++mt)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    // Edge tiles: 8-row groups of this warp's block that lie beyond n hold only TMA zero-fill;
+    // skipping them (warp-uniform) makes a ragged last tile row/column cost what it uses.
+    const int64_t rows_left = prm.n - (static_cast<int64_t>(bi) * kTile + wm * 64);
+    const int64_t cols_left = prm.n - (static_cast<int64_t>(bj) * kTile + wn * 32);
+    const int mt_valid = rows_left >= 64 ? 8 : (rows_left <= 0 ? 0 : static_cast<int>((rows_left + 7) / 8));
+    const int nt_valid = cols_left >= 32 ? 4 : (cols_left <= 0 ? 0 : static_cast<int>((cols_left + 7) / 8));
+    const bool full_tile = (mt_valid == 8) && (nt_valid == 4);
 
-    for (int s = s0; s < s1; ++s) {
-      mbar_wait(&full_bar[stage], phase);
+    for (;;) {  // steps of this item; the slot for the current step is already full
       const double* sI = reinterpret_cast<const double*>(smem + stage * kGrmStageBytes);
       const double* sJ = sI + kTilePad * kKT;
       const double* sMu = sJ + kTilePad * kKT;
       const double* pa = sI + t * kTilePad + wm * 64 + g;
       const double* pb = sJ + t * kTilePad + wn * 32 + g;
+      if (full_tile) {
 #pragma unroll
-      for (int kk = 0; kk < kKT / 4; ++kk) {
-        // Only the column-block operand is centred: sum_j a_ij (a_i'j - mu_j) = Kc[i,i'] + w_i'
-        // with w = (A - 1 mu')mu, removed by grm_wcorrect_kernel.  w has the magnitude of the
-        // centred entries themselves, so nothing cancels (unlike A A' - ...), and the MMA loop
-        // carries 4 DADD instead of 12 per 32 DMMA.
-        const double mu = sMu[kk * 4 + t];
-        double a[8], b[4];
+        for (int kk = 0; kk < kKT / 4; ++kk) {
+          // Only the column-block operand is centred: sum_j a_ij (a_i'j - mu_j) = Kc[i,i'] + w_i'
+          // with w = (A - 1 mu')mu, removed by grm_wcorrect_kernel.  w has the magnitude of the
+          // centred entries themselves, so nothing cancels (unlike A A' - ...), and the MMA loop
+          // carries 4 DADD instead of 12 per 32 DMMA.
+          const double mu = sMu[kk * 4 + t];
+          double a[8], b[4];
 #pragma unroll
-        for (int mt = 0; mt < 8; ++mt) a[mt] = pa[kk * 4 * kTilePad + mt * 8];
+          for (int mt = 0; mt < 8; ++mt) a[mt] = pa[kk * 4 * kTilePad + mt * 8];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) b[nt] = pb[kk * 4 * kTilePad + nt * 8] - mu;
+          for (int nt = 0; nt < 4; ++nt) b[nt] = pb[kk * 4 * kTilePad + nt * 8] - mu;
 #pragma unroll
-        for (int mt = 0; mt < 8; ++mt)
+          for (int mt = 0; mt < 8; ++mt)
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+            for (int nt = 0; nt < 4; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+        }
+      } else if (mt_valid > 0 && nt_valid > 0) {
+#pragma unroll
+        for (int kk = 0; kk < kKT / 4; ++kk) {
+          const double mu = sMu[kk * 4 + t];
+          double b[4];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) b[nt] = pb[kk * 4 * kTilePad + nt * 8] - mu;
+#pragma unroll
+          for (int mt = 0; mt < 8; ++mt) {
+            if (mt < mt_valid) {
+              const double a = pa[kk * 4 * kTilePad + mt * 8];
+#pragma unroll
+              for (int nt = 0; nt < 4; ++nt)
+                if (nt < nt_valid) dmma884(acc[mt][nt][0], acc[mt][nt][1], a, b[nt]);
+            }
+          }
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[stage]);
@@ -144,11 +196,14 @@ __global__ void __launch_bounds__(kGrmThreads, 1)
         stage = 0;
         phase ^= 1u;
       }
+      if (md.z & 2) break;  // that was the item's last step
+      mbar_wait(&full_bar[stage], phase);
+      md = meta[stage];
     }
 
     // epilogue: accumulate the 64x32 block into dK (column-major, ld = n)
-    const int64_t row_base = static_cast<int64_t>(ij.x) * kTile + wm * 64 + g;
-    const int64_t col_base = static_cast<int64_t>(ij.y) * kTile + wn * 32 + 2 * t;
+    const int64_t row_base = static_cast<int64_t>(bi) * kTile + wm * 64 + g;
+    const int64_t col_base = static_cast<int64_t>(bj) * kTile + wn * 32 + 2 * t;
     const bool atomic = prm.num_slices > 1;
 #pragma unroll
     for (int mt = 0; mt < 8; ++mt) {
@@ -268,11 +323,22 @@ void launch_grm_accumulate(const double* A, int64_t n, int64_t p, int64_t lda, c
   // tile table
   int2* h_ij = nullptr;
   GBM_CUDA(cudaMallocHost(&h_ij, sizeof(int2) * num_tiles));
+  // full tiles first, ragged edge tiles (last row/column block) last: with the dynamic fetch the
+  // cheap edge tiles fill the tail of the schedule
   int q = 0;
-  for (int i = 0; i < nb; ++i)
-    for (int j = 0; j <= i; ++j) h_ij[q++] = make_int2(i, j);
+  const bool ragged = (n % kTile) != 0;
+  for (int pass = 0; pass < 2; ++pass)
+    for (int i = 0; i < nb; ++i)
+      for (int j = 0; j <= i; ++j) {
+        const bool edge = ragged && (i == nb - 1);  // j <= i, so an edge column block implies an edge row block
+        if ((pass == 0) != edge) h_ij[q++] = make_int2(i, j);
+      }
+  const int num_full_tiles = ragged ? num_tiles - nb : num_tiles;
   int2* d_ij = nullptr;
+  int* d_counter = nullptr;
   GBM_CUDA(cudaMallocAsync(&d_ij, sizeof(int2) * num_tiles, stream));
+  GBM_CUDA(cudaMallocAsync(&d_counter, sizeof(int), stream));
+  GBM_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(int), stream));
   GBM_CUDA(cudaMemcpyAsync(d_ij, h_ij, sizeof(int2) * num_tiles, cudaMemcpyHostToDevice, stream));
 
   alignas(64) CUtensorMap tmA;
@@ -282,19 +348,22 @@ void launch_grm_accumulate(const double* A, int64_t n, int64_t p, int64_t lda, c
   prm.n = n;
   prm.p = p;
   prm.num_tiles = num_tiles;
+  prm.num_full_tiles = num_full_tiles;
   prm.num_slices = num_slices;
   prm.steps_total = steps_total;
   prm.steps_per_slice = steps_per_slice;
   prm.tile_ij = d_ij;
   prm.mu = mu;
   prm.dK = dK;
-  GBM_CUDA(cudaFuncSetAttribute(grm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGrmSmemBytes));
+  prm.counter = d_counter;
   const int64_t items = static_cast<int64_t>(num_tiles) * num_slices;
   const int grid = static_cast<int>(items < sm_count ? items : sm_count);
+  GBM_CUDA(cudaFuncSetAttribute(grm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGrmSmemBytes));
   grm_dmma_kernel<<<grid, kGrmThreads, kGrmSmemBytes, stream>>>(tmA, prm);
   GBM_CUDA(cudaGetLastError());
   if (centred) launch_grm_wcorrection(A, n, p, lda, mu, dK, stream);
   GBM_CUDA(cudaFreeAsync(d_ij, stream));
+  GBM_CUDA(cudaFreeAsync(d_counter, stream));
   GBM_CUDA(cudaStreamSynchronize(stream));  // h_ij must outlive the async copy
   GBM_CUDA(cudaFreeHost(h_ij));
 }

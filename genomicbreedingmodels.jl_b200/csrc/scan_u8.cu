@@ -31,8 +31,9 @@ namespace gbm {
 constexpr int kU8ConsumerWarps = 4;
 constexpr int kU8Rows = kU8ConsumerWarps * 32 * 8;  // rows per stage: every consumer lane owns 8 rows
 constexpr int kU8ConsumerThreads = kU8ConsumerWarps * 32;
-constexpr int kU8Threads = kU8ConsumerThreads + 32;
-constexpr int kU8SmemBudget = 200 * 1024;
+constexpr int kU8Threads = kU8ConsumerThreads;   // no producer warp: lane 0 of warp 0 refills the ring
+constexpr int kU8CtasPerSm = 2;                  // 4 warps x 2 CTAs = 2 warps per scheduler, <= 255 registers
+constexpr int kU8SmemBudget = 100 * 1024;
 constexpr double kLevels = 240.0;
 
 template <int C, int M, bool MINNZ>
@@ -94,7 +95,7 @@ struct DotBytes {
 };
 
 template <int C, int M, bool MINNZ, int NI>
-__global__ void __launch_bounds__(kU8Threads, 1)
+__global__ void __launch_bounds__(kU8Threads, kU8CtasPerSm)
     scan_sums_u8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmQ,
                         const U8Params prm) {
   using Cfg = U8Cfg<C, M, MINNZ>;
@@ -116,37 +117,34 @@ __global__ void __launch_bounds__(kU8Threads, 1)
   }
   __syncthreads();
 
-  if (warp == kU8ConsumerWarps) {
-    if (lane == 0) {
-      prefetch_tensormap(&tmA);
-      if (M > 0) prefetch_tensormap(&tmQ);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
-        for (int chunk = 0; chunk < prm.chunks; ++chunk) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
-          uint8_t* dst = ring + stage * Cfg::STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(dst, &tmA, chunk * (kU8Rows / 8), tile * C, &full_bar[stage], kEvictFirst);
-          if (M > 0) {
+  // Flat iteration space of this CTA: (tile, chunk) pairs, tile = blockIdx.x + k * gridDim.x.
+  const int my_tiles = (prm.num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                       static_cast<int>(gridDim.x);
+  const int total_iters = my_tiles * prm.chunks;
+  auto issue = [&](int j) {  // called by thread 0 only: TMA loads of flat iteration j into its ring slot
+    const int tile = static_cast<int>(blockIdx.x) + (j / prm.chunks) * static_cast<int>(gridDim.x);
+    const int chunk = j % prm.chunks;
+    const int st = j % STAGES;
+    uint8_t* dst = ring + st * Cfg::STAGE_BYTES;
+    mbar_arrive_expect_tx(&full_bar[st], Cfg::STAGE_BYTES);
+    tma_load_2d(dst, &tmA, chunk * (kU8Rows / 8), tile * C, &full_bar[st], kEvictFirst);
+    if (M > 0) {
 #pragma unroll
-            for (int b = 0; b < kU8Rows / 256; ++b)  // Q boxes are 256 rows x M, laid out [b][m][256]
-              tma_load_2d(dst + Cfg::A_BYTES + b * 256 * M * 8, &tmQ, chunk * kU8Rows + b * 256, 0,
-                          &full_bar[stage], kEvictLast);
-          }
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1u;
-          }
-        }
-      }
+      for (int b = 0; b < kU8Rows / 256; ++b)  // Q boxes are 256 rows x M, laid out [b][m][256]
+        tma_load_2d(dst + Cfg::A_BYTES + b * 256 * M * 8, &tmQ, chunk * kU8Rows + b * 256, 0, &full_bar[st],
+                    kEvictLast);
     }
-    return;
+  };
+  if (tid == 0) {
+    prefetch_tensormap(&tmA);
+    if (M > 0) prefetch_tensormap(&tmQ);
+    for (int j = 0; j < STAGES && j < total_iters; ++j) issue(j);
   }
 
   int stage = 0;
   uint32_t phase = 0;
   int parity = 0;
+  int it = 0;  // flat iteration index
   const int r = 8 * tid;  // this lane's 8 rows inside a 1024-row chunk
   for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x, parity ^= 1) {
     uint32_t s1[C], s2[C];
@@ -206,6 +204,17 @@ __global__ void __launch_bounds__(kU8Threads, 1)
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      if (tid == 0 && it >= 1) {
+        // refill one slot behind: the slot of iteration it-1 has been released by every warp by
+        // now (or will be within a few cycles), so this wait does not hold warp 0 back
+        const int j = it - 1 + STAGES;
+        if (j < total_iters) {
+          const int pst = (it - 1) % STAGES;
+          mbar_wait(&empty_bar[pst], static_cast<uint32_t>(((it - 1) / STAGES) & 1));
+          issue(j);
+        }
+      }
+      ++it;
       if (++stage == STAGES) {
         stage = 0;
         phase ^= 1u;
@@ -313,7 +322,8 @@ static void launch_u8_cfg(const uint8_t* A8, int64_t n, int64_t p, int64_t ld8, 
   prm.rec = rec;
   auto kern = scan_sums_u8_kernel<C, M, MINNZ, NI>;
   GBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  const int grid = prm.num_tiles < sm_count ? prm.num_tiles : sm_count;
+  const int max_grid = sm_count * kU8CtasPerSm;
+  const int grid = prm.num_tiles < max_grid ? prm.num_tiles : max_grid;
   kern<<<grid, kU8Threads, Cfg::SMEM_BYTES, stream>>>(tmA, tmQ, prm);
   GBM_CUDA(cudaGetLastError());
 }

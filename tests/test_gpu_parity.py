@@ -285,10 +285,15 @@ def test_scan_host_matches_resident_scan(gbm):
     dm = gbm.DeviceMatrix.upload(A)
     a = dm.scan(ys, pc[:, None], model=1)
     dm.free()
-    b = gbm.scan_host(A, ys, pc[:, None], model=1)
+    b = gbm.scan_host(A, ys, pc[:, None], model=1, pack=False)  # plain Float64 blocks: bit-identical
     for key in ("beta", "se", "stat", "neglog10p", "mean", "sd"):
         assert np.array_equal(a[key], b[key], equal_nan=True), key
     assert np.array_equal(a["keep"], b["keep"])
+    c = gbm.scan_host(A, ys, pc[:, None], model=1)  # default: host-packed blocks, same results to rounding
+    keep = a["keep"]
+    assert np.array_equal(keep, c["keep"])
+    for key in ("beta", "se", "stat"):
+        assert np.nanmax(np.abs(a[key][keep] - c[key][keep])) < 1e-11 * np.nanmax(np.abs(a[key][keep])), key
 
 
 def test_scan_is_deterministic_and_shard_invariant(gbm):
