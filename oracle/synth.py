@@ -67,10 +67,11 @@ def column_params(seed: int, j):
     return thr, fixed, level
 
 
-def block(seed: int, n: int, j0: int, ncols: int, kind: int) -> np.ndarray:
+def block(seed: int, n: int, j0: int, ncols: int, kind: int, rows=None) -> np.ndarray:
     """Columns j0 .. j0+ncols-1 (0-based, global column index) as an (n, ncols)
-    Fortran-ordered Float64 array."""
-    i = np.arange(n, dtype=np.uint64)[:, None]
+    Fortran-ordered Float64 array.  ``rows`` (optional 0-based row indices) restricts the
+    output to those rows, (len(rows), ncols): values depend on (seed, row, column) only."""
+    i = (np.arange(n, dtype=np.uint64) if rows is None else np.asarray(rows, dtype=np.uint64))[:, None]
     j = (np.arange(ncols, dtype=np.uint64) + np.uint64(j0))[None, :]
     thr, fixed, level = column_params(seed, j)
     hcol = _col_hash(seed, j)

@@ -469,3 +469,47 @@ def test_config4_tetraploid_pipeline_reduced(gbm):
     assert f.extras["ploidy"] == 4 == prep.ploidy
     assert np.array_equal(f.extras["idx_cols"], prep.idx_cols)
     assert rel_err(f.b_hat, z_ref) < RTOL
+
+
+def test_full_size_config3_sampled_parity(gbm):
+    """BASELINE configs[2] at full size (n = 10,000 x p = 1,000,000, 80 GB in HBM): the scan's
+    results on columns sampled across the whole range (including byte offsets beyond 2^32)
+    against the oracle on the regenerated columns, the filter count, and the uncentred GRM on
+    entries recomputed on the CPU from regenerated rows."""
+    import torch
+
+    n, p = 10000, 1_000_000
+    free, _ = torch.cuda.mem_get_info(0)
+    if free < 95e9:
+        pytest.skip("needs ~90 GB of free HBM")
+    dm = gbm.DeviceMatrix.generate(42, n, p, synth.KIND_DIPLOID)
+    rng = np.random.default_rng(0)
+    y, pc = rng.normal(size=n), rng.normal(size=n)
+    res = dm.scan(y, pc[:, None], model=1, want=("stat", "beta"))
+    keep = res["keep"]
+    cols = np.unique(np.concatenate([[0, 1, 15, 16, p - 1, p - 2, 536870912 // 10000 + 1], rng.integers(0, p, 48)]))
+    A = np.asfortranarray(np.hstack([synth.block(42, n, int(j), 1, synth.KIND_DIPLOID) for j in cols]))
+    mu, v = go.column_std(A)
+    assert np.array_equal(keep[cols], v > go.EPS)
+    np.testing.assert_allclose(res["mean"][cols], mu, rtol=1e-13, atol=1e-15)
+    pcn = pc - pc.mean()
+    ok = v > go.EPS
+    ref = go.scan_closed_form(A[:, ok], y - y.mean(), pcn / np.linalg.norm(pcn))
+    assert rel_err(res["stat"][cols[ok], 0], ref["stat_lmm"]) < RTOL
+    assert rel_err(res["beta"][cols[ok], 0], ref["beta"]) < RTOL
+    st = dm.colstats()
+    assert st["idx_cols"].size == keep.sum() and np.all(np.diff(st["idx_cols"]) > 0)
+    assert np.array_equal(st["idx_cols"], np.flatnonzero(keep) + 1)
+    # uncentred GRM (A A'/p): a few entries from regenerated rows
+    dK = torch.empty(n * n, dtype=torch.float64, device="cuda:0")
+    dm.grm(0, 2, 1, out=dK)
+    rows = np.array([0, 1, 4999, 9999])
+    R = np.zeros((rows.size, p))
+    for j0 in range(0, p, 50000):
+        R[:, j0:j0 + 50000] = synth.block(42, n, j0, 50000, synth.KIND_DIPLOID, rows=rows)
+    want = (R @ R.T) / p
+    K = dK.view(n, n)  # column-major n x n == K' as a C-order view; K is symmetric
+    rt = torch.as_tensor(rows, device="cuda:0")
+    got = K.index_select(0, rt).index_select(1, rt).cpu().numpy()
+    assert np.max(np.abs(got - want)) < 1e-11 * np.abs(want).max()
+    dm.free()
