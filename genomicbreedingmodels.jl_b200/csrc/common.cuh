@@ -41,6 +41,7 @@ struct State {
   cudaEvent_t stage_copied[2] = {nullptr, nullptr}, stage_consumed[2] = {nullptr, nullptr};
   double h2d_ms = 0, kernel_ms = 0, main_ms = 0, d2h_ms = 0;
   int64_t launches = 0;
+  int64_t packed_blocks = 0;
 };
 State& state();
 void require_ready();

@@ -168,6 +168,7 @@ static void reset_timing() {
   State& st = state();
   st.h2d_ms = st.kernel_ms = st.main_ms = st.d2h_ms = 0.0;
   st.launches = 0;
+  st.packed_blocks = 0;
 }
 
 static void copy_out(void* user, const void* dev, size_t bytes, cudaStream_t s) {
@@ -451,6 +452,7 @@ int gbm_last_timing(gbm_timing* t) {
   t->main_ms = st.main_ms;
   t->d2h_ms = st.d2h_ms;
   t->launches = st.launches;
+  t->packed_blocks = st.packed_blocks;
   GBM_API_END
 }
 
@@ -1166,7 +1168,9 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
   out.bind_all(p, T, beta, se, stat, neglog10p, mean, sd, keep);
   auto passes = build_passes(sv, n, T);
   const std::vector<double*> no_rec;
-  bool pack = (flags & GBM_SCAN_HOST_NO_PACK) == 0 && !is_device_ptr(A);  // auto: pack blocks that are all dosage codes
+  // auto: pack blocks that are all dosage codes -- when this process has enough host cores to
+  // out-run the PCIe link with the packer (8 threads read ~45 GB/s of Float64)
+  bool pack = (flags & GBM_SCAN_HOST_NO_PACK) == 0 && !is_device_ptr(A) && host_threads() >= 8;
   const int kflags = flags & GBM_PVALUE_TWO_SIDED;
   // column blocks of ~256 MB of Float64, double-buffered: the copy engine fills one buffer while the
   // scan kernel streams the other
@@ -1252,7 +1256,7 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
   GBM_CUDA(cudaStreamSynchronize(st.stream));
   GBM_CUDA(cudaStreamSynchronize(st.copy_stream));
   st.kernel_ms = all.ms();  // copy + compute overlapped: wall time of the pipeline on the device
-  st.launches = packed_blocks;  // reported through gbm_last_timing: blocks that went down the packed path
+  st.packed_blocks = packed_blocks;
   (void)total_blocks;
   GBM_API_END
 }

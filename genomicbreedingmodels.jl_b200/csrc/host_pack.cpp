@@ -7,6 +7,7 @@
 // Plain C++ (no CUDA): AVX2 body selected at run time, scalar fallback, persistent workers.
 #include <immintrin.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <condition_variable>
@@ -145,6 +146,9 @@ int host_threads() {
   if (sched_getaffinity(0, sizeof(set), &set) == 0) t = CPU_COUNT(&set);
 #endif
   if (t <= 0) t = static_cast<int>(std::thread::hardware_concurrency());
+  // one process per GPU (torchrun / MPI): share the host cores between the local ranks
+  const char* lws = getenv("LOCAL_WORLD_SIZE");
+  if (lws && atoi(lws) > 1) t /= atoi(lws);
   if (t < 1) t = 1;
   return t > 64 ? 64 : t;
 }

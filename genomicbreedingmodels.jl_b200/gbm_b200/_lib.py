@@ -45,7 +45,7 @@ class CudaError(RuntimeError):
 
 class Timing(ctypes.Structure):
     _fields_ = [("h2d_ms", c_double), ("kernel_ms", c_double), ("main_ms", c_double), ("d2h_ms", c_double),
-                ("launches", c_int64)]
+                ("launches", c_int64), ("packed_blocks", c_int64)]
 
 
 # every exported symbol of include/gbm_b200.h: name -> (restype, argtypes)
@@ -168,7 +168,7 @@ def last_timing() -> dict:
     t = Timing()
     check(load().gbm_last_timing(byref(t)))
     return {"h2d_ms": t.h2d_ms, "kernel_ms": t.kernel_ms, "main_ms": t.main_ms, "d2h_ms": t.d2h_ms,
-            "launches": int(t.launches)}
+            "launches": int(t.launches), "packed_blocks": int(t.packed_blocks)}
 
 
 def device_info() -> dict:

@@ -67,6 +67,7 @@ typedef struct gbm_timing {
   double main_ms;   /* the dominant kernel alone (scan sums / DMMA) */
   double d2h_ms;    /* device -> host copies                        */
   int64_t launches; /* kernels launched by the call                 */
+  int64_t packed_blocks; /* gbm_scan_host: column blocks that crossed PCIe as 1-byte codes */
 } gbm_timing;
 
 /* ---- life cycle ------------------------------------------------------------------- */
