@@ -368,6 +368,7 @@ int gbm_init(int device) {
   if (prop.major != 10)
     GBM_THROW(GBM_ERR_CUDA, std::string("libgbm_b200 is built for sm_100a (B200) only; found ") + prop.name);
   if (st.ready && st.device == device) return GBM_OK;
+  if (st.ready) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_init: already initialised on another device; call gbm_shutdown first");
   st.device = device;
   st.sm_count = prop.multiProcessorCount;
   if (!st.own_stream) GBM_CUDA(cudaStreamCreateWithFlags(&st.own_stream, cudaStreamNonBlocking));
@@ -681,6 +682,48 @@ int gbm_matrix_download(const gbm_matrix* m, int64_t j0, int64_t ncols, double* 
   GBM_CUDA(cudaMemcpy2DAsync(dst, ldd * sizeof(double), m->d + j0 * m->lda, m->lda * sizeof(double),
                              m->n * sizeof(double), ncols, cudaMemcpyDefault, st.stream));
   GBM_CUDA(cudaStreamSynchronize(st.stream));
+  GBM_API_END
+}
+
+int gbm_matrix_download_cols(const gbm_matrix* m, const int64_t* idx_cols, int64_t ncols, int standardise,
+                             double* dst, int64_t ldd) {
+  GBM_API_BEGIN
+  require_ready();
+  if (!m || !dst || ncols < 0 || ldd < m->n) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_matrix_download_cols: bad arguments");
+  if (m->dtype != 0) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_matrix_download_cols: Float64 matrices only");
+  if (!idx_cols && ncols != m->p) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_matrix_download_cols: ncols must be p without an index");
+  if (ncols == 0) return GBM_OK;
+  State& st = state();
+  const int64_t n = m->n;
+  DevBuf<int64_t> dcols(idx_cols ? ncols : 0, st.stream);
+  if (idx_cols) {
+    std::vector<int64_t> hc(ncols);
+    GBM_CUDA(cudaMemcpy(hc.data(), idx_cols, sizeof(int64_t) * ncols, cudaMemcpyDefault));
+    for (int64_t v : hc)
+      if (v < 1 || v > m->p) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_matrix_download_cols: column index out of bounds");
+    GBM_CUDA(cudaMemcpyAsync(dcols.p, hc.data(), sizeof(int64_t) * ncols, cudaMemcpyHostToDevice, st.stream));
+    GBM_CUDA(cudaStreamSynchronize(st.stream));
+  }
+  DevBuf<double> dmean(standardise ? m->p : 0, st.stream), dsd(standardise ? m->p : 0, st.stream);
+  if (standardise) {  // column mean / sd by the streaming kernel (gwas.jl:112, :129)
+    const int stride = scan_record_stride(0, true);
+    DevBuf<double> rec(static_cast<size_t>(m->p) * stride, st.stream);
+    scan_sums_any(m, 0, m->p, nullptr, 0, 0, rec.p);
+    launch_colstats_finalize(rec.p, stride, n, m->p, dmean.p, dsd.p, nullptr, nullptr, st.stream);
+  }
+  // gather (+ standardise) column blocks on the device, copy each block out
+  const int64_t ldt = round_up(n, 16);
+  const int64_t PB = std::max<int64_t>(1, std::min<int64_t>(ncols, (int64_t(256) << 20) / (8 * ldt)));
+  DevBuf<double> tmp(static_cast<size_t>(ldt) * PB, st.stream);
+  for (int64_t c0 = 0; c0 < ncols; c0 += PB) {
+    const int64_t pc = std::min(PB, ncols - c0);
+    launch_gather_standardise(idx_cols ? m->d : m->d + c0 * m->lda, m->lda, n, idx_cols ? dcols.p + c0 : nullptr, pc,
+                              standardise ? (idx_cols ? dmean.p : dmean.p + c0) : nullptr,
+                              standardise ? (idx_cols ? dsd.p : dsd.p + c0) : nullptr, tmp.p, ldt, st.stream);
+    GBM_CUDA(cudaMemcpy2DAsync(dst + c0 * ldd, ldd * sizeof(double), tmp.p, ldt * sizeof(double), n * sizeof(double),
+                               pc, cudaMemcpyDefault, st.stream));
+    GBM_CUDA(cudaStreamSynchronize(st.stream));
+  }
   GBM_API_END
 }
 

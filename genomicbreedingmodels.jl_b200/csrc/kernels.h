@@ -77,6 +77,9 @@ void launch_row_centre(const double* Ks, double* Z, int64_t n, int64_t ld, cudaS
 void launch_gather(const double* src, int64_t lds, const int64_t* rows, int64_t n, const int64_t* cols, int64_t p,
                    double* dst, int64_t ldd, cudaStream_t stream);
 
+void launch_gather_standardise(const double* src, int64_t lds, int64_t n, const int64_t* cols, int64_t ncols,
+                               const double* mean, const double* sd, double* dst, int64_t ldd, cudaStream_t stream);
+
 // gemm_tn.cu --------------------------------------------------------------------------
 // C (M x N, ldc) = A' B with A: K x M (lda), B: K x N (ldb), all column-major, device; lda, ldb even.
 void launch_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M,

@@ -86,4 +86,34 @@ void launch_gather(const double* src, int64_t lds, const int64_t* rows, int64_t 
   GBM_CUDA(cudaGetLastError());
 }
 
+// dst[i, c] = (src[i, cols[c]-1] - mean[cols[c]-1]) / sd[cols[c]-1]   (mean/sd nullable: plain gather)
+// G = (G .- mean(G, dims=1)) ./ v[idx_cols]'  (/root/reference/src/gwas.jl:114, :129) on the device.
+__global__ void __launch_bounds__(256)
+    gather_standardise_kernel(const double* __restrict__ src, int64_t lds, int64_t n, const int64_t* __restrict__ cols,
+                              const double* __restrict__ mean, const double* __restrict__ sd,
+                              double* __restrict__ dst, int64_t ldd) {
+  const int64_t c = blockIdx.y;
+  const int64_t sj = cols ? cols[c] - 1 : c;
+  const double mu = mean ? mean[sj] : 0.0, v = sd ? sd[sj] : 1.0;
+  const double* s = src + sj * lds;
+  double* d = dst + c * ldd;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    d[i] = (mean || sd) ? (s[i] - mu) / v : s[i];
+}
+
+void launch_gather_standardise(const double* src, int64_t lds, int64_t n, const int64_t* cols, int64_t ncols,
+                               const double* mean, const double* sd, double* dst, int64_t ldd, cudaStream_t stream) {
+  if (n <= 0 || ncols <= 0) return;
+  unsigned gx = static_cast<unsigned>((n + 255) / 256);
+  if (gx > 16) gx = 16;
+  for (int64_t c0 = 0; c0 < ncols; c0 += 65535) {
+    const unsigned gy = static_cast<unsigned>(ncols - c0 < 65535 ? ncols - c0 : 65535);
+    gather_standardise_kernel<<<dim3(gx, gy), 256, 0, stream>>>(src, lds, n, cols ? cols + c0 : nullptr, mean, sd,
+                                                                 dst + c0 * ldd, ldd);
+    if (!cols) src += 65535 * lds;
+  }
+  GBM_CUDA(cudaGetLastError());
+}
+
 }  // namespace gbm

@@ -98,6 +98,15 @@ class DeviceMatrix:
         check(_lib.load().gbm_matrix_download(self._h, j0, ncols, ptr(out), self.n))
         return out
 
+    def download_cols(self, idx_cols=None, standardise: bool = False) -> np.ndarray:
+        """G[:, idx_cols] (1-based), optionally column-standardised on the device
+        (/root/reference/src/gwas.jl:114, :129)."""
+        idx = None if idx_cols is None else np.ascontiguousarray(idx_cols, dtype=np.int64)
+        ncols = self.p if idx is None else idx.size
+        out = np.empty((self.n, ncols), dtype=np.float64, order="F")
+        check(_lib.load().gbm_matrix_download_cols(self._h, ptr(idx), ncols, int(standardise), ptr(out), self.n))
+        return out
+
     def free(self):
         if self._h is not None:
             check(_lib.load().gbm_matrix_free(self._h))

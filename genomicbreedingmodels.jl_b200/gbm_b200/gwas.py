@@ -214,9 +214,7 @@ def gwasprep(*, genomes: Genomes, phenomes: Phenomes, idx_entries=None, idx_loci
     pr = _prepare(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type, standardise,
                   need_kstd=True, need_pc1=False)
     try:
-        G = pr.dm.download()[:, pr.idx_cols - 1]  # :114
-        if standardise:  # :129, with the device's mean / sd
-            G = (G - pr.stats["mean"][pr.idx_cols - 1][None, :]) / pr.stats["sd"][pr.idx_cols - 1][None, :]
+        G = pr.dm.download_cols(pr.idx_cols, standardise=standardise)  # :114, :129 on the device
         K = pr.K
         fit = _new_fit(pr)
     finally:

@@ -208,12 +208,11 @@ function gwasprep(;
     idx_trait::Int64 = 1, GRM_type::String = "simple", standardise::Bool = true, verbose::Bool = false,
 )::Tuple{Matrix{Float64},Vector{Float64},Matrix{Float64},Fit}
     pr = prepare(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type, standardise; need_kstd = true, need_pc1 = false)
-    G = Matrix{Float64}(undef, pr.dm.n, pr.dm.p)
-    check(ccall((:gbm_matrix_download, LIBGBM), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64), pr.dm.handle, 0, pr.dm.p, G, pr.dm.n))
-    G = G[:, pr.stats.idx_cols]
-    if standardise
-        G = (G .- pr.stats.mean[pr.stats.idx_cols]') ./ pr.stats.sd[pr.stats.idx_cols]'
-    end
+    # G = G[:, idx_cols]; G = (G .- mean(G, dims=1)) ./ v[idx_cols]'   (src/gwas.jl:114, :129), on the device
+    l = length(pr.stats.idx_cols)
+    G = Matrix{Float64}(undef, pr.dm.n, l)
+    check(ccall((:gbm_matrix_download_cols, LIBGBM), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64, Cint, Ptr{Float64}, Int64),
+                pr.dm.handle, pr.stats.idx_cols, l, standardise ? 1 : 0, G, pr.dm.n))
     fit = newfit(pr)
     free!(pr.dm)
     (G, pr.y, pr.K, fit)

@@ -105,6 +105,11 @@ int gbm_matrix_upload_packed(const uint8_t* codes, int64_t n, int64_t p, int64_t
 /* multi-threaded host packer (all cores of the calling process' affinity mask) */
 int gbm_pack_host(const double* A, int64_t n, int64_t p, int64_t lda, uint8_t* out, int64_t ldo, int64_t* n_inexact);
 int gbm_matrix_download(const gbm_matrix* m, int64_t j0, int64_t ncols, double* dst, int64_t ldd);
+/* G = G[:, idx_cols] and, with standardise != 0, G = (G .- mean(G, dims=1)) ./ std(G, dims=1)'
+ * (/root/reference/src/gwas.jl:114, :129) on the device; dst (host or device) is n x ncols.
+ * idx_cols: 1-based, NULL = all columns. */
+int gbm_matrix_download_cols(const gbm_matrix* m, const int64_t* idx_cols, int64_t ncols, int standardise,
+                             double* dst, int64_t ldd);
 int gbm_matrix_info(const gbm_matrix* m, int64_t* n, int64_t* p, int64_t* lda, double** device_ptr);
 int gbm_matrix_free(gbm_matrix* m);
 
