@@ -452,6 +452,21 @@ def main():
             _, tf = gm.grm(_lib.GRM_SIMPLE, 2, 0, out=dK)
             if i:
                 tfs.append(tf)
+        # the same GRM from the packed (1-byte dosage) copy: exact integer contraction on the
+        # tcgen05 INT8 tensor cores (csrc/grm_i8.cu)
+        i8 = None
+        gk = gm.pack()
+        if gk is not None:
+            tfi = []
+            for i in range(4):
+                _, tf = gk.grm(_lib.GRM_SIMPLE, 2, 0, out=dK)
+                if i:
+                    tfi.append(tf)
+            gk.free()
+            tf8 = float(np.median(tfi))
+            i8 = {"metric": "GRM from 1-byte dosage codes, tcgen05 kind::i8 (exact)", "value": tf8,
+                  "unit": "TFLOP/s-equivalent, n(n+1)p / time (incl. centring passes)",
+                  "ms": gn * (gn + 1) * gp / tf8 / 1e9, "speedup_vs_fp64_dmma": tf8 / float(np.median(tfs))}
         gm.free()
         # cuBLAS DGEMM peak on this box (the practical FP64 tensor roofline)
         a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
@@ -471,6 +486,8 @@ def main():
                        "workload": f"grmsimple n={gn} p={gp} diploid (BASELINE configs[1])",
                        "cublas_dgemm_8192_tflops": best, "frac_of_cublas_dgemm": float(np.median(tfs)) / best,
                        "datasheet_fp64_tflops": 40.0, "frac_of_datasheet": float(np.median(tfs)) / 40.0}
+        if i8 is not None:
+            line["grm_int8"] = i8
 
     if rank == 0 and args.pipeline:
         line["pipeline"] = run_pipeline(gbm_b200, _lib, n, p_loc, j0, ys)

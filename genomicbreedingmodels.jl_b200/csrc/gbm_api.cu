@@ -84,6 +84,20 @@ void make_tensor_map_2d_u64(CUtensorMap* map, const void* base, uint64_t rows64,
   if (r != CUDA_SUCCESS) GBM_THROW(GBM_ERR_CUDA, "cuTensorMapEncodeTiled (u64) failed with code " + std::to_string((int)r));
 }
 
+void make_tensor_map_2d_u8_sw128(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_bytes,
+                                 uint32_t box_rows, uint32_t box_cols) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (ld_bytes & 15u) != 0)
+    GBM_THROW(GBM_ERR_ARGUMENT, "packed matrix must be 16-byte aligned with a pitch that is a multiple of 16");
+  cuuint64_t gdim[2] = {rows, cols};
+  cuuint64_t gstride[1] = {ld_bytes};
+  cuuint32_t box[2] = {box_rows, box_cols};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_tiled()(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) GBM_THROW(GBM_ERR_CUDA, "cuTensorMapEncodeTiled (u8, swizzle 128B) failed with code " + std::to_string((int)r));
+}
+
 static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 static bool is_device_ptr(const void* p) {
@@ -813,6 +827,11 @@ static void column_means_padded(const gbm_matrix* m, double* dmu_pad /* round_up
   st.launches += 2;
 }
 
+static bool use_int8_grm() {
+  static const bool v = [] { const char* e = getenv("GBM_GRM_INT8"); return e ? atoi(e) != 0 : true; }();
+  return v;
+}
+
 static void grm_accumulate_impl(const gbm_matrix* m, int centre, double* dK, double* dsumq /*device, nullable*/,
                                 double* tflops) {
   State& st = state();
@@ -830,6 +849,21 @@ static void grm_accumulate_impl(const gbm_matrix* m, int centre, double* dK, dou
   mainsp.start();
   if (m->dtype == 0) {
     launch_grm_accumulate(m->d, m->n, m->p, m->lda, dmu.p, dK, st.sm_count, st.stream, centre != 0);
+  } else if (use_int8_grm()) {
+    // packed codes: exact integer contraction on the tcgen05 INT8 tensor cores (grm_i8.cu)
+    const int64_t n = m->n;
+    DevBuf<double> dG(static_cast<size_t>(n) * n, st.stream), dS(m->p, st.stream), dU(n, st.stream), dM2(1, st.stream);
+    GBM_CUDA(cudaMemsetAsync(dG.p, 0, sizeof(double) * n * n, st.stream));
+    GBM_CUDA(cudaMemsetAsync(dU.p, 0, sizeof(double) * n, st.stream));
+    GBM_CUDA(cudaMemsetAsync(dM2.p, 0, sizeof(double), st.stream));
+    launch_grm_i8_accumulate(m->d8, n, m->p, m->ld8, dG.p, st.sm_count, st.stream);
+    if (centre) {
+      // dmu holds the column means (a scale): S_j = round(mu_j * n * 240) are the exact code sums
+      launch_code_sums(dmu.p, m->p, n, dS.p, dM2.p, st.stream);
+      launch_rowdot_u8(m->d8, n, m->p, m->ld8, dS.p, dU.p, st.stream);
+    }
+    launch_grm_i8_combine(dG.p, n, dU.p, dM2.p, centre, dK, st.stream);
+    st.launches += 4;
   } else {
     // packed codes: decode column blocks (<= 1 GB of Float64) and accumulate block by block
     const int64_t ldt = round_up(m->n, 16);

@@ -80,6 +80,16 @@ void launch_gather(const double* src, int64_t lds, const int64_t* rows, int64_t 
 void launch_gather_standardise(const double* src, int64_t lds, int64_t n, const int64_t* cols, int64_t ncols,
                                const double* mean, const double* sd, double* dst, int64_t ldd, cudaStream_t stream);
 
+// grm_i8.cu ---------------------------------------------------------------------------
+// dG (n x n, zeroed by the caller) += lower-triangle tiles of C C' for the code matrix C (exact integers)
+void launch_grm_i8_accumulate(const uint8_t* A8, int64_t n, int64_t p, int64_t ld8, double* dG, int sm_count,
+                              cudaStream_t stream);
+void launch_rowdot_u8(const uint8_t* A8, int64_t n, int64_t p, int64_t ld8, const double* S, double* U,
+                      cudaStream_t stream);
+void launch_code_sums(const double* mean, int64_t p, int64_t n, double* S, double* M2, cudaStream_t stream);
+void launch_grm_i8_combine(const double* G, int64_t n, const double* U, const double* M2, int centre, double* dK,
+                           cudaStream_t stream);
+
 // gemm_tn.cu --------------------------------------------------------------------------
 // C (M x N, ldc) = A' B with A: K x M (lda), B: K x N (ldb), all column-major, device; lda, ldb even.
 void launch_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int64_t M,
