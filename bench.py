@@ -545,6 +545,7 @@ def run_pipeline(gbm_b200, _lib, n, p_loc, j0, ys):
         res = dm.scan(ys, pc[:, None], model=_lib.MODEL_LMM)
         out["scan_s"] = time.perf_counter() - t0
         out["scan_kernel_ms"] = _lib.last_timing()["main_ms"]
+        out["scan_timing"] = _lib.last_timing()
         if attempt == "cold":
             out["first_pass_total_s"] = time.perf_counter() - t_all
     out["markers_kept"] = int(st["idx_cols"].size)
@@ -552,6 +553,36 @@ def run_pipeline(gbm_b200, _lib, n, p_loc, j0, ys):
     tot = out["colstats_s"] + out["grm_s"] + out["kstd_pc1_s"] + out["scan_s"]
     out["total_s"] = tot
     out["markers_per_s_whole_gwaslmm"] = p_loc / tot
+    # the same pipeline on the packed (1-byte dosage) copy: u8 scan kernels + exact INT8 tensor-core GRM
+    t0 = time.perf_counter()
+    pk = dm.pack()
+    pack_s = time.perf_counter() - t0
+    if pk is not None:
+        pkd = {"pack_s": pack_s}
+        for attempt in ("cold", "warm"):
+            t0 = time.perf_counter()
+            st2 = pk.colstats()
+            pkd["colstats_s"] = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            _, tf = pk.grm(_lib.GRM_SIMPLE, 2, 0, out=dK)
+            pkd["grm_s"] = time.perf_counter() - t0
+            pkd["grm_tflops_equivalent"] = tf
+            t0 = time.perf_counter()
+            pc2, eig_ms = gbm_b200.kstd_pc1_device(dK.data_ptr(), n)
+            pkd["kstd_pc1_s"] = time.perf_counter() - t0
+            pkd["cusolver_eig_s"] = eig_ms * 1e-3
+            t0 = time.perf_counter()
+            res2 = pk.scan(ys, pc2[:, None], model=_lib.MODEL_LMM)
+            pkd["scan_s"] = time.perf_counter() - t0
+        tot2 = pkd["colstats_s"] + pkd["grm_s"] + pkd["kstd_pc1_s"] + pkd["scan_s"]
+        pkd["total_s"] = tot2
+        pkd["markers_per_s_whole_gwaslmm"] = p_loc / tot2
+        keep = res["keep"]
+        d = np.abs(res2["stat"][keep, 0] - res["stat"][keep, 0])
+        pkd["max_abs_diff_z_vs_float64_pipeline"] = float(np.nanmax(d))
+        pkd["filter_identical"] = bool(np.array_equal(st2["idx_cols"], st["idx_cols"]))
+        out["packed_int8"] = pkd
+        pk.free()
     dm.free()
     return out
 

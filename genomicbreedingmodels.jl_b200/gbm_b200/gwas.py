@@ -143,12 +143,17 @@ def grmploidyaware(genomes: Genomes, ploidy: int = 2, idx_entries=None, idx_loci
 class _Prep:
     """Device-resident state shared by gwasprep / gwasols / gwaslmm."""
 
-    __slots__ = ("dm", "y", "K", "pc1", "stats", "idx_cols", "entries", "populations", "loci_alleles", "trait",
-                 "ploidy", "rows1", "cols1", "eig_ms")
+    __slots__ = ("dm", "packed", "scan_dm", "y", "K", "pc1", "stats", "idx_cols", "entries", "populations",
+                 "loci_alleles", "trait", "ploidy", "rows1", "cols1", "eig_ms")
+
+    def free(self):
+        if getattr(self, "packed", None) is not None:
+            self.packed.free()
+        self.dm.free()
 
 
 def _prepare(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type, standardise, need_kstd,
-             need_pc1) -> _Prep:
+             need_pc1, use_packed: bool = True) -> _Prep:
     rows1, cols1, y = _validate_and_select(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait)  # gwas.jl:93-100
     if GRM_type not in GRM_TYPES:  # :101-107
         raise ArgumentError("Unrecognised `GRM_type`. Please select from:\n\t‣ " + "\n\t‣ ".join(GRM_TYPES))
@@ -161,11 +166,15 @@ def _prepare(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_ty
     subset = rows1 is not None or cols1 is not None
     # G = allele_frequencies[rows, cols] goes straight to the device (prediction.jl:129)
     pr.dm = DeviceMatrix.upload(A, rows1, cols1)
-    pr.stats = pr.dm.colstats()  # v = std(G, dims=1); idx_cols (:112-113)
+    # dosage data (every element an exact ploidy level) also gets a one-byte-per-genotype copy:
+    # the scan then reads 1/8 of the bytes and the GRM runs exactly on the INT8 tensor cores
+    pr.packed = pr.dm.pack() if use_packed else None
+    pr.scan_dm = pr.packed if pr.packed is not None else pr.dm
+    pr.stats = pr.scan_dm.colstats()  # v = std(G, dims=1); idx_cols (:112-113)
     if np.isnan(pr.stats["sd"]).any():
         # Matrix{Float64}(::Matrix{Union{Float64,Missing}}) throws on a missing genotype
         # (prediction.jl:129); a NaN/Inf genotype shows up here as a NaN column sd.
-        pr.dm.free()
+        pr.free()
         raise ErrorException("cannot convert a value of type Missing to Float64")
     pr.idx_cols = pr.stats["idx_cols"]
     r0 = np.arange(A.shape[0]) if rows1 is None else rows1 - 1
@@ -176,13 +185,18 @@ def _prepare(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_ty
     pr.trait = trait
     # GRM on the FULL genomes (:117-126)
     pr.ploidy = None
-    full = pr.dm if not subset else DeviceMatrix.upload(A)
+    full = pr.scan_dm if not subset else DeviceMatrix.upload(A)
+    full_packed = None
+    if subset and use_packed:
+        full_packed = full.pack()
     try:
         if GRM_type == "ploidy-aware":
             pr.ploidy = int(round(1.0 / pr.stats["min_nonzero_kept"]))  # :119
-        K = _grm_of(full, GRM_type, pr.ploidy)
+        K = _grm_of(full_packed if full_packed is not None else full, GRM_type, pr.ploidy)
     finally:
-        if full is not pr.dm:
+        if full_packed is not None:
+            full_packed.free()
+        if full is not pr.scan_dm:
             full.free()
     pr.pc1, pr.eig_ms = None, 0.0
     if standardise:  # :127-131
@@ -218,7 +232,7 @@ def gwasprep(*, genomes: Genomes, phenomes: Phenomes, idx_entries=None, idx_loci
         K = pr.K
         fit = _new_fit(pr)
     finally:
-        pr.dm.free()
+        pr.free()
     return np.asfortranarray(G), pr.y, K, fit
 
 
@@ -234,7 +248,7 @@ def _gwas(model_name: str, model: int, genomes, phenomes, idx_entries, idx_loci_
                 "(idx_entries or missing phenotypes): the covariate PC1 and G have different numbers of rows.")
         fit = _new_fit(pr)
         fit.model = model_name  # :231 / :354
-        res = pr.dm.scan(pr.y, pr.pc1[:, None], model=model)  # marker loop :239-249 / :363-389
+        res = pr.scan_dm.scan(pr.y, pr.pc1[:, None], model=model)  # marker loop :239-249 / :363-389
         sel = pr.idx_cols - 1
         b = res["stat"][sel, 0]
         if model == _lib.MODEL_LMM:
@@ -244,6 +258,7 @@ def _gwas(model_name: str, model: int, genomes, phenomes, idx_entries, idx_loci_
             "beta": res["beta"][sel, 0], "se": res["se"][sel, 0], "neglog10p": res["neglog10p"][sel, 0],
             "pvalue": np.power(10.0, -res["neglog10p"][sel, 0]), "idx_cols": pr.idx_cols, "pc1": pr.pc1,
             "ploidy": pr.ploidy, "eig_ms": pr.eig_ms, "timing": _lib.last_timing(),
+            "storage": "u8 dosage codes" if pr.packed is not None else "float64",
         }
         if verbose:
             lod = fit.extras["neglog10p"]
@@ -254,7 +269,7 @@ def _gwas(model_name: str, model: int, genomes, phenomes, idx_entries, idx_loci_
             raise ErrorException(f"Error performing GWAS via {model_name[5:]} using the {GRM_type} GRM.")
         return fit
     finally:
-        pr.dm.free()
+        pr.free()
 
 
 def gwasols(*, genomes: Genomes, phenomes: Phenomes, idx_entries=None, idx_loci_alleles=None, idx_trait: int = 1,
@@ -296,7 +311,7 @@ def gwasreml(*, genomes: Genomes, phenomes: Phenomes, idx_entries=None, idx_loci
         y = (pr.y - pr.y.mean()) / np.std(pr.y, ddof=1)  # :128 (z is invariant to it)
         plan = LmmPlan(pr.K, y)
         try:
-            res = plan.run(pr.dm)
+            res = plan.run(pr.scan_dm)
         finally:
             plan.free()
         sel = pr.idx_cols - 1
@@ -309,4 +324,4 @@ def gwasreml(*, genomes: Genomes, phenomes: Phenomes, idx_entries=None, idx_loci
             raise ErrorException("Error performing GWAS via REML using the " + GRM_type + " GRM.")
         return fit
     finally:
-        pr.dm.free()
+        pr.free()
