@@ -421,11 +421,15 @@ def main():
             if world > 1:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dtp = float(tt.item())
+            ltm = _lib.last_timing()
             e2e_packed = {"value": pe * world * args.e2e_steps / dtp, "unit": "markers/s",
-                          "h2d_bytes_per_step": n * pe + 16 * n, "d2h_bytes_per_step": pe * (6 * 8 + 1),
+                          "h2d_bytes_per_step": ltm["h2d_bytes"] + 16 * n, "d2h_bytes_per_step": pe * (6 * 8 + 1),
                           "host_threads": len(os.sched_getaffinity(0)),
-                          "note": "same Float64 host buffer through the default gbm_scan_host: host cores pack each "
-                                  "block to 1-byte codes (exactness-checked) before H2D"}
+                          "blocks_as_codes": ltm["packed_blocks"], "blocks_packed_by_host": ltm["host_packed_blocks"],
+                          "note": "same Float64 host buffer through the default gbm_scan_host: column blocks are "
+                                  "handed out dynamically to the host cores (pack to 1-byte codes, exactness-checked, "
+                                  "then H2D) and to the copy engine (Float64 H2D, packed on the device); h2d bytes "
+                                  "are those of the last timed step"}
         else:
             e2e_packed = None
         line["e2e_float64_copies"] = {"value": pe * world * args.e2e_steps / dt, "unit": "markers/s",

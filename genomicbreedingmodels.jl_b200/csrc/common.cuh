@@ -34,14 +34,24 @@ struct State {
   cudaStream_t copy_stream = nullptr;
   void* cusolver = nullptr;
   cudaEvent_t ev[8] = {};
-  void* stage_buf[2] = {nullptr, nullptr};  // cached H2D staging for gbm_scan_host
-  size_t stage_bytes = 0;
-  void* pack_host[2] = {nullptr, nullptr};  // pinned host staging for packed blocks
-  size_t pack_bytes = 0;
-  cudaEvent_t stage_copied[2] = {nullptr, nullptr}, stage_consumed[2] = {nullptr, nullptr};
+  // gbm_scan_host staging, cached across calls.  Host lane: blocks packed to codes by the host cores
+  // (pinned host_codes -> dev_codes).  Copy-engine lane: Float64 blocks DMA'd as they are (raw_f64),
+  // packed on the device (raw_codes, raw_flag = count of non-code elements).
+  static constexpr int kRawSlots = 3;
+  void* host_codes[2] = {nullptr, nullptr};
+  void* dev_codes[2] = {nullptr, nullptr};
+  size_t code_bytes = 0;
+  cudaEvent_t hl_copied[2] = {nullptr, nullptr}, hl_consumed[2] = {nullptr, nullptr};
+  void* raw_f64[kRawSlots] = {};
+  void* raw_codes[kRawSlots] = {};
+  size_t raw_bytes = 0, raw_code_bytes = 0;
+  unsigned long long* raw_flag_dev = nullptr;   // kRawSlots counters
+  unsigned long long* raw_flag_host = nullptr;  // pinned mirror
+  cudaEvent_t raw_copied[kRawSlots] = {}, raw_packed[kRawSlots] = {}, raw_consumed[kRawSlots] = {};
+  cudaStream_t raw_stream = nullptr;
   double h2d_ms = 0, kernel_ms = 0, main_ms = 0, d2h_ms = 0;
   int64_t launches = 0;
-  int64_t packed_blocks = 0;
+  int64_t packed_blocks = 0, host_packed_blocks = 0, h2d_bytes = 0;
 };
 State& state();
 void require_ready();

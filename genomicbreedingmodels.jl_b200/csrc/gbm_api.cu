@@ -8,6 +8,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -110,6 +112,17 @@ static bool is_device_ptr(const void* p) {
   return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
+// page-locked host memory (cudaMallocHost / cudaHostRegister): async copies from it do not block
+static bool is_pinned_host_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
 // stream-ordered scratch buffer
 template <typename T>
 struct DevBuf {
@@ -182,7 +195,32 @@ static void reset_timing() {
   State& st = state();
   st.h2d_ms = st.kernel_ms = st.main_ms = st.d2h_ms = 0.0;
   st.launches = 0;
-  st.packed_blocks = 0;
+  st.packed_blocks = st.host_packed_blocks = st.h2d_bytes = 0;
+}
+
+// staging of gbm_scan_host (see State)
+static void free_scan_host_staging(State& st) {
+  for (int b = 0; b < 2; ++b) {
+    if (st.host_codes[b]) cudaFreeHost(st.host_codes[b]);
+    if (st.dev_codes[b]) cudaFree(st.dev_codes[b]);
+    st.host_codes[b] = st.dev_codes[b] = nullptr;
+    if (st.hl_copied[b]) cudaEventDestroy(st.hl_copied[b]);
+    if (st.hl_consumed[b]) cudaEventDestroy(st.hl_consumed[b]);
+    st.hl_copied[b] = st.hl_consumed[b] = nullptr;
+  }
+  for (int b = 0; b < State::kRawSlots; ++b) {
+    if (st.raw_f64[b]) cudaFree(st.raw_f64[b]);
+    if (st.raw_codes[b]) cudaFree(st.raw_codes[b]);
+    st.raw_f64[b] = st.raw_codes[b] = nullptr;
+    if (st.raw_copied[b]) cudaEventDestroy(st.raw_copied[b]);
+    if (st.raw_packed[b]) cudaEventDestroy(st.raw_packed[b]);
+    if (st.raw_consumed[b]) cudaEventDestroy(st.raw_consumed[b]);
+    st.raw_copied[b] = st.raw_packed[b] = st.raw_consumed[b] = nullptr;
+  }
+  if (st.raw_flag_dev) cudaFree(st.raw_flag_dev);
+  if (st.raw_flag_host) cudaFreeHost(st.raw_flag_host);
+  st.raw_flag_dev = st.raw_flag_host = nullptr;
+  st.code_bytes = st.raw_bytes = st.raw_code_bytes = 0;
 }
 
 static void copy_out(void* user, const void* dev, size_t bytes, cudaStream_t s) {
@@ -407,22 +445,11 @@ int gbm_shutdown(void) {
     cusolverDnDestroy(reinterpret_cast<cusolverDnHandle_t>(st.cusolver));
     st.cusolver = nullptr;
   }
-  for (int b = 0; b < 2; ++b) {
-    if (st.stage_buf[b]) cudaFree(st.stage_buf[b]);
-    st.stage_buf[b] = nullptr;
-    if (st.stage_copied[b]) cudaEventDestroy(st.stage_copied[b]);
-    if (st.stage_consumed[b]) cudaEventDestroy(st.stage_consumed[b]);
-    st.stage_copied[b] = st.stage_consumed[b] = nullptr;
-  }
-  st.stage_bytes = 0;
-  for (int b = 0; b < 2; ++b) {
-    if (st.pack_host[b]) cudaFreeHost(st.pack_host[b]);
-    st.pack_host[b] = nullptr;
-  }
-  st.pack_bytes = 0;
+  free_scan_host_staging(st);
   if (st.own_stream) cudaStreamDestroy(st.own_stream);
   if (st.copy_stream) cudaStreamDestroy(st.copy_stream);
-  st.own_stream = st.copy_stream = st.stream = nullptr;
+  if (st.raw_stream) cudaStreamDestroy(st.raw_stream);
+  st.own_stream = st.copy_stream = st.raw_stream = st.stream = nullptr;
   st.ready = false;
   GBM_API_END
 }
@@ -468,6 +495,8 @@ int gbm_last_timing(gbm_timing* t) {
   t->d2h_ms = st.d2h_ms;
   t->launches = st.launches;
   t->packed_blocks = st.packed_blocks;
+  t->host_packed_blocks = st.host_packed_blocks;
+  t->h2d_bytes = st.h2d_bytes;
   GBM_API_END
 }
 
@@ -1210,8 +1239,10 @@ int gbm_scan(const gbm_matrix* m, const double* Y, int64_t T, int64_t ldy, const
 }  // extern "C"
 
 namespace gbm {
-bool pack_block_host(const double* A, int64_t n, int64_t lda, int64_t pc, uint8_t* out, int64_t ldo);
+bool pack_block_host(const double* A, int64_t n, int64_t lda, int64_t pc, uint8_t* out, int64_t ldo,
+                     const std::function<void()>* idle);
 int64_t count_inexact_host(const double* A, int64_t n, int64_t lda, int64_t pc);
+bool pack_check_columns(const double* A, int64_t n, int64_t lda, int64_t pc, int isa, uint8_t* col_ok);
 int host_threads();
 }  // namespace gbm
 
@@ -1221,10 +1252,18 @@ int gbm_pack_host(const double* A, int64_t n, int64_t p, int64_t lda, uint8_t* o
   GBM_API_BEGIN
   if (!A || !out || !n_inexact || n < 1 || p < 1 || lda < n || ldo < n)
     GBM_THROW(GBM_ERR_ARGUMENT, "gbm_pack_host: bad arguments");
-  if (pack_block_host(A, n, lda, p, out, ldo))
+  if (pack_block_host(A, n, lda, p, out, ldo, nullptr))
     *n_inexact = 0;
   else
     *n_inexact = count_inexact_host(A, n, lda, p);
+  GBM_API_END
+}
+
+int gbm_pack_host_check(const double* A, int64_t n, int64_t p, int64_t lda, int isa, uint8_t* col_ok) {
+  GBM_API_BEGIN
+  if (!A || !col_ok || n < 1 || p < 1 || lda < n) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_pack_host_check: bad arguments");
+  if (!pack_check_columns(A, n, lda, p, isa, col_ok))
+    GBM_THROW(GBM_ERR_ARGUMENT, "gbm_pack_host_check: this CPU does not have the requested instruction set");
   GBM_API_END
 }
 
@@ -1245,96 +1284,216 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
   out.bind_all(p, T, beta, se, stat, neglog10p, mean, sd, keep);
   auto passes = build_passes(sv, n, T);
   const std::vector<double*> no_rec;
-  // auto: pack blocks that are all dosage codes -- when this process has enough host cores to
-  // out-run the PCIe link with the packer (8 threads read ~45 GB/s of Float64)
-  bool pack = (flags & GBM_SCAN_HOST_NO_PACK) == 0 && !is_device_ptr(A) && host_threads() >= 8;
   const int kflags = flags & GBM_PVALUE_TWO_SIDED;
-  // column blocks of ~256 MB of Float64, double-buffered: the copy engine fills one buffer while the
-  // scan kernel streams the other
+  const bool want_codes = (flags & GBM_SCAN_HOST_NO_PACK) == 0;  // scan blocks as 1-byte codes when they are codes
+  const bool device_src = is_device_ptr(A);
+  const bool pinned = device_src || is_pinned_host_ptr(A);
+  // Two lanes feed the scan kernels, column blocks are handed out dynamically (results do not
+  // depend on the lane: a block that is all dosage codes is scanned by the u8 kernel, any other
+  // block by the Float64 kernel, wherever it was packed):
+  //  * host lane: the host cores pack a block to codes (exactness-checked) into pinned staging, 1/8 of
+  //    the bytes cross PCIe.  Needs >= 2 host threads; stops at the first block that is not all codes.
+  //  * copy-engine lane: the block crosses PCIe as Float64 (cudaMemcpyAsync from the caller's pinned
+  //    buffer) and is packed on the device.  Pageable memory would make those copies synchronous, so
+  //    this lane then only takes what the host lane cannot.
+  bool host_lane = want_codes && !device_src && host_threads() >= 2;
+  bool raw_lane = pinned || !host_lane;
+  if (const char* e = getenv("GBM_SCAN_HOST_LANES")) {  // "host" / "copy": measurement switch
+    if (!strcmp(e, "host") && host_lane) raw_lane = false;
+    if (!strcmp(e, "copy")) host_lane = false, raw_lane = true;
+  }
+  // column blocks of ~128 MB of Float64
   const int64_t ldd = round_up(n, 16);
   const int64_t ld8 = round_up(n, 128);
-  int64_t blk = std::max<int64_t>(16, ((int64_t(256) << 20) / (8 * ldd)) / 16 * 16);
+  int64_t blk = std::max<int64_t>(16, ((int64_t(128) << 20) / (8 * ldd)) / 16 * 16);
   blk = std::min(blk, round_up(p, 16));
+  const int64_t nblk = (p + blk - 1) / blk;
+  constexpr int kRaw = State::kRawSlots;
   // staging buffers and events are cached across calls
   const size_t need = sizeof(double) * ldd * blk;
-  if (st.stage_bytes < need) {
-    for (int b = 0; b < 2; ++b) {
-      if (st.stage_buf[b]) cudaFree(st.stage_buf[b]);
-      st.stage_buf[b] = nullptr;
-      GBM_CUDA(cudaMalloc(&st.stage_buf[b], need));
-    }
-    st.stage_bytes = need;
-  }
   const size_t need8 = static_cast<size_t>(ld8) * blk;
-  if (pack && st.pack_bytes < need8) {
-    for (int b = 0; b < 2; ++b) {
-      if (st.pack_host[b]) cudaFreeHost(st.pack_host[b]);
-      st.pack_host[b] = nullptr;
-      GBM_CUDA(cudaMallocHost(&st.pack_host[b], need8));
+  if (!st.raw_stream) GBM_CUDA(cudaStreamCreateWithFlags(&st.raw_stream, cudaStreamNonBlocking));
+  auto make_event = [](cudaEvent_t* e) {
+    if (!*e) GBM_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  };
+  if (st.raw_bytes < need) {
+    for (int b = 0; b < kRaw; ++b) {
+      if (st.raw_f64[b]) cudaFree(st.raw_f64[b]);
+      st.raw_f64[b] = nullptr;
+      GBM_CUDA(cudaMalloc(&st.raw_f64[b], need));
     }
-    st.pack_bytes = need8;
+    st.raw_bytes = need;
   }
-  double* buf[2] = {static_cast<double*>(st.stage_buf[0]), static_cast<double*>(st.stage_buf[1])};
-  cudaEvent_t* copied = st.stage_copied;
-  cudaEvent_t* consumed = st.stage_consumed;
-  for (int b = 0; b < 2; ++b) {
-    if (!copied[b]) GBM_CUDA(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
-    if (!consumed[b]) GBM_CUDA(cudaEventCreateWithFlags(&consumed[b], cudaEventDisableTiming));
-    if (ldd != n && !pack) GBM_CUDA(cudaMemsetAsync(buf[b], 0, need, st.copy_stream));
+  if (want_codes && st.raw_code_bytes < need8) {
+    for (int b = 0; b < kRaw; ++b) {
+      if (st.raw_codes[b]) cudaFree(st.raw_codes[b]);
+      st.raw_codes[b] = nullptr;
+      GBM_CUDA(cudaMalloc(&st.raw_codes[b], need8));
+    }
+    st.raw_code_bytes = need8;
+  }
+  if (!st.raw_flag_dev) {
+    GBM_CUDA(cudaMalloc(reinterpret_cast<void**>(&st.raw_flag_dev), sizeof(unsigned long long) * kRaw));
+    GBM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&st.raw_flag_host), sizeof(unsigned long long) * kRaw));
+  }
+  if (host_lane && st.code_bytes < need8) {
+    for (int b = 0; b < 2; ++b) {
+      if (st.host_codes[b]) cudaFreeHost(st.host_codes[b]);
+      if (st.dev_codes[b]) cudaFree(st.dev_codes[b]);
+      st.host_codes[b] = st.dev_codes[b] = nullptr;
+      GBM_CUDA(cudaMallocHost(&st.host_codes[b], need8));
+      GBM_CUDA(cudaMalloc(&st.dev_codes[b], need8));
+    }
+    st.code_bytes = need8;
+  }
+  for (int b = 0; b < 2; ++b) make_event(&st.hl_copied[b]), make_event(&st.hl_consumed[b]);
+  for (int b = 0; b < kRaw; ++b) {
+    make_event(&st.raw_copied[b]), make_event(&st.raw_packed[b]), make_event(&st.raw_consumed[b]);
+    if (ldd != n) GBM_CUDA(cudaMemsetAsync(st.raw_f64[b], 0, need, st.raw_stream));  // pad rows stay zero
   }
   const bool contiguous = (lda == n && ldd == n);
-  int64_t packed_blocks = 0, total_blocks = 0;
+
+  int64_t next = 0;              // next unassigned block
+  std::deque<int64_t> handback;  // blocks the host lane could not pack
+  int64_t code_blocks = 0, host_blocks = 0, h2d_bytes = 0;
+  auto take_block = [&](bool for_raw) -> int64_t {
+    if (for_raw && !handback.empty()) {
+      const int64_t bi = handback.front();
+      handback.pop_front();
+      return bi;
+    }
+    return next < nblk ? next++ : -1;
+  };
+  struct RawSlot {
+    int state = 0;  // 0 free, 1 copy in flight, 2 device pack in flight
+    int64_t bi = -1;
+  } slot[kRaw];
+  int raw_busy = 0;
+
   Span all(st.stream);
   all.start();
-  GBM_CUDA(cudaEventRecord(consumed[0], st.stream));
-  GBM_CUDA(cudaEventRecord(consumed[1], st.stream));
-  int b = 0;
-  for (int64_t j0 = 0; j0 < p; j0 += blk, b ^= 1) {
-    const int64_t pc = std::min(blk, p - j0);
-    ++total_blocks;
+  for (int b = 0; b < 2; ++b) GBM_CUDA(cudaEventRecord(st.hl_consumed[b], st.stream));
+  for (int b = 0; b < kRaw; ++b) GBM_CUDA(cudaEventRecord(st.raw_consumed[b], st.stream));
+
+  auto raw_issue = [&](int s) {
+    const int64_t bi = take_block(true);
+    if (bi < 0) return;
+    const int64_t j0 = bi * blk, pc = std::min(blk, p - j0);
+    double* dst = static_cast<double*>(st.raw_f64[s]);
+    GBM_CUDA(cudaStreamWaitEvent(st.raw_stream, st.raw_consumed[s], 0));
+    if (contiguous)
+      GBM_CUDA(cudaMemcpyAsync(dst, A + j0 * lda, sizeof(double) * n * pc, cudaMemcpyDefault, st.raw_stream));
+    else
+      GBM_CUDA(cudaMemcpy2DAsync(dst, ldd * sizeof(double), A + j0 * lda, lda * sizeof(double), n * sizeof(double),
+                                 pc, cudaMemcpyDefault, st.raw_stream));
+    GBM_CUDA(cudaEventRecord(st.raw_copied[s], st.raw_stream));
+    h2d_bytes += static_cast<int64_t>(sizeof(double)) * n * pc;
+    slot[s].state = 1;
+    slot[s].bi = bi;
+    ++raw_busy;
+  };
+  auto event_done = [&](cudaEvent_t e, bool wait) {
+    if (wait) {
+      GBM_CUDA(cudaEventSynchronize(e));
+      return true;
+    }
+    const cudaError_t r = cudaEventQuery(e);
+    if (r == cudaSuccess) return true;
+    if (r != cudaErrorNotReady) GBM_CUDA(r);
+    return false;
+  };
+  auto raw_scan = [&](int s, bool as_codes) {
+    const int64_t j0 = slot[s].bi * blk, pc = std::min(blk, p - j0);
     gbm_matrix view;
     view.n = n;
     view.p = pc;
-    bool packed_ok = false;
-    if (pack) {
-      // the pinned pack buffer b was handed to the copy engine two blocks ago: wait for that copy
-      GBM_CUDA(cudaEventSynchronize(copied[b]));
-      uint8_t* hp = static_cast<uint8_t*>(st.pack_host[b]);
-      packed_ok = pack_block_host(A + j0 * lda, n, lda, pc, hp, ld8);
-      if (!packed_ok) pack = false;  // not dosage data: stop trying, the rest travels as Float64
-      if (packed_ok) {
-        GBM_CUDA(cudaStreamWaitEvent(st.copy_stream, consumed[b], 0));
-        GBM_CUDA(cudaMemcpyAsync(buf[b], hp, static_cast<size_t>(ld8) * pc, cudaMemcpyHostToDevice, st.copy_stream));
-        view.dtype = 1;
-        view.d8 = reinterpret_cast<uint8_t*>(buf[b]);
-        view.ld8 = ld8;
-        ++packed_blocks;
-      }
-    }
-    if (!packed_ok) {
-      GBM_CUDA(cudaStreamWaitEvent(st.copy_stream, consumed[b], 0));
-      if (pack && ldd != n) GBM_CUDA(cudaMemsetAsync(buf[b], 0, sizeof(double) * ldd * pc, st.copy_stream));
-      if (contiguous)
-        GBM_CUDA(cudaMemcpyAsync(buf[b], A + j0 * lda, sizeof(double) * n * pc, cudaMemcpyDefault, st.copy_stream));
-      else
-        GBM_CUDA(cudaMemcpy2DAsync(buf[b], ldd * sizeof(double), A + j0 * lda, lda * sizeof(double),
-                                   n * sizeof(double), pc, cudaMemcpyDefault, st.copy_stream));
+    if (as_codes) {
+      view.dtype = 1;
+      view.d8 = static_cast<uint8_t*>(st.raw_codes[s]);
+      view.ld8 = ld8;
+      ++code_blocks;
+    } else {
       view.dtype = 0;
-      view.d = buf[b];
+      view.d = static_cast<double*>(st.raw_f64[s]);
       view.lda = ldd;
     }
-    GBM_CUDA(cudaEventRecord(copied[b], st.copy_stream));
-    GBM_CUDA(cudaStreamWaitEvent(st.stream, copied[b], 0));
     scan_block(view, pc, passes, no_rec, sv.k_eff, model, kflags, out.view(), p, j0, nullptr);
-    GBM_CUDA(cudaEventRecord(consumed[b], st.stream));
+    GBM_CUDA(cudaEventRecord(st.raw_consumed[s], st.stream));
+    slot[s].state = 0;
+    --raw_busy;
+    raw_issue(s);
+  };
+  // advances the copy-engine lane; wait = block on the oldest pending event instead of polling
+  auto raw_service = [&](bool wait) {
+    if (!raw_lane) return;
+    for (int s = 0; s < kRaw; ++s) {
+      if (slot[s].state == 0) raw_issue(s);
+      if (slot[s].state == 1 && event_done(st.raw_copied[s], wait)) {
+        if (!want_codes) {
+          raw_scan(s, false);
+          continue;
+        }
+        const int64_t pc = std::min(blk, p - slot[s].bi * blk);
+        GBM_CUDA(cudaMemsetAsync(st.raw_flag_dev + s, 0, sizeof(unsigned long long), st.stream));
+        launch_pack_u8(static_cast<double*>(st.raw_f64[s]), n, pc, ldd, static_cast<uint8_t*>(st.raw_codes[s]), ld8,
+                       st.raw_flag_dev + s, st.stream);
+        GBM_CUDA(cudaMemcpyAsync(st.raw_flag_host + s, st.raw_flag_dev + s, sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, st.stream));
+        GBM_CUDA(cudaEventRecord(st.raw_packed[s], st.stream));
+        slot[s].state = 2;
+        st.launches += 1;
+      }
+      if (slot[s].state == 2 && event_done(st.raw_packed[s], wait)) raw_scan(s, st.raw_flag_host[s] == 0);
+    }
+  };
+  const std::function<void()> idle = [&] { raw_service(false); };
+
+  raw_service(false);
+  for (int hb = 0; host_lane; hb ^= 1) {
+    const int64_t bi = take_block(false);
+    if (bi < 0) break;
+    const int64_t j0 = bi * blk, pc = std::min(blk, p - j0);
+    // the pinned buffer hb went to the copy engine two host-lane blocks ago: wait for that copy
+    GBM_CUDA(cudaEventSynchronize(st.hl_copied[hb]));
+    uint8_t* hp = static_cast<uint8_t*>(st.host_codes[hb]);
+    if (!pack_block_host(A + j0 * lda, n, lda, pc, hp, ld8, raw_lane ? &idle : nullptr)) {
+      // not dosage data: this block and the rest travel as Float64
+      handback.push_back(bi);
+      host_lane = false;
+      raw_lane = true;
+      break;
+    }
+    GBM_CUDA(cudaStreamWaitEvent(st.copy_stream, st.hl_consumed[hb], 0));
+    GBM_CUDA(cudaMemcpyAsync(st.dev_codes[hb], hp, static_cast<size_t>(ld8) * pc, cudaMemcpyHostToDevice, st.copy_stream));
+    GBM_CUDA(cudaEventRecord(st.hl_copied[hb], st.copy_stream));
+    GBM_CUDA(cudaStreamWaitEvent(st.stream, st.hl_copied[hb], 0));
+    gbm_matrix view;
+    view.n = n;
+    view.p = pc;
+    view.dtype = 1;
+    view.d8 = static_cast<uint8_t*>(st.dev_codes[hb]);
+    view.ld8 = ld8;
+    scan_block(view, pc, passes, no_rec, sv.k_eff, model, kflags, out.view(), p, j0, nullptr);
+    GBM_CUDA(cudaEventRecord(st.hl_consumed[hb], st.stream));
+    ++code_blocks;
+    ++host_blocks;
+    h2d_bytes += ld8 * pc;
+    raw_service(false);
+  }
+  // drain: whatever is left goes through the copy-engine lane
+  while (raw_busy > 0 || next < nblk || !handback.empty()) {
+    if (!raw_lane) GBM_THROW(GBM_ERR_RUNTIME, "gbm_scan_host: internal scheduling error");
+    raw_service(true);
   }
   all.stop();
   out.copy_back(p, T);
   GBM_CUDA(cudaStreamSynchronize(st.stream));
   GBM_CUDA(cudaStreamSynchronize(st.copy_stream));
+  GBM_CUDA(cudaStreamSynchronize(st.raw_stream));
   st.kernel_ms = all.ms();  // copy + compute overlapped: wall time of the pipeline on the device
-  st.packed_blocks = packed_blocks;
-  (void)total_blocks;
+  st.packed_blocks = code_blocks;
+  st.host_packed_blocks = host_blocks;
+  st.h2d_bytes = device_src ? 0 : h2d_bytes;
   GBM_API_END
 }
 

@@ -10,9 +10,12 @@
 #include <stdlib.h>
 
 #include <atomic>
+#include <chrono>
+#include <exception>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -35,34 +38,88 @@ static inline bool pack_col_scalar(const double* col, int64_t n, uint8_t* dst, i
   return bad;
 }
 
-__attribute__((target("avx2"))) static bool pack_col_avx2(const double* col, int64_t n, uint8_t* dst) {
-  const __m256d k240 = _mm256_set1_pd(240.0);
-  const __m128i hi = _mm_set1_epi32(240);
-  const __m128i zero = _mm_setzero_si128();
-  int badmask = 0;
+// Division-free exactness test used by the vector bodies.  For a in [0, 1] and c = rint(240 a):
+//   fl(c / 240) == a   <=>   r == 0  or  |r| * 2^52 < 120 * 2^e(a),   r = fma(a, 240, -c),
+// because 240 a - c is a small multiple of ulp(a) (so the fma returns it exactly), c / 240 is
+// either exactly representable (15 | c, then r == 0) or strictly inside a binade at least
+// 1/240 - 1/256 away from any power of two (so a and c / 240 share ulp(a) = 2^(e(a) - 52) and
+// ties cannot occur), and "a is the double nearest to c / 240" is |a - c/240| < ulp(a) / 2.
+// 2^e(a) is a with its mantissa bits cleared.  tests/test_abi_and_host.py checks the
+// equivalence with the division on every code, its neighbours and random doubles.
+__attribute__((target("avx2,fma"))) static bool pack_col_avx2(const double* col, int64_t n, uint8_t* dst) {
+  const __m256d k240 = _mm256_set1_pd(240.0), k120 = _mm256_set1_pd(120.0), one = _mm256_set1_pd(1.0);
+  const __m256d two52 = _mm256_set1_pd(4503599627370496.0), zero = _mm256_setzero_pd();
+  const __m256d expmask = _mm256_castsi256_pd(_mm256_set1_epi64x(0x7FF0000000000000ll));
+  const __m256d absmask = _mm256_castsi256_pd(_mm256_set1_epi64x(0x7FFFFFFFFFFFFFFFll));
+  __m256d badv = zero;
   int64_t i = 0;
   for (; i + 8 <= n; i += 8) {
     const __m256d a0 = _mm256_loadu_pd(col + i), a1 = _mm256_loadu_pd(col + i + 4);
     const __m128i c0 = _mm256_cvtpd_epi32(_mm256_mul_pd(a0, k240));  // round to nearest
     const __m128i c1 = _mm256_cvtpd_epi32(_mm256_mul_pd(a1, k240));
-    const __m256d b0 = _mm256_div_pd(_mm256_cvtepi32_pd(c0), k240);
-    const __m256d b1 = _mm256_div_pd(_mm256_cvtepi32_pd(c1), k240);
-    badmask |= _mm256_movemask_pd(_mm256_cmp_pd(b0, a0, _CMP_NEQ_UQ)) | _mm256_movemask_pd(_mm256_cmp_pd(b1, a1, _CMP_NEQ_UQ));
-    // range 0..240 (cvt of NaN / huge gives INT_MIN, caught here or by the compare above)
-    const __m128i oob = _mm_or_si128(_mm_or_si128(_mm_cmpgt_epi32(c0, hi), _mm_cmpgt_epi32(zero, c0)),
-                                     _mm_or_si128(_mm_cmpgt_epi32(c1, hi), _mm_cmpgt_epi32(zero, c1)));
-    badmask |= _mm_movemask_epi8(oob);
+    const __m256d r0 = _mm256_and_pd(_mm256_fmsub_pd(a0, k240, _mm256_cvtepi32_pd(c0)), absmask);
+    const __m256d r1 = _mm256_and_pd(_mm256_fmsub_pd(a1, k240, _mm256_cvtepi32_pd(c1)), absmask);
+    // good = in [0, 1] (ordered compares: NaN fails) and (r == 0 or |r| 2^52 < 120 2^e)
+    const __m256d in0 = _mm256_and_pd(_mm256_cmp_pd(a0, zero, _CMP_GE_OQ), _mm256_cmp_pd(a0, one, _CMP_LE_OQ));
+    const __m256d in1 = _mm256_and_pd(_mm256_cmp_pd(a1, zero, _CMP_GE_OQ), _mm256_cmp_pd(a1, one, _CMP_LE_OQ));
+    const __m256d ok0 = _mm256_or_pd(_mm256_cmp_pd(r0, zero, _CMP_EQ_OQ),
+                                     _mm256_cmp_pd(_mm256_mul_pd(r0, two52), _mm256_mul_pd(_mm256_and_pd(a0, expmask), k120), _CMP_LT_OQ));
+    const __m256d ok1 = _mm256_or_pd(_mm256_cmp_pd(r1, zero, _CMP_EQ_OQ),
+                                     _mm256_cmp_pd(_mm256_mul_pd(r1, two52), _mm256_mul_pd(_mm256_and_pd(a1, expmask), k120), _CMP_LT_OQ));
+    badv = _mm256_or_pd(badv, _mm256_or_pd(_mm256_andnot_pd(_mm256_and_pd(in0, ok0), one), _mm256_andnot_pd(_mm256_and_pd(in1, ok1), one)));
     const __m128i w16 = _mm_packus_epi32(c0, c1);
     const __m128i w8 = _mm_packus_epi16(w16, w16);
     _mm_storel_epi64(reinterpret_cast<__m128i*>(dst + i), w8);
   }
-  bool bad = badmask != 0;
+  bool bad = _mm256_movemask_pd(_mm256_cmp_pd(badv, zero, _CMP_NEQ_UQ)) != 0;
   if (i < n) bad |= pack_col_scalar(col, n, dst, i);
   return bad;
 }
 
-static bool have_avx2() {
-  static const bool v = __builtin_cpu_supports("avx2");
+__attribute__((target("avx512f,avx512vl,avx512dq"))) static bool pack_col_avx512(const double* col, int64_t n, uint8_t* dst) {
+  const __m512d k240 = _mm512_set1_pd(240.0), k120 = _mm512_set1_pd(120.0), one = _mm512_set1_pd(1.0);
+  const __m512d two52 = _mm512_set1_pd(4503599627370496.0), zero = _mm512_setzero_pd();
+  const __m512i expmask = _mm512_set1_epi64(0x7FF0000000000000ll);
+  __mmask8 good = 0xFF;
+  int64_t i = 0;
+  for (; i + 16 <= n; i += 16) {
+    const __m512d a0 = _mm512_loadu_pd(col + i), a1 = _mm512_loadu_pd(col + i + 8);
+    const __m256i c0 = _mm512_cvtpd_epi32(_mm512_mul_pd(a0, k240));
+    const __m256i c1 = _mm512_cvtpd_epi32(_mm512_mul_pd(a1, k240));
+    const __m512d r0 = _mm512_abs_pd(_mm512_fmsub_pd(a0, k240, _mm512_cvtepi32_pd(c0)));
+    const __m512d r1 = _mm512_abs_pd(_mm512_fmsub_pd(a1, k240, _mm512_cvtepi32_pd(c1)));
+    const __m512d e0 = _mm512_castsi512_pd(_mm512_and_epi64(_mm512_castpd_si512(a0), expmask));
+    const __m512d e1 = _mm512_castsi512_pd(_mm512_and_epi64(_mm512_castpd_si512(a1), expmask));
+    const __mmask8 in0 = _mm512_cmp_pd_mask(a0, zero, _CMP_GE_OQ) & _mm512_cmp_pd_mask(a0, one, _CMP_LE_OQ);
+    const __mmask8 in1 = _mm512_cmp_pd_mask(a1, zero, _CMP_GE_OQ) & _mm512_cmp_pd_mask(a1, one, _CMP_LE_OQ);
+    const __mmask8 ok0 = _mm512_cmp_pd_mask(r0, zero, _CMP_EQ_OQ) |
+                         _mm512_cmp_pd_mask(_mm512_mul_pd(r0, two52), _mm512_mul_pd(e0, k120), _CMP_LT_OQ);
+    const __mmask8 ok1 = _mm512_cmp_pd_mask(r1, zero, _CMP_EQ_OQ) |
+                         _mm512_cmp_pd_mask(_mm512_mul_pd(r1, two52), _mm512_mul_pd(e1, k120), _CMP_LT_OQ);
+    good &= in0 & ok0 & in1 & ok1;
+    const __m128i b0 = _mm256_cvtepi32_epi8(c0), b1 = _mm256_cvtepi32_epi8(c1);  // low 8 bytes each
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + i), _mm_unpacklo_epi64(b0, b1));
+  }
+  bool bad = good != 0xFF;
+  if (i < n) bad |= pack_col_scalar(col, n, dst, i);
+  return bad;
+}
+
+// 0 scalar, 1 avx2+fma, 2 avx512; GBM_PACK_ISA=scalar|avx2|avx512 caps it (testing)
+static int pack_isa() {
+  static const int v = [] {
+    int best = 0;
+    if (__builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma")) best = 1;
+    if (best == 1 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512vl") &&
+        __builtin_cpu_supports("avx512dq"))
+      best = 2;
+    if (const char* e = getenv("GBM_PACK_ISA")) {
+      const std::string s(e);
+      const int cap = s == "scalar" ? 0 : s == "avx2" ? 1 : 2;
+      if (cap < best) best = cap;
+    }
+    return best;
+  }();
   return v;
 }
 
@@ -70,12 +127,14 @@ static bool have_avx2() {
 // found an element that is not a code) and raises it itself in that case
 static void pack_columns(const double* A, int64_t n, int64_t lda, int64_t c0, int64_t c1, uint8_t* out, int64_t ldo,
                          std::atomic<int>* stop) {
-  const bool avx2 = have_avx2();
+  const int isa = pack_isa();
   for (int64_t j = c0; j < c1; ++j) {
     if (stop->load(std::memory_order_relaxed)) return;
     const double* col = A + j * lda;
     uint8_t* dst = out + j * ldo;
-    const bool bad = avx2 ? pack_col_avx2(col, n, dst) : pack_col_scalar(col, n, dst, 0);
+    const bool bad = isa == 2   ? pack_col_avx512(col, n, dst)
+                     : isa == 1 ? pack_col_avx2(col, n, dst)
+                                : pack_col_scalar(col, n, dst, 0);
     for (int64_t i = n; i < ldo; ++i) dst[i] = 0;
     if (bad) {
       stop->store(1, std::memory_order_relaxed);
@@ -100,14 +159,32 @@ class Pool {
     for (auto& w : workers_) w.join();
   }
   int size() const { return n_; }
-  void run(const std::function<void(int)>& fn) {
+  // Runs fn(t) on every worker and waits.  While waiting, the calling thread invokes *idle
+  // about every 100 us (gbm_scan_host services its copy-engine lane there); an exception from
+  // idle is re-thrown once the workers have finished.
+  void run(const std::function<void(int)>& fn, const std::function<void()>* idle = nullptr) {
     std::unique_lock<std::mutex> lk(m_);
     fn_ = &fn;
     pending_ = n_;
     ++epoch_;
     cv_.notify_all();
-    done_.wait(lk, [this] { return pending_ == 0; });
+    std::exception_ptr err;
+    while (pending_ != 0) {
+      if (!idle || err) {
+        done_.wait(lk, [this] { return pending_ == 0; });
+        break;
+      }
+      if (done_.wait_for(lk, std::chrono::microseconds(100), [this] { return pending_ == 0; })) break;
+      lk.unlock();
+      try {
+        (*idle)();
+      } catch (...) {
+        err = std::current_exception();
+      }
+      lk.lock();
+    }
     fn_ = nullptr;
+    if (err) std::rethrow_exception(err);
   }
 
  private:
@@ -161,7 +238,8 @@ static Pool& pool() {
 // Packs the n x pc block at A (pitch lda) into out (pitch ldo bytes, rows n..ldo-1 zeroed).
 // Returns true when every element is exactly a code; false as soon as one is not (out is then
 // incomplete and must not be used).
-bool pack_block_host(const double* A, int64_t n, int64_t lda, int64_t pc, uint8_t* out, int64_t ldo) {
+bool pack_block_host(const double* A, int64_t n, int64_t lda, int64_t pc, uint8_t* out, int64_t ldo,
+                     const std::function<void()>* idle) {
   Pool& pl = pool();
   const int T = pl.size();
   std::atomic<int> stop(0);
@@ -176,9 +254,28 @@ bool pack_block_host(const double* A, int64_t n, int64_t lda, int64_t pc, uint8_
       const int64_t c0 = c * chunk, c1 = c0 + chunk < pc ? c0 + chunk : pc;
       pack_columns(A, n, lda, c0, c1, out, ldo, &stop);
     }
-  });
+  }, idle);
   (void)T;
   return stop.load() == 0;
+}
+
+// Testing hook: the single-column packer body of one ISA level (0 scalar with the division,
+// 1 AVX2+FMA, 2 AVX-512) on every column; col_ok[j] = 1 when column j was accepted.
+// Returns false when the CPU lacks that ISA.
+bool pack_check_columns(const double* A, int64_t n, int64_t lda, int64_t pc, int isa, uint8_t* col_ok) {
+  const bool has1 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma");
+  const bool has2 = has1 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512vl") &&
+                    __builtin_cpu_supports("avx512dq");
+  if (isa < 0 || isa > 2 || (isa == 1 && !has1) || (isa == 2 && !has2)) return false;
+  std::vector<uint8_t> tmp(static_cast<size_t>(n) + 64);
+  for (int64_t j = 0; j < pc; ++j) {
+    const double* col = A + j * lda;
+    const bool bad = isa == 2   ? pack_col_avx512(col, n, tmp.data())
+                     : isa == 1 ? pack_col_avx2(col, n, tmp.data())
+                                : pack_col_scalar(col, n, tmp.data(), 0);
+    col_ok[j] = bad ? 0 : 1;
+  }
+  return true;
 }
 
 // count of inexact elements (no early exit) -- for gbm_pack_host's report

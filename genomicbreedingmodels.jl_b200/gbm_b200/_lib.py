@@ -45,7 +45,7 @@ class CudaError(RuntimeError):
 
 class Timing(ctypes.Structure):
     _fields_ = [("h2d_ms", c_double), ("kernel_ms", c_double), ("main_ms", c_double), ("d2h_ms", c_double),
-                ("launches", c_int64), ("packed_blocks", c_int64)]
+                ("launches", c_int64), ("packed_blocks", c_int64), ("host_packed_blocks", c_int64), ("h2d_bytes", c_int64)]
 
 
 # every exported symbol of include/gbm_b200.h: name -> (restype, argtypes)
@@ -66,6 +66,7 @@ SIGNATURES = {
     "gbm_matrix_pack": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int64)]),
     "gbm_matrix_upload_packed": (c_int, [_P, c_int64, c_int64, c_int64, POINTER(c_void_p)]),
     "gbm_pack_host": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int64, POINTER(c_int64)]),
+    "gbm_pack_host_check": (c_int, [_P, c_int64, c_int64, c_int64, c_int, _P]),
     "gbm_matrix_download": (c_int, [c_void_p, c_int64, c_int64, _P, c_int64]),
     "gbm_matrix_download_cols": (c_int, [c_void_p, _P, c_int64, c_int, _P, c_int64]),
     "gbm_matrix_info": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_void_p)]),
@@ -117,7 +118,7 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.gbm_abi_version() != 1:
+        if lib.gbm_abi_version() != 2:
             raise CudaError("libgbm_b200.so ABI version mismatch")
         _lib = lib
     return _lib
@@ -169,7 +170,8 @@ def last_timing() -> dict:
     t = Timing()
     check(load().gbm_last_timing(byref(t)))
     return {"h2d_ms": t.h2d_ms, "kernel_ms": t.kernel_ms, "main_ms": t.main_ms, "d2h_ms": t.d2h_ms,
-            "launches": int(t.launches), "packed_blocks": int(t.packed_blocks)}
+            "launches": int(t.launches), "packed_blocks": int(t.packed_blocks),
+            "host_packed_blocks": int(t.host_packed_blocks), "h2d_bytes": int(t.h2d_bytes)}
 
 
 def device_info() -> dict:

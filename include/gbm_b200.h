@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define GBM_ABI_VERSION 1
+#define GBM_ABI_VERSION 2
 
 #define GBM_OK 0
 #define GBM_ERR_ARGUMENT 1 /* Julia ArgumentError */
@@ -51,7 +51,8 @@ extern "C" {
 #define GBM_MODEL_LMM 1 /* gwaslmm z statistic, p-values from Normal()   (gwas.jl:385, :392) */
 /* scan flags */
 #define GBM_PVALUE_TWO_SIDED 1 /* default is the one-sided upper tail of |stat| */
-#define GBM_SCAN_HOST_NO_PACK 4 /* gbm_scan_host: never pack blocks to 1-byte codes on the host (default: auto) */
+#define GBM_SCAN_HOST_NO_PACK 4 /* gbm_scan_host: never pack blocks to 1-byte codes, every block crosses PCIe and is
+                                   scanned as Float64 (default: blocks that are all dosage codes are packed) */
 
 /* synthetic generator kinds (oracle/synth.py defines the arithmetic) */
 #define GBM_KIND_DIPLOID 0
@@ -67,7 +68,10 @@ typedef struct gbm_timing {
   double main_ms;   /* the dominant kernel alone (scan sums / DMMA) */
   double d2h_ms;    /* device -> host copies                        */
   int64_t launches; /* kernels launched by the call                 */
-  int64_t packed_blocks; /* gbm_scan_host: column blocks that crossed PCIe as 1-byte codes */
+  int64_t packed_blocks; /* gbm_scan_host: column blocks scanned as 1-byte codes (all elements are codes) */
+  int64_t host_packed_blocks; /* ... of which packed by the host cores, i.e. crossed PCIe as 1 byte per genotype;
+                                 the others crossed as Float64 and were packed on the device */
+  int64_t h2d_bytes; /* gbm_scan_host: genotype bytes that crossed PCIe */
 } gbm_timing;
 
 /* ---- life cycle ------------------------------------------------------------------- */
@@ -104,6 +108,10 @@ int gbm_matrix_pack(const gbm_matrix* m, gbm_matrix** out, int64_t* n_inexact);
 int gbm_matrix_upload_packed(const uint8_t* codes, int64_t n, int64_t p, int64_t ld, gbm_matrix** out);
 /* multi-threaded host packer (all cores of the calling process' affinity mask) */
 int gbm_pack_host(const double* A, int64_t n, int64_t p, int64_t lda, uint8_t* out, int64_t ldo, int64_t* n_inexact);
+/* testing hook: col_ok[j] = 1 when the packer body of ISA level `isa` (0 scalar, 1 AVX2+FMA, 2 AVX-512)
+ * accepts column j as all-codes; the vector bodies use a division-free test that must agree with
+ * fl(c/240) == a element for element */
+int gbm_pack_host_check(const double* A, int64_t n, int64_t p, int64_t lda, int isa, uint8_t* col_ok);
 int gbm_matrix_download(const gbm_matrix* m, int64_t j0, int64_t ncols, double* dst, int64_t ldd);
 /* G = G[:, idx_cols] and, with standardise != 0, G = (G .- mean(G, dims=1)) ./ std(G, dims=1)'
  * (/root/reference/src/gwas.jl:114, :129) on the device; dst (host or device) is n x ncols.
@@ -169,12 +177,15 @@ int gbm_scan_plan_run(gbm_scan_plan* plan, double* beta, double* se, double* sta
                       double* sd, uint8_t* keep);
 int gbm_scan_plan_free(gbm_scan_plan* plan);
 
-/* One call from host memory to results (the end-to-end path): uploads A in column blocks
- * through pinned staging while the previous block is scanned. Same outputs as gbm_scan.
- * By default each block is first packed to 1-byte dosage codes by the host cores (exactness-
- * checked; the first block that is not all codes switches the call to plain Float64 copies), so
- * 8x fewer bytes cross PCIe for dosage data with identical results; GBM_SCAN_HOST_NO_PACK
- * disables that. */
+/* One call from host memory to results (the end-to-end path).  A is cut into ~128 MB column blocks
+ * handed out dynamically to two lanes that run concurrently with the scan kernels:
+ *  - host lane: the host cores pack a block to 1-byte dosage codes (exactness-checked) into pinned
+ *    staging, so 1/8 of the bytes cross PCIe; it stops at the first block that is not all codes;
+ *  - copy-engine lane (A page-locked, or the host lane unavailable): the block crosses PCIe as
+ *    Float64 and is packed on the device.
+ * A block that is all codes is scanned by the u8 kernel, any other block by the Float64 kernel,
+ * whichever lane carried it, so the outputs do not depend on the scheduling.  Same outputs as
+ * gbm_scan.  GBM_SCAN_HOST_NO_PACK: plain Float64 copies and the Float64 kernel only. */
 int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const double* Y, int64_t T, int64_t ldy,
                   const double* C, int64_t k, int64_t ldc, int model, int flags, double* beta, double* se,
                   double* stat, double* neglog10p, double* mean, double* sd, uint8_t* keep);

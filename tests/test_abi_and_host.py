@@ -31,7 +31,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     # the ctypes harness binds exactly the header's symbols
     assert sorted(gbm_b200._lib.SIGNATURES) == decl
     lib = gbm_b200.load()
-    assert lib.gbm_abi_version() == 1
+    assert lib.gbm_abi_version() == 2
 
 
 def test_library_is_sm100a_with_tma_and_dmma():
@@ -199,3 +199,48 @@ def test_host_packer_without_gpu():
     _, bad = gbm_b200.pack_host(C)
     want = int(np.sum((np.rint(C * 240.0) / 240.0) != C))
     assert bad == want and bad > 0
+
+
+def test_host_packer_vector_predicate_equals_the_division():
+    """The AVX2 / AVX-512 packer bodies decide `fl(c/240) == a` without dividing (host_pack.cpp);
+    they must agree with the scalar division element for element: every code, its neighbouring
+    doubles, half-way values, binade edges, specials and random doubles."""
+    import ctypes
+
+    from gbm_b200 import _lib
+
+    lib = _lib.load()
+    codes = np.arange(0, 241, dtype=np.float64) / 240.0
+    cand = [codes]
+    for k in (1, 2, 3, 7):
+        up, dn = codes.copy(), codes.copy()
+        for _ in range(k):
+            up, dn = np.nextafter(up, 2.0), np.nextafter(dn, -1.0)
+        cand += [up, dn]
+    cand.append((np.arange(0, 240) + 0.5) / 240.0)
+    cand.append(np.arange(0, 241, dtype=np.float64) * (1.0 / 240.0))  # c * fl(1/240): often 1 ulp off
+    cand.append(2.0 ** -np.arange(0, 60.0))
+    cand.append(np.array([-0.0, 5e-324, 1e-310, 2.2250738585072014e-308, 1e-300, -1e-300, np.nan, np.inf, -np.inf,
+                          1.0000000000000002, 241.0 / 240.0, 2.0, 1e300, -1.0 / 240.0, 4.0e9, -4.0e9]))
+    rng = np.random.default_rng(11)
+    cand.append(rng.random(20000))
+    cand.append(np.rint(rng.random(20000) * 240.0) / 240.0 + rng.integers(-2, 3, 20000) * 2.0 ** -54)
+    v = np.concatenate(cand)
+    A = np.asfortranarray(np.tile(v, (16, 1)))  # one column of 16 equal values per candidate: the vector body sees it
+    n, p = A.shape
+    got = {}
+    for isa in (0, 1, 2):
+        ok = np.zeros(p, dtype=np.uint8)
+        rc = lib.gbm_pack_host_check(_lib.ptr(A), n, p, n, isa, _lib.ptr(ok))
+        if rc != 0:
+            assert isa > 0  # CPU without that ISA
+            continue
+        got[isa] = ok
+    with np.errstate(all="ignore"):
+        c = np.rint(v * 240.0)
+        want = ((c >= 0) & (c <= 240) & (c / 240.0 == v)).astype(np.uint8)
+    assert np.array_equal(got[0], want)
+    assert len(got) >= 2, "no vector ISA on this host: nothing checked"
+    for isa, ok in got.items():
+        bad = np.nonzero(ok != want)[0]
+        assert bad.size == 0, (isa, v[bad[:5]], ok[bad[:5]], want[bad[:5]])

@@ -111,12 +111,10 @@ def test_scan_host_pack_flag(gbm, kind, expect_packed):
     A, ys, pc = _problem(13, n, p, kind)
     a = gbm.scan_host(A, ys, pc[:, None], model=1, pack=False)
     b = gbm.scan_host(A, ys, pc[:, None], model=1)  # auto-pack is the default
-    packed_blocks = gbm.last_timing()["packed_blocks"]
-    import os
-
-    ws = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
-    enough_cores = len(os.sched_getaffinity(0)) // max(ws, 1) >= 8  # the library's auto-pack rule
-    assert (packed_blocks > 0) == (expect_packed and enough_cores)
+    tm = gbm.last_timing()
+    # a block that is all codes is scanned as codes whichever lane carried it
+    assert (tm["packed_blocks"] > 0) == expect_packed
+    assert tm["host_packed_blocks"] <= tm["packed_blocks"]
     keep = a["keep"]
     assert np.array_equal(keep, b["keep"])
     tol = 1e-11 if expect_packed else 0.0
