@@ -38,10 +38,11 @@ struct State {
   // (pinned host_codes -> dev_codes).  Copy-engine lane: Float64 blocks DMA'd as they are (raw_f64),
   // packed on the device (raw_codes, raw_flag = count of non-code elements).
   static constexpr int kRawSlots = 3;
-  void* host_codes[2] = {nullptr, nullptr};
-  void* dev_codes[2] = {nullptr, nullptr};
+  static constexpr int kHostSlots = 3;
+  void* host_codes[kHostSlots] = {};
+  void* dev_codes[kHostSlots] = {};
   size_t code_bytes = 0;
-  cudaEvent_t hl_copied[2] = {nullptr, nullptr}, hl_consumed[2] = {nullptr, nullptr};
+  cudaEvent_t hl_copied[kHostSlots] = {}, hl_consumed[kHostSlots] = {};
   void* raw_f64[kRawSlots] = {};
   void* raw_codes[kRawSlots] = {};
   size_t raw_bytes = 0, raw_code_bytes = 0;

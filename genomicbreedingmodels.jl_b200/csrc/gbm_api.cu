@@ -200,7 +200,7 @@ static void reset_timing() {
 
 // staging of gbm_scan_host (see State)
 static void free_scan_host_staging(State& st) {
-  for (int b = 0; b < 2; ++b) {
+  for (int b = 0; b < State::kHostSlots; ++b) {
     if (st.host_codes[b]) cudaFreeHost(st.host_codes[b]);
     if (st.dev_codes[b]) cudaFree(st.dev_codes[b]);
     st.host_codes[b] = st.dev_codes[b] = nullptr;
@@ -1239,6 +1239,9 @@ int gbm_scan(const gbm_matrix* m, const double* Y, int64_t T, int64_t ldy, const
 }  // extern "C"
 
 namespace gbm {
+struct PackJob;
+PackJob* pack_submit(const double* A, int64_t n, int64_t lda, int64_t pc, uint8_t* out, int64_t ldo);
+bool pack_wait(PackJob* job, const std::function<void()>* idle);
 bool pack_block_host(const double* A, int64_t n, int64_t lda, int64_t pc, uint8_t* out, int64_t ldo,
                      const std::function<void()>* idle);
 int64_t count_inexact_host(const double* A, int64_t n, int64_t lda, int64_t pc);
@@ -1296,11 +1299,18 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
   //  * copy-engine lane: the block crosses PCIe as Float64 (cudaMemcpyAsync from the caller's pinned
   //    buffer) and is packed on the device.  Pageable memory would make those copies synchronous, so
   //    this lane then only takes what the host lane cannot.
-  bool host_lane = want_codes && !device_src && host_threads() >= 2;
-  bool raw_lane = pinned || !host_lane;
-  if (const char* e = getenv("GBM_SCAN_HOST_LANES")) {  // "host" / "copy": measurement switch
-    if (!strcmp(e, "host") && host_lane) raw_lane = false;
+  // Default: the host lane alone when this process has >= 8 host threads (the packer then out-runs the
+  // PCIe link: ~110 GB/s of Float64 read by 16 cores against 55 GB/s), else the copy-engine lane alone.
+  // Running both at once is a switch (GBM_SCAN_HOST_LANES=both): on the pool's hosts the copy engine's
+  // reads slow the packing cores down by more than they add (measured 82 GB/s together, 100 GB/s host
+  // lane alone), on a host with more memory bandwidth per core it pays.
+  bool host_lane = want_codes && !device_src && host_threads() >= 8;
+  bool raw_lane = !host_lane;
+  if (const char* e = getenv("GBM_SCAN_HOST_LANES")) {
+    const bool can_host = want_codes && !device_src && host_threads() >= 2;
+    if (!strcmp(e, "host") && can_host) host_lane = true, raw_lane = false;
     if (!strcmp(e, "copy")) host_lane = false, raw_lane = true;
+    if (!strcmp(e, "both") && can_host) host_lane = true, raw_lane = pinned;
   }
   // column blocks of ~128 MB of Float64
   const int64_t ldd = round_up(n, 16);
@@ -1336,8 +1346,9 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
     GBM_CUDA(cudaMalloc(reinterpret_cast<void**>(&st.raw_flag_dev), sizeof(unsigned long long) * kRaw));
     GBM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&st.raw_flag_host), sizeof(unsigned long long) * kRaw));
   }
+  constexpr int kHost = State::kHostSlots;
   if (host_lane && st.code_bytes < need8) {
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kHost; ++b) {
       if (st.host_codes[b]) cudaFreeHost(st.host_codes[b]);
       if (st.dev_codes[b]) cudaFree(st.dev_codes[b]);
       st.host_codes[b] = st.dev_codes[b] = nullptr;
@@ -1346,7 +1357,7 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
     }
     st.code_bytes = need8;
   }
-  for (int b = 0; b < 2; ++b) make_event(&st.hl_copied[b]), make_event(&st.hl_consumed[b]);
+  for (int b = 0; b < kHost; ++b) make_event(&st.hl_copied[b]), make_event(&st.hl_consumed[b]);
   for (int b = 0; b < kRaw; ++b) {
     make_event(&st.raw_copied[b]), make_event(&st.raw_packed[b]), make_event(&st.raw_consumed[b]);
     if (ldd != n) GBM_CUDA(cudaMemsetAsync(st.raw_f64[b], 0, need, st.raw_stream));  // pad rows stay zero
@@ -1372,7 +1383,7 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
 
   Span all(st.stream);
   all.start();
-  for (int b = 0; b < 2; ++b) GBM_CUDA(cudaEventRecord(st.hl_consumed[b], st.stream));
+  for (int b = 0; b < kHost; ++b) GBM_CUDA(cudaEventRecord(st.hl_consumed[b], st.stream));
   for (int b = 0; b < kRaw; ++b) GBM_CUDA(cudaEventRecord(st.raw_consumed[b], st.stream));
 
   auto raw_issue = [&](int s) {
@@ -1449,32 +1460,63 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
   const std::function<void()> idle = [&] { raw_service(false); };
 
   raw_service(false);
-  for (int hb = 0; host_lane; hb ^= 1) {
-    const int64_t bi = take_block(false);
-    if (bi < 0) break;
+  // host lane: up to kHost blocks are queued with the packer ahead of the one being waited for, so the
+  // workers never join between blocks
+  struct HostSlots {
+    PackJob* job[State::kHostSlots] = {};
+    int64_t bi[State::kHostSlots] = {};
+    int head = 0, fill = 0, count = 0;
+    ~HostSlots() {  // never leave workers writing into the staging buffers behind an exception
+      for (PackJob*& j : job)
+        if (j) pack_wait(j, nullptr), j = nullptr;
+    }
+  } hs;
+  while (host_lane) {
+    while (hs.count < kHost) {
+      const int64_t bi = take_block(false);
+      if (bi < 0) break;
+      const int s = hs.fill;
+      const int64_t j0 = bi * blk, pc = std::min(blk, p - j0);
+      // the pinned buffer s went to the copy engine kHost host-lane blocks ago: wait for that copy
+      GBM_CUDA(cudaEventSynchronize(st.hl_copied[s]));
+      hs.job[s] = pack_submit(A + j0 * lda, n, lda, pc, static_cast<uint8_t*>(st.host_codes[s]), ld8);
+      hs.bi[s] = bi;
+      hs.fill = (s + 1) % kHost;
+      ++hs.count;
+    }
+    if (hs.count == 0) break;
+    const int s = hs.head;
+    const int64_t bi = hs.bi[s];
     const int64_t j0 = bi * blk, pc = std::min(blk, p - j0);
-    // the pinned buffer hb went to the copy engine two host-lane blocks ago: wait for that copy
-    GBM_CUDA(cudaEventSynchronize(st.hl_copied[hb]));
-    uint8_t* hp = static_cast<uint8_t*>(st.host_codes[hb]);
-    if (!pack_block_host(A + j0 * lda, n, lda, pc, hp, ld8, raw_lane ? &idle : nullptr)) {
-      // not dosage data: this block and the rest travel as Float64
+    PackJob* job = hs.job[s];
+    hs.job[s] = nullptr;
+    hs.head = (s + 1) % kHost;
+    --hs.count;
+    if (!pack_wait(job, raw_lane ? &idle : nullptr)) {
+      // not dosage data: this block, the queued ones and the rest travel as Float64
       handback.push_back(bi);
+      for (; hs.count > 0; --hs.count, hs.head = (hs.head + 1) % kHost) {
+        pack_wait(hs.job[hs.head], nullptr);
+        hs.job[hs.head] = nullptr;
+        handback.push_back(hs.bi[hs.head]);
+      }
       host_lane = false;
       raw_lane = true;
       break;
     }
-    GBM_CUDA(cudaStreamWaitEvent(st.copy_stream, st.hl_consumed[hb], 0));
-    GBM_CUDA(cudaMemcpyAsync(st.dev_codes[hb], hp, static_cast<size_t>(ld8) * pc, cudaMemcpyHostToDevice, st.copy_stream));
-    GBM_CUDA(cudaEventRecord(st.hl_copied[hb], st.copy_stream));
-    GBM_CUDA(cudaStreamWaitEvent(st.stream, st.hl_copied[hb], 0));
+    GBM_CUDA(cudaStreamWaitEvent(st.copy_stream, st.hl_consumed[s], 0));
+    GBM_CUDA(cudaMemcpyAsync(st.dev_codes[s], st.host_codes[s], static_cast<size_t>(ld8) * pc, cudaMemcpyHostToDevice,
+                             st.copy_stream));
+    GBM_CUDA(cudaEventRecord(st.hl_copied[s], st.copy_stream));
+    GBM_CUDA(cudaStreamWaitEvent(st.stream, st.hl_copied[s], 0));
     gbm_matrix view;
     view.n = n;
     view.p = pc;
     view.dtype = 1;
-    view.d8 = static_cast<uint8_t*>(st.dev_codes[hb]);
+    view.d8 = static_cast<uint8_t*>(st.dev_codes[s]);
     view.ld8 = ld8;
     scan_block(view, pc, passes, no_rec, sv.k_eff, model, kflags, out.view(), p, j0, nullptr);
-    GBM_CUDA(cudaEventRecord(st.hl_consumed[hb], st.stream));
+    GBM_CUDA(cudaEventRecord(st.hl_consumed[s], st.stream));
     ++code_blocks;
     ++host_blocks;
     h2d_bytes += ld8 * pc;

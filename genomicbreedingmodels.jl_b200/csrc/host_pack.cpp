@@ -13,7 +13,9 @@
 #include <chrono>
 #include <exception>
 #include <condition_variable>
+#include <algorithm>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -76,13 +78,17 @@ __attribute__((target("avx2,fma"))) static bool pack_col_avx2(const double* col,
   return bad;
 }
 
-__attribute__((target("avx512f,avx512vl,avx512dq"))) static bool pack_col_avx512(const double* col, int64_t n, uint8_t* dst) {
+__attribute__((target("avx512f,avx512vl,avx512dq"))) static bool pack_col_avx512(const double* col, int64_t n, uint8_t* dst, int pf) {
   const __m512d k240 = _mm512_set1_pd(240.0), k120 = _mm512_set1_pd(120.0), one = _mm512_set1_pd(1.0);
   const __m512d two52 = _mm512_set1_pd(4503599627370496.0), zero = _mm512_setzero_pd();
   const __m512i expmask = _mm512_set1_epi64(0x7FF0000000000000ll);
   __mmask8 good = 0xFF;
   int64_t i = 0;
   for (; i + 16 <= n; i += 16) {
+    // software prefetch one page ahead: the hardware streamer stops at 4 KB boundaries (pinned host
+    // memory is 4 KB-paged) and the early touch also starts the page walk
+    _mm_prefetch(reinterpret_cast<const char*>(col + i) + pf, _MM_HINT_T0);
+    _mm_prefetch(reinterpret_cast<const char*>(col + i) + pf + 64, _MM_HINT_T0);
     const __m512d a0 = _mm512_loadu_pd(col + i), a1 = _mm512_loadu_pd(col + i + 8);
     const __m256i c0 = _mm512_cvtpd_epi32(_mm512_mul_pd(a0, k240));
     const __m256i c1 = _mm512_cvtpd_epi32(_mm512_mul_pd(a1, k240));
@@ -105,6 +111,14 @@ __attribute__((target("avx512f,avx512vl,avx512dq"))) static bool pack_col_avx512
   return bad;
 }
 
+static int pack_prefetch_bytes() {
+  static const int v = [] {
+    const char* e = getenv("GBM_PACK_PREFETCH");
+    return e ? atoi(e) : 4096;
+  }();
+  return v;
+}
+
 // 0 scalar, 1 avx2+fma, 2 avx512; GBM_PACK_ISA=scalar|avx2|avx512 caps it (testing)
 static int pack_isa() {
   static const int v = [] {
@@ -123,98 +137,21 @@ static int pack_isa() {
   return v;
 }
 
-// packs columns [c0, c1) of the block; stops early once `stop` is raised (another worker
-// found an element that is not a code) and raises it itself in that case
-static void pack_columns(const double* A, int64_t n, int64_t lda, int64_t c0, int64_t c1, uint8_t* out, int64_t ldo,
-                         std::atomic<int>* stop) {
+// packs columns [c0, c1) of the block; returns true when an element is not a code
+static bool pack_columns(const double* A, int64_t n, int64_t lda, int64_t c0, int64_t c1, uint8_t* out, int64_t ldo) {
   const int isa = pack_isa();
+  const int pf = pack_prefetch_bytes();
   for (int64_t j = c0; j < c1; ++j) {
-    if (stop->load(std::memory_order_relaxed)) return;
     const double* col = A + j * lda;
     uint8_t* dst = out + j * ldo;
-    const bool bad = isa == 2   ? pack_col_avx512(col, n, dst)
+    const bool bad = isa == 2   ? pack_col_avx512(col, n, dst, pf)
                      : isa == 1 ? pack_col_avx2(col, n, dst)
                                 : pack_col_scalar(col, n, dst, 0);
     for (int64_t i = n; i < ldo; ++i) dst[i] = 0;
-    if (bad) {
-      stop->store(1, std::memory_order_relaxed);
-      return;
-    }
+    if (bad) return true;
   }
+  return false;
 }
-
-// ---- persistent workers ---------------------------------------------------------------
-class Pool {
- public:
-  explicit Pool(int n) : n_(n) {
-    for (int t = 0; t < n_; ++t) workers_.emplace_back([this, t] { loop(t); });
-  }
-  ~Pool() {
-    {
-      std::lock_guard<std::mutex> lk(m_);
-      quit_ = true;
-      ++epoch_;
-    }
-    cv_.notify_all();
-    for (auto& w : workers_) w.join();
-  }
-  int size() const { return n_; }
-  // Runs fn(t) on every worker and waits.  While waiting, the calling thread invokes *idle
-  // about every 100 us (gbm_scan_host services its copy-engine lane there); an exception from
-  // idle is re-thrown once the workers have finished.
-  void run(const std::function<void(int)>& fn, const std::function<void()>* idle = nullptr) {
-    std::unique_lock<std::mutex> lk(m_);
-    fn_ = &fn;
-    pending_ = n_;
-    ++epoch_;
-    cv_.notify_all();
-    std::exception_ptr err;
-    while (pending_ != 0) {
-      if (!idle || err) {
-        done_.wait(lk, [this] { return pending_ == 0; });
-        break;
-      }
-      if (done_.wait_for(lk, std::chrono::microseconds(100), [this] { return pending_ == 0; })) break;
-      lk.unlock();
-      try {
-        (*idle)();
-      } catch (...) {
-        err = std::current_exception();
-      }
-      lk.lock();
-    }
-    fn_ = nullptr;
-    if (err) std::rethrow_exception(err);
-  }
-
- private:
-  void loop(int t) {
-    uint64_t seen = 0;
-    for (;;) {
-      const std::function<void(int)>* fn;
-      {
-        std::unique_lock<std::mutex> lk(m_);
-        cv_.wait(lk, [&] { return epoch_ != seen; });
-        seen = epoch_;
-        if (quit_) return;
-        fn = fn_;
-      }
-      (*fn)(t);
-      {
-        std::lock_guard<std::mutex> lk(m_);
-        if (--pending_ == 0) done_.notify_one();
-      }
-    }
-  }
-  int n_;
-  std::vector<std::thread> workers_;
-  std::mutex m_;
-  std::condition_variable cv_, done_;
-  const std::function<void(int)>* fn_ = nullptr;
-  int pending_ = 0;
-  uint64_t epoch_ = 0;
-  bool quit_ = false;
-};
 
 int host_threads() {
   int t = 0;
@@ -230,33 +167,131 @@ int host_threads() {
   return t > 64 ? 64 : t;
 }
 
-static Pool& pool() {
-  static Pool p(host_threads());
-  return p;
+// ---- persistent workers over a queue of block jobs -----------------------------------------
+// A job is one column block cut into chunks of ~256 KB of Float64.  Workers take chunks from the
+// oldest job that still has some, so several submitted blocks are packed back to back without a
+// join between them (gbm_scan_host keeps a few blocks submitted ahead of the one it waits for).
+struct PackJob {
+  const double* A;
+  int64_t n, lda, pc;
+  uint8_t* out;
+  int64_t ldo;
+  int64_t chunk, nchunks;
+  int64_t next = 0, done = 0;  // guarded by the queue mutex
+  std::atomic<int> bad{0};
+};
+
+class PackQueue {
+ public:
+  explicit PackQueue(int n) {
+    for (int t = 0; t < n; ++t) workers_.emplace_back([this] { loop(); });
+  }
+  ~PackQueue() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      quit_ = true;
+    }
+    work_.notify_all();
+    for (auto& w : workers_) w.join();
+  }
+  void submit(PackJob* job) {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      jobs_.push_back(job);
+    }
+    work_.notify_all();
+  }
+  // Waits for the job, removes it from the queue.  While waiting the calling thread invokes *idle
+  // about every 100 us; an exception from idle is re-thrown once the job has finished.
+  void wait(PackJob* job, const std::function<void()>* idle) {
+    std::unique_lock<std::mutex> lk(m_);
+    std::exception_ptr err;
+    auto finished = [job] { return job->done == job->nchunks; };
+    while (!finished()) {
+      if (!idle || err) {
+        done_.wait(lk, finished);
+        break;
+      }
+      if (done_.wait_for(lk, std::chrono::microseconds(100), finished)) break;
+      lk.unlock();
+      try {
+        (*idle)();
+      } catch (...) {
+        err = std::current_exception();
+      }
+      lk.lock();
+    }
+    for (size_t i = 0; i < jobs_.size(); ++i)
+      if (jobs_[i] == job) {
+        jobs_.erase(jobs_.begin() + i);
+        break;
+      }
+    if (err) std::rethrow_exception(err);
+  }
+
+ private:
+  void loop() {
+    std::unique_lock<std::mutex> lk(m_);
+    for (;;) {
+      PackJob* job = nullptr;
+      for (PackJob* j : jobs_)
+        if (j->next < j->nchunks) {
+          job = j;
+          break;
+        }
+      if (!job) {
+        if (quit_) return;
+        work_.wait(lk);
+        continue;
+      }
+      const int64_t c = job->next++;
+      lk.unlock();
+      if (!job->bad.load(std::memory_order_relaxed)) {
+        const int64_t c0 = c * job->chunk, c1 = std::min(job->pc, c0 + job->chunk);
+        if (pack_columns(job->A, job->n, job->lda, c0, c1, job->out, job->ldo)) job->bad.store(1, std::memory_order_relaxed);
+      }
+      lk.lock();
+      if (++job->done == job->nchunks) done_.notify_all();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::vector<PackJob*> jobs_;
+  std::mutex m_;
+  std::condition_variable work_, done_;
+  bool quit_ = false;
+};
+
+static PackQueue& pack_queue() {
+  static PackQueue q(host_threads());
+  return q;
 }
 
-// Packs the n x pc block at A (pitch lda) into out (pitch ldo bytes, rows n..ldo-1 zeroed).
-// Returns true when every element is exactly a code; false as soon as one is not (out is then
-// incomplete and must not be used).
+// Queues the n x pc block at A (pitch lda) for packing into out (pitch ldo bytes, rows n..ldo-1 zeroed).
+PackJob* pack_submit(const double* A, int64_t n, int64_t lda, int64_t pc, uint8_t* out, int64_t ldo) {
+  PackJob* job = new PackJob;
+  job->A = A;
+  job->n = n;
+  job->lda = lda;
+  job->pc = pc;
+  job->out = out;
+  job->ldo = ldo;
+  job->chunk = std::max<int64_t>(1, (int64_t(256) << 10) / (8 * n));
+  job->nchunks = (pc + job->chunk - 1) / job->chunk;
+  pack_queue().submit(job);
+  return job;
+}
+
+// Waits for a submitted block and frees the job.  True when every element is exactly a code; false as soon as
+// one is not (out is then incomplete and must not be used).
+bool pack_wait(PackJob* job, const std::function<void()>* idle) {
+  std::unique_ptr<PackJob> own(job);
+  pack_queue().wait(job, idle);
+  return job->bad.load() == 0;
+}
+
 bool pack_block_host(const double* A, int64_t n, int64_t lda, int64_t pc, uint8_t* out, int64_t ldo,
                      const std::function<void()>* idle) {
-  Pool& pl = pool();
-  const int T = pl.size();
-  std::atomic<int> stop(0);
-  // interleaved chunks of 16 columns keep the workers' streams close together in memory
-  const int64_t chunk = 16;
-  const int64_t nchunks = (pc + chunk - 1) / chunk;
-  std::atomic<int64_t> next(0);
-  pl.run([&](int) {
-    for (;;) {
-      const int64_t c = next.fetch_add(1, std::memory_order_relaxed);
-      if (c >= nchunks || stop.load(std::memory_order_relaxed)) return;
-      const int64_t c0 = c * chunk, c1 = c0 + chunk < pc ? c0 + chunk : pc;
-      pack_columns(A, n, lda, c0, c1, out, ldo, &stop);
-    }
-  }, idle);
-  (void)T;
-  return stop.load() == 0;
+  return pack_wait(pack_submit(A, n, lda, pc, out, ldo), idle);
 }
 
 // Testing hook: the single-column packer body of one ISA level (0 scalar with the division,
@@ -270,7 +305,7 @@ bool pack_check_columns(const double* A, int64_t n, int64_t lda, int64_t pc, int
   std::vector<uint8_t> tmp(static_cast<size_t>(n) + 64);
   for (int64_t j = 0; j < pc; ++j) {
     const double* col = A + j * lda;
-    const bool bad = isa == 2   ? pack_col_avx512(col, n, tmp.data())
+    const bool bad = isa == 2   ? pack_col_avx512(col, n, tmp.data(), 4096)
                      : isa == 1 ? pack_col_avx2(col, n, tmp.data())
                                 : pack_col_scalar(col, n, tmp.data(), 0);
     col_ok[j] = bad ? 0 : 1;
@@ -278,25 +313,28 @@ bool pack_check_columns(const double* A, int64_t n, int64_t lda, int64_t pc, int
   return true;
 }
 
-// count of inexact elements (no early exit) -- for gbm_pack_host's report
+// count of inexact elements (no early exit) -- for gbm_pack_host's report; failure path only
 int64_t count_inexact_host(const double* A, int64_t n, int64_t lda, int64_t pc) {
-  Pool& pl = pool();
-  std::vector<int64_t> bad(pl.size(), 0);
+  const int T = host_threads();
+  std::vector<int64_t> bad(T, 0);
   std::atomic<int64_t> next(0);
-  pl.run([&](int t) {
-    int64_t local = 0;
-    for (;;) {
-      const int64_t j = next.fetch_add(1, std::memory_order_relaxed);
-      if (j >= pc) break;
-      const double* col = A + j * lda;
-      for (int64_t i = 0; i < n; ++i) {
-        const double a = col[i], s = a * 240.0;
-        const int code = (s >= -0.5 && s < 240.5) ? static_cast<int>(s + 0.5) : 0;
-        local += (static_cast<double>(code) / 240.0 != a);
+  std::vector<std::thread> th;
+  for (int t = 0; t < T; ++t)
+    th.emplace_back([&, t] {
+      int64_t local = 0;
+      for (;;) {
+        const int64_t j = next.fetch_add(1, std::memory_order_relaxed);
+        if (j >= pc) break;
+        const double* col = A + j * lda;
+        for (int64_t i = 0; i < n; ++i) {
+          const double a = col[i], s = a * 240.0;
+          const int code = (s >= -0.5 && s < 240.5) ? static_cast<int>(s + 0.5) : 0;
+          local += (static_cast<double>(code) / 240.0 != a);
+        }
       }
-    }
-    bad[t] = local;
-  });
+      bad[t] = local;
+    });
+  for (auto& x : th) x.join();
   int64_t tot = 0;
   for (int64_t b : bad) tot += b;
   return tot;

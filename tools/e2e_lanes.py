@@ -79,3 +79,35 @@ for name, lanes, flags in (("float64 copies, Float64 kernel (NO_PACK)", None, _l
         else:
             out["identical_to_other_lane"] = all(np.array_equal(ref[k], hout[k], equal_nan=True) for k in ref)
     print(json.dumps(out), flush=True)
+
+# does the copy engine slow the packing cores down?  pack the pinned buffer on all cores while plain
+# pinned H2D copies of another pinned buffer run back to back
+import threading
+
+os.environ.pop("GBM_SCAN_HOST_LANES", None)
+other = torch.empty((pe // 4, n), dtype=torch.float64, pin_memory=True)
+other.zero_()
+dev = torch.empty_like(other, device="cuda")
+codes = np.empty((n, pe), dtype=np.uint8, order="F")
+res = {}
+
+
+def packer():
+    t0 = time.perf_counter()
+    for _ in range(3):
+        _lib.check(lib.gbm_pack_host(_lib.ptr(host), n, pe, n, _lib.ptr(codes), n, ctypes.byref(bad)))
+    res["pack_GBps"] = 3 * 8.0 * n * pe / (time.perf_counter() - t0) / 1e9
+
+
+th = threading.Thread(target=packer)
+th.start()
+copied = 0
+t0 = time.perf_counter()
+while th.is_alive():
+    dev.copy_(other, non_blocking=True)
+    torch.cuda.synchronize()
+    copied += other.numel() * 8
+res["h2d_GBps"] = copied / (time.perf_counter() - t0) / 1e9
+th.join()
+res["what"] = "gbm_pack_host and plain pinned H2D copies at the same time"
+print(json.dumps(res), flush=True)
