@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-packed", action="store_true")
     ap.add_argument("--cpu-markers", type=int, default=0, help="markers in the CPU sample (0: sized for ~10-20 s)")
+    ap.add_argument("--no-transform", action="store_true", help="skip the pairwise transformation screen (SURVEY 8f-4)")
+    ap.add_argument("--transform-l", type=int, default=8192, help="loci in the pairwise screen (l^2 regressions)")
     ap.add_argument("--pipeline", action="store_true", help="also time the whole gwaslmm pipeline (GRM + PC1) once")
     ap.add_argument("--lmm-markers", type=int, default=0,
                     help="also run the GRM-covariance LMM engine (eigen-rotation GEMM + per-marker delta search) "
@@ -493,6 +495,9 @@ def main():
         if i8 is not None:
             line["grm_int8"] = i8
 
+    if rank == 0 and not args.no_transform:
+        line["transform2"] = run_transform2(gbm_b200, n, args.transform_l)
+
     if rank == 0 and args.pipeline:
         line["pipeline"] = run_pipeline(gbm_b200, _lib, n, p_loc, j0, ys)
 
@@ -587,6 +592,34 @@ def run_pipeline(gbm_b200, _lib, n, p_loc, j0, ys):
         pkd["filter_identical"] = bool(np.array_equal(st2["idx_cols"], st["idx_cols"]))
         out["packed_int8"] = pkd
         pk.free()
+    dm.free()
+    return out
+
+
+def run_transform2(gbm_b200, n, l):
+    """Pairwise transformation screen (transform2 with f = mult, transformation.jl:319-466): l^2
+    regressions y ~ 1 + x_i x_j on a resident n x l matrix.  FP64-pipe-bound: 5 FP64 instructions
+    per (pair, row); the roofline is the 64 FP64 instructions / clk / SM of the B200 pipe."""
+    from gbm_b200 import _lib, transform as tr
+
+    dm = gbm_b200.DeviceMatrix.generate(SEED, n, l, KIND_DIPLOID)
+    rng = np.random.default_rng(5)
+    y = rng.normal(size=n)
+    out = {"workload": f"transform2(mult) n={n} l={l}: {l * l} regressions (ordered pairs)"}
+    for f, name, instr in ((tr.mult, "mult", 5), (tr.raise_, "raise", None)):
+        tr.transform2_screen(dm, y, f, 1000)
+        t0 = time.perf_counter()
+        _, cnt, _ = tr.transform2_screen(dm, y, f, 1000)
+        wall = time.perf_counter() - t0
+        ms = _lib.last_timing()["main_ms"]
+        d = {"pair_kernel_ms": ms, "regressions_per_s": l * l / (ms * 1e-3), "wall_s_with_selection": wall,
+             "selected": int(cnt.size)}
+        if instr:
+            info = _lib.device_info()
+            per_clk = instr * float(l) * l * n / (ms * 1e-3) / (info["sm_count"] * 1.965e9)
+            d["fp64_instr_per_clk_per_sm"] = per_clk
+            d["frac_of_fp64_pipe"] = per_clk / 64.0
+        out[name] = d
     dm.free()
     return out
 

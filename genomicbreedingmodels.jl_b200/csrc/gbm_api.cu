@@ -1778,3 +1778,200 @@ int gbm_measure_copy_bandwidth(int64_t bytes, int reps, double* gbps) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------
+// transformation screens (transform1 / transform2 of transformation.jl)
+// ------------------------------------------------------------------------------------
+namespace {
+
+// Float64 view of a handle: the slab itself, or a decoded copy of a packed one
+struct F64View {
+  const double* d = nullptr;
+  int64_t lda = 0;
+  std::unique_ptr<DevBuf<double>> tmp;
+  F64View(const gbm_matrix* m, cudaStream_t s) {
+    if (m->dtype == 0) {
+      d = m->d;
+      lda = m->lda;
+    } else {
+      lda = round_up(m->n, 16);
+      tmp.reset(new DevBuf<double>(static_cast<size_t>(lda) * m->p, s));
+      launch_decode_u8(m->d8, m->n, m->p, m->ld8, tmp->p, lda, s);
+      d = tmp->p;
+    }
+    if ((lda & 1) != 0 || (reinterpret_cast<uintptr_t>(d) & 15u) != 0)
+      GBM_THROW(GBM_ERR_ARGUMENT, "device matrix must be 16-byte aligned with an even leading dimension");
+  }
+};
+
+// y -> (ybar, device copy of y - ybar)
+struct CentredTrait {
+  double ybar = 0.0;
+  DevBuf<double> dyc;
+  CentredTrait(const double* y, int64_t n, cudaStream_t s) : dyc(static_cast<size_t>(round_up(n, 2)), s) {
+    std::vector<double> h(static_cast<size_t>(round_up(n, 2)), 0.0);
+    GBM_CUDA(cudaMemcpy(h.data(), y, sizeof(double) * n, cudaMemcpyDefault));
+    long double sum = 0;
+    for (int64_t i = 0; i < n; ++i) sum += h[i];
+    ybar = static_cast<double>(sum / n);
+    for (int64_t i = 0; i < n; ++i) h[i] -= ybar;
+    GBM_CUDA(cudaMemcpyAsync(dyc.p, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, s));
+    GBM_CUDA(cudaStreamSynchronize(s));
+  }
+};
+
+void check_transform_args(const gbm_matrix* m, const double* y, int64_t n_new, const void* idx, const int64_t* count) {
+  if (!m || !y || !idx || !count) GBM_THROW(GBM_ERR_ARGUMENT, "transform screen: null pointer");
+  if (m->n < 2) GBM_THROW(GBM_ERR_ARGUMENT, "transform screen: at least 2 entries are needed");
+  if (n_new < 0) GBM_THROW(GBM_ERR_ARGUMENT, "transform screen: n_new_features_per_transformation must not be negative");
+}
+
+const char* kCannotTransform =
+    "Cannot transform the allele frequencies using this function (NaN effects). Please consider adding a larger "
+    "`\xcf\xb5` and/or using absolute values, i.e. use `use_abs=true`.";
+
+}  // namespace
+
+extern "C" {
+
+int gbm_transform1_screen(const gbm_matrix* m, const double* y, int f, double eps, int use_abs, double var_threshold,
+                          int64_t n_new, double* beta, int64_t* idx, int64_t* count) {
+  GBM_API_BEGIN
+  require_ready();
+  check_transform_args(m, y, n_new, idx, count);
+  if (f < GBM_F1_SQUARE || f > GBM_F1_LOG10EPS) GBM_THROW(GBM_ERR_ARGUMENT, "transform1: unknown transformation code");
+  if (n_new > m->p)  // sortperm(...)[1:n_new] on a shorter vector (transformation.jl:212)
+    GBM_THROW(GBM_ERR_ARGUMENT, "BoundsError: attempt to access " + std::to_string(m->p) + "-element Vector{Int64} at index [1:" +
+                                    std::to_string(n_new) + "]");
+  State& st = state();
+  reset_timing();
+  F64View A(m, st.stream);
+  CentredTrait yt(y, m->n, st.stream);
+  DevBuf<double> dbeta(static_cast<size_t>(m->p), st.stream);
+  Span mainsp(st.stream);
+  mainsp.start();
+  launch_transform1_scan(f, A.d, m->n, m->p, A.lda, yt.dyc.p, yt.ybar, eps, use_abs, var_threshold, dbeta.p, nullptr,
+                         st.sm_count, st.stream);
+  mainsp.stop();
+  bool has_nan = false;
+  *count = transform_select(dbeta.p, m->p, n_new, eps, idx, nullptr, &has_nan, st.sm_count, st.stream);
+  if (beta) copy_out(beta, dbeta.p, sizeof(double) * m->p, st.stream);
+  GBM_CUDA(cudaStreamSynchronize(st.stream));
+  st.main_ms = st.kernel_ms = mainsp.ms();
+  st.launches = 1;
+  if (has_nan) GBM_THROW(GBM_ERR_ARGUMENT, kCannotTransform);
+  GBM_API_END
+}
+
+int gbm_transform2_screen(const gbm_matrix* m, const double* y, int f, double eps, int use_abs, double var_threshold,
+                          int commutative, int64_t n_new, double* beta, int64_t* counters, double* beta_sel,
+                          int64_t* count) {
+  GBM_API_BEGIN
+  require_ready();
+  check_transform_args(m, y, n_new, counters, count);
+  if (f < GBM_F2_MULT || f > GBM_F2_RAISE) GBM_THROW(GBM_ERR_ARGUMENT, "transform2: unknown transformation code");
+  const int64_t l = m->p;
+  if (l > 3000000) GBM_THROW(GBM_ERR_ARGUMENT, "transform2: l^2 effects do not fit");
+  if (n_new > l * l)
+    GBM_THROW(GBM_ERR_ARGUMENT, "BoundsError: attempt to access " + std::to_string(l * l) + "-element Vector{Int64} at index [1:" +
+                                    std::to_string(n_new) + "]");
+  State& st = state();
+  reset_timing();
+  F64View A(m, st.stream);
+  CentredTrait yt(y, m->n, st.stream);
+  DevBuf<double> dvar(static_cast<size_t>(l), st.stream);
+  // beta on the device: the caller's buffer when it is device memory, else scratch
+  const bool user_dev = beta && is_device_ptr(beta);
+  DevBuf<double> dscratch(user_dev ? 0 : static_cast<size_t>(l) * l, st.stream);
+  double* dbeta = user_dev ? beta : dscratch.p;
+  GBM_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(double) * l * l, st.stream));
+  launch_transform1_scan(-1, A.d, m->n, l, A.lda, yt.dyc.p, yt.ybar, eps, use_abs, var_threshold, nullptr, dvar.p,
+                         st.sm_count, st.stream);
+  Span mainsp(st.stream);
+  mainsp.start();
+  launch_transform2_scan(f, A.d, m->n, l, A.lda, yt.dyc.p, yt.ybar, dvar.p, eps, use_abs, var_threshold, commutative,
+                         dbeta, st.stream);
+  mainsp.stop();
+  bool has_nan = false;
+  std::vector<int64_t> sel(static_cast<size_t>(std::max<int64_t>(n_new, 1)));
+  std::vector<double> val(sel.size());
+  const int64_t cnt = transform_select(dbeta, l * l, n_new, eps, sel.data(), val.data(), &has_nan, st.sm_count, st.stream);
+  // sort!(idx) (transformation.jl:430): ascending positions, values follow
+  std::vector<int64_t> order(static_cast<size_t>(cnt));
+  for (int64_t k = 0; k < cnt; ++k) order[k] = k;
+  std::sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return sel[a] < sel[b]; });
+  for (int64_t k = 0; k < cnt; ++k) {
+    counters[k] = sel[order[k]];
+    if (beta_sel) beta_sel[k] = val[order[k]];
+  }
+  *count = cnt;
+  if (beta && !user_dev) copy_out(beta, dbeta, sizeof(double) * l * l, st.stream);
+  GBM_CUDA(cudaStreamSynchronize(st.stream));
+  st.main_ms = st.kernel_ms = mainsp.ms();
+  st.launches = 2;
+  if (has_nan) GBM_THROW(GBM_ERR_ARGUMENT, kCannotTransform);
+  GBM_API_END
+}
+
+static void check_apply_args(const gbm_matrix* m, const int64_t* idx, int64_t count, const double* T, int64_t ldt) {
+  if (!m || count < 0 || (count > 0 && (!idx || !T)) || ldt < (m ? m->n : 0))
+    GBM_THROW(GBM_ERR_ARGUMENT, "transform apply: bad arguments");
+}
+
+// copies a 1-based index list to the device after range-checking it against [1, hi]
+static void upload_indices(const int64_t* idx, int64_t count, int64_t hi, int64_t* dst, cudaStream_t s) {
+  std::vector<int64_t> h(static_cast<size_t>(count));
+  GBM_CUDA(cudaMemcpy(h.data(), idx, sizeof(int64_t) * count, cudaMemcpyDefault));
+  for (int64_t v : h)
+    if (v < 1 || v > hi) GBM_THROW(GBM_ERR_ARGUMENT, "transform apply: feature index out of bounds");
+  GBM_CUDA(cudaMemcpyAsync(dst, h.data(), sizeof(int64_t) * count, cudaMemcpyHostToDevice, s));
+  GBM_CUDA(cudaStreamSynchronize(s));
+}
+
+int gbm_transform1_apply(const gbm_matrix* m, int f, double eps, int use_abs, const int64_t* idx, int64_t count,
+                         double* T, int64_t ldt) {
+  GBM_API_BEGIN
+  require_ready();
+  check_apply_args(m, idx, count, T, ldt);
+  if (f < GBM_F1_SQUARE || f > GBM_F1_LOG10EPS) GBM_THROW(GBM_ERR_ARGUMENT, "transform1: unknown transformation code");
+  if (count == 0) return GBM_OK;
+  State& st = state();
+  F64View A(m, st.stream);
+  DevBuf<int64_t> didx(static_cast<size_t>(count), st.stream);
+  upload_indices(idx, count, m->p, didx.p, st.stream);
+  const bool user_dev = is_device_ptr(T);
+  DevBuf<double> dscratch(user_dev ? 0 : static_cast<size_t>(m->n) * count, st.stream);
+  double* dT = user_dev ? T : dscratch.p;
+  const int64_t ld = user_dev ? ldt : m->n;
+  launch_transform1_apply(f, A.d, m->n, A.lda, didx.p, count, eps, use_abs, dT, ld, st.stream);
+  if (!user_dev)
+    GBM_CUDA(cudaMemcpy2DAsync(T, ldt * sizeof(double), dT, ld * sizeof(double), m->n * sizeof(double), count,
+                               cudaMemcpyDeviceToHost, st.stream));
+  GBM_CUDA(cudaStreamSynchronize(st.stream));
+  GBM_API_END
+}
+
+int gbm_transform2_apply(const gbm_matrix* m, int f, double eps, int use_abs, const int64_t* counters, int64_t count,
+                         double* T, int64_t ldt) {
+  GBM_API_BEGIN
+  require_ready();
+  check_apply_args(m, counters, count, T, ldt);
+  if (f < GBM_F2_MULT || f > GBM_F2_RAISE) GBM_THROW(GBM_ERR_ARGUMENT, "transform2: unknown transformation code");
+  if (count == 0) return GBM_OK;
+  State& st = state();
+  F64View A(m, st.stream);
+  DevBuf<int64_t> didx(static_cast<size_t>(count), st.stream);
+  upload_indices(counters, count, m->p * m->p, didx.p, st.stream);
+  const bool user_dev = is_device_ptr(T);
+  DevBuf<double> dscratch(user_dev ? 0 : static_cast<size_t>(m->n) * count, st.stream);
+  double* dT = user_dev ? T : dscratch.p;
+  const int64_t ld = user_dev ? ldt : m->n;
+  launch_transform2_apply(f, A.d, m->n, m->p, A.lda, didx.p, count, eps, use_abs, dT, ld, st.stream);
+  if (!user_dev)
+    GBM_CUDA(cudaMemcpy2DAsync(T, ldt * sizeof(double), dT, ld * sizeof(double), m->n * sizeof(double), count,
+                               cudaMemcpyDeviceToHost, st.stream));
+  GBM_CUDA(cudaStreamSynchronize(st.stream));
+  GBM_API_END
+}
+
+}  // extern "C"

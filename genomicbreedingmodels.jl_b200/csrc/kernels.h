@@ -104,4 +104,24 @@ void launch_lmm_delta(int Q0, const double* Ar, int64_t n, int64_t pb, int64_t l
 // null-model log(delta) on the host from rotated vectors
 double lmm_null_lam0(int Q0, const double* S, const double* Cr, int64_t ldcr, const double* Yr, int64_t n);
 
+// transform.cu -------------------------------------------------------------------------
+// Per-locus OLS screen of f(x): beta[j] (0 when var(x) < var_thr) and colvar[j] = var(x) (nullable).
+// f = -1: variance pass only.  yc = y - ybar (device, n).
+void launch_transform1_scan(int f, const double* A, int64_t n, int64_t p, int64_t lda, const double* yc, double ybar,
+                            double eps, int use_abs, double var_thr, double* beta, double* colvar, int sm_count,
+                            cudaStream_t stream);
+// Pairwise screen: beta[(i-1) l + (j-1)] for every evaluated pair; beta must be zeroed by the caller.
+void launch_transform2_scan(int f, const double* A, int64_t n, int64_t l, int64_t lda, const double* yc, double ybar,
+                            const double* colvar, double eps, int use_abs, double var_thr, int commutative,
+                            double* beta, cudaStream_t stream);
+void launch_transform1_apply(int f, const double* A, int64_t n, int64_t lda, const int64_t* idx, int64_t count,
+                             double eps, int use_abs, double* T, int64_t ldt, cudaStream_t stream);
+void launch_transform2_apply(int f, const double* A, int64_t n, int64_t l, int64_t lda, const int64_t* counters,
+                             int64_t count, double eps, int use_abs, double* T, int64_t ldt, cudaStream_t stream);
+// top n_new of abs(beta) in Julia's stable sortperm order, filtered by abs(beta) > eps; returns the count,
+// idx_host (1-based) and optionally the selected values.  A NaN among the top entries is reported by *has_nan.
+int64_t transform_select(const double* beta_dev, int64_t len, int64_t n_new, double eps, int64_t* idx_host,
+                         double* beta_host, bool* has_nan, int sm_count, cudaStream_t stream);
+void launch_gather_values(const double* src, const long long* idx1, int64_t count, double* dst, cudaStream_t stream);
+
 }  // namespace gbm

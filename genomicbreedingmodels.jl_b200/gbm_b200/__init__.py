@@ -6,10 +6,12 @@ from ._lib import ArgumentError, CudaError, ErrorException, build, init, last_ti
 from .core import DeviceMatrix, LmmPlan, ScanPlan, gemm_tn, grm_finalize, kstd_pc1, kstd_pc1_device, measure_copy_bandwidth, neglog10_sf, pack_host, scan_host
 from .gwas import extractxyetc, grmploidyaware, grmsimple, gwaslmm, gwasols, gwasprep, gwasreml
 from .structs import GRM, Fit, Genomes, Phenomes
+from . import transform
+from .transform import epistasisfeatures, transform1, transform2
 
 __all__ = [
     "ArgumentError", "CudaError", "ErrorException", "build", "init", "load", "last_timing", "DeviceMatrix", "LmmPlan", "ScanPlan", "gemm_tn",
     "grm_finalize", "kstd_pc1", "kstd_pc1_device", "measure_copy_bandwidth", "neglog10_sf", "pack_host", "scan_host",
     "extractxyetc", "grmploidyaware", "grmsimple", "gwaslmm", "gwasols", "gwasprep", "gwasreml", "GRM", "Fit", "Genomes",
-    "Phenomes",
+    "Phenomes", "transform", "transform1", "transform2", "epistasisfeatures",
 ]

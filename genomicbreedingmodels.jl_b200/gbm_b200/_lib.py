@@ -87,6 +87,11 @@ SIGNATURES = {
     "gbm_lmm_plan_run": (c_int, [c_void_p, c_void_p, c_int, _P, _P, _P, _P, _P, POINTER(c_double), POINTER(c_double)]),
     "gbm_lmm_plan_free": (c_int, [c_void_p]),
     "gbm_gemm_tn": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_int64, c_int64, POINTER(c_double)]),
+    "gbm_transform1_screen": (c_int, [c_void_p, _P, c_int, c_double, c_int, c_double, c_int64, _P, _P, POINTER(c_int64)]),
+    "gbm_transform2_screen": (c_int, [c_void_p, _P, c_int, c_double, c_int, c_double, c_int, c_int64, _P, _P, _P,
+                                      POINTER(c_int64)]),
+    "gbm_transform1_apply": (c_int, [c_void_p, c_int, c_double, c_int, _P, c_int64, _P, c_int64]),
+    "gbm_transform2_apply": (c_int, [c_void_p, c_int, c_double, c_int, _P, c_int64, _P, c_int64]),
     "gbm_neglog10_sf": (c_int, [_P, c_int64, c_int, c_double, _P]),
     "gbm_measure_copy_bandwidth": (c_int, [c_int64, c_int, POINTER(c_double)]),
 }

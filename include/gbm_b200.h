@@ -213,6 +213,36 @@ int gbm_lmm_plan_free(gbm_lmm_plan* plan);
 int gbm_gemm_tn(const double* dA, int64_t lda, const double* dB, int64_t ldb, double* dC, int64_t ldc, int64_t M,
                 int64_t N, int64_t K, double* tflops);
 
+/* ---- transformation screens: the regressions of transform1 / transform2 /
+ *      epistasisfeatures (/root/reference/src/transformation.jl:130-239, :319-466, :540-651) ----------
+ * The reference calls `ols(genomes = g, phenomes = p)` ([1 f(x)] \ y, linear.jl:85) once per locus
+ * (transform1) or once per ordered pair of loci (transform2: l^2 fits) and keeps b_hat[2].  `f` is one
+ * of the package's named endofunctions (transformation.jl:1-55); an arbitrary Julia closure cannot
+ * cross a C ABI, the shims raise ArgumentError for anything else. */
+#define GBM_F1_SQUARE 0     /* square(x) = x^2                                            :9  */
+#define GBM_F1_INVONEPLUS 1 /* invoneplus(x) = 1 / (1 + x)                                :18 */
+#define GBM_F1_LOG10EPS 2   /* log10epsdivlog10eps(x) = log10(x + eps) / log10(eps)       :27 */
+#define GBM_F2_MULT 0       /* mult(x, y) = x * y                                         :36 */
+#define GBM_F2_ADDNORM 1    /* addnorm(x, y) = (x + y) / 2                                :45 */
+#define GBM_F2_RAISE 2      /* raise(x, y) = x^y                                          :54 */
+/* transform1 (:157-221): X .+= eps; use_abs -> abs.(X); beta[j] = slope of y ~ 1 + f(x_j), 0 when
+ * var(x_j) < var_threshold; idx = sortperm(abs.(beta), rev = true)[1:n_new] filtered by abs(beta) > eps, in
+ * that order (1-based).  y: n (host or device).  beta: p values, host or device, nullable.  idx: n_new slots. */
+int gbm_transform1_screen(const gbm_matrix* m, const double* y, int f, double eps, int use_abs, double var_threshold,
+                          int64_t n_new, double* beta, int64_t* idx, int64_t* count);
+/* transform2 (:346-430): beta[(i-1) p + (j-1)] for every ordered pair (commutative: j >= i only), 0 for skipped
+ * pairs; counters = the selected one-based positions in beta, ASCENDING (sort!(idx), :430); beta_sel their values.
+ * beta: p*p values (host or device) or NULL -- the p^2 array then never leaves the device. */
+int gbm_transform2_screen(const gbm_matrix* m, const double* y, int f, double eps, int use_abs, double var_threshold,
+                          int commutative, int64_t n_new, double* beta, int64_t* counters, double* beta_sel,
+                          int64_t* count);
+/* T = f.(X[:, idx]) resp. f.(X[:, i], X[:, j]) for the selected features, then abs(T) < eps -> 0 and
+ * abs(T - 1) < eps -> 1 (:223-227, :440-461).  T: n x count, pitch ldt, host or device. */
+int gbm_transform1_apply(const gbm_matrix* m, int f, double eps, int use_abs, const int64_t* idx, int64_t count,
+                         double* T, int64_t ldt);
+int gbm_transform2_apply(const gbm_matrix* m, int f, double eps, int use_abs, const int64_t* counters, int64_t count,
+                         double* T, int64_t ldt);
+
 /* -log10 upper-tail probabilities on the device (log-space; finite where 1 - cdf saturates) */
 int gbm_neglog10_sf(const double* stat, int64_t len, int dist /*0: TDist(df), 1: Normal*/, double df, double* out);
 
