@@ -598,7 +598,7 @@ def run_pipeline(gbm_b200, _lib, n, p_loc, j0, ys):
 
 def run_transform2(gbm_b200, n, l):
     """Pairwise transformation screen (transform2 with f = mult, transformation.jl:319-466): l^2
-    regressions y ~ 1 + x_i x_j on a resident n x l matrix.  FP64-pipe-bound: 5 FP64 instructions
+    regressions y ~ 1 + x_i x_j on a resident n x l matrix.  FP64-pipe-bound: 4 FP64 instructions
     per (pair, row); the roofline is the 64 FP64 instructions / clk / SM of the B200 pipe."""
     from gbm_b200 import _lib, transform as tr
 
@@ -606,7 +606,7 @@ def run_transform2(gbm_b200, n, l):
     rng = np.random.default_rng(5)
     y = rng.normal(size=n)
     out = {"workload": f"transform2(mult) n={n} l={l}: {l * l} regressions (ordered pairs)"}
-    for f, name, instr in ((tr.mult, "mult", 5), (tr.raise_, "raise", None)):
+    for f, name, instr in ((tr.mult, "mult", 4), (tr.addnorm, "addnorm", 5), (tr.raise_, "raise", None)):
         tr.transform2_screen(dm, y, f, 1000)
         t0 = time.perf_counter()
         _, cnt, _ = tr.transform2_screen(dm, y, f, 1000)

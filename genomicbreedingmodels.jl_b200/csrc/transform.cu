@@ -9,8 +9,10 @@
 // rank test and minimum-norm solution of Julia's pivoted-QR `\` when [1 z] is rank deficient.
 //
 //   transform1_scan_kernel  one warp per locus, HBM-bound: 8 n bytes per locus, read once
+//   transform_prep_kernel   X' = abs?(X + eps) once (and log X' for raise), so the pair kernel's inner loop
+//                           is nothing but the regression sums
 //   transform2_scan_kernel  64 x 64 tiles of pairs, rows streamed through shared memory (cp.async,
-//                           two stages); FP64-pipe-bound: 5 FP64 instructions per (pair, row) for mult
+//                           two stages); FP64-pipe-bound: 4 FP64 instructions per (pair, row) for mult
 //   transform{1,2}_apply    materialise the selected features T = f.(X[:, idx]) with the eps clean-up
 //   transform_select        sortperm(abs.(beta), rev = true)[1:n_new] + abs(beta) > eps (stable radix sort)
 #include <cub/device/device_radix_sort.cuh>
@@ -134,16 +136,50 @@ struct T2Stage {
   double aj[kTile * kPitch];
   double y[kRows];
 };
+constexpr int kRaiseFast = 3;  // raise through exp(x_j log x_i) on a precomputed log matrix (all x' > 0)
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 
+// X' = prep(X) (and L = log X' when Lp != null); *nonpos is raised when some x' is not a positive finite number
+__global__ void __launch_bounds__(256)
+    transform_prep_kernel(const double* __restrict__ A, int64_t n, int64_t lda, double eps, int use_abs,
+                          double* __restrict__ Xp, double* __restrict__ Lp, int64_t ldx, int* __restrict__ nonpos) {
+  const int64_t j = blockIdx.y;
+  bool bad = false;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x; i < ldx; i += static_cast<int64_t>(gridDim.x) * 256) {
+    const double x = i < n ? prep(A[j * lda + i], eps, use_abs) : 0.0;
+    Xp[j * ldx + i] = x;
+    if (Lp) {
+      Lp[j * ldx + i] = i < n ? log(x) : 0.0;
+      bad |= i < n && !(x > 0.0 && x < INFINITY);
+    }
+  }
+  if (bad) atomicOr(nonpos, 1);
+}
+
+// d = f(x_i, x_j) - z0 from the staged operands: `ai` holds x'_i (log x'_i for kRaiseFast), `aj` holds x'_j
+template <int F>
+__device__ __forceinline__ double pair_feature(double ai, double aj) {
+  if constexpr (F == GBM_F2_MULT) return __dmul_rn(ai, aj);
+  else if constexpr (F == GBM_F2_ADDNORM) return __dadd_rn(ai, aj) * 0.5;
+  else if constexpr (F == kRaiseFast) return exp(aj * ai);
+  else return pow(ai, aj);
+}
+template <int F>
+__device__ __forceinline__ double pair_shifted(double ai, double aj, double z0) {
+  if constexpr (F == GBM_F2_MULT) return fma(ai, aj, -z0);  // one rounding instead of two
+  else return pair_feature<F>(ai, aj) - z0;
+}
+
+// Xi: operand matrix of the i side (X', or log X' for kRaiseFast); Xj: X'.  Both n x l, pitch ldx.
 template <int F>
 __global__ void __launch_bounds__(256, 1)
-    transform2_scan_kernel(const double* __restrict__ A, int64_t n, int64_t l, int64_t lda,
-                           const double* __restrict__ yc, double ybar, const double* __restrict__ colvar,
-                           double eps, int use_abs, double var_thr, int commutative, double* __restrict__ beta) {
+    transform2_scan_kernel(const double* __restrict__ Xi, const double* __restrict__ Xj, int64_t n, int64_t l,
+                           int64_t ldx, const double* __restrict__ yc, double ybar,
+                           const double* __restrict__ colvar, double var_thr, int commutative,
+                           double* __restrict__ beta) {
   const int bi = blockIdx.y, bj = blockIdx.x;
   if (commutative && bj < bi) return;  // every pair of the tile has j < i (transformation.jl:373)
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -162,8 +198,8 @@ __global__ void __launch_bounds__(256, 1)
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int c = (tid >> 5) + 8 * k;
-        cp_async8(&st.ai[c * kPitch + row], A + icol(c) * lda + r0 + row);
-        cp_async8(&st.aj[c * kPitch + row], A + jcol(c) * lda + r0 + row);
+        cp_async8(&st.ai[c * kPitch + row], Xi + icol(c) * ldx + r0 + row);
+        cp_async8(&st.aj[c * kPitch + row], Xj + jcol(c) * ldx + r0 + row);
       }
       if (tid < 32) cp_async8(&st.y[row], yc + r0 + row);
     }
@@ -175,14 +211,14 @@ __global__ void __launch_bounds__(256, 1)
     double xi[4], xj[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-      xi[a] = prep(A[icol(ti + 16 * a) * lda], eps, use_abs);
-      xj[a] = prep(A[jcol(tj + 16 * a) * lda], eps, use_abs);
+      xi[a] = Xi[icol(ti + 16 * a) * ldx];
+      xj[a] = Xj[jcol(tj + 16 * a) * ldx];
     }
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
-        z0[a][b] = f2<F>(xi[a], xj[b]);
+        z0[a][b] = pair_feature<F>(xi[a], xj[b]);
         s1[a][b] = s2[a][b] = sy[a][b] = 0.0;
       }
   }
@@ -199,23 +235,29 @@ __global__ void __launch_bounds__(256, 1)
     __syncthreads();
     const T2Stage& st = stage[c & 1];
     const int rmax = static_cast<int>(min(static_cast<int64_t>(kRows), n - c * kRows));
-    for (int r = 0; r < rmax; ++r) {
+    auto row_step = [&](int r) {
       double xi[4], xj[4];
       const double y = st.y[r];
 #pragma unroll
       for (int a = 0; a < 4; ++a) {
-        xi[a] = prep(st.ai[(ti + 16 * a) * kPitch + r], eps, use_abs);
-        xj[a] = prep(st.aj[(tj + 16 * a) * kPitch + r], eps, use_abs);
+        xi[a] = st.ai[(ti + 16 * a) * kPitch + r];
+        xj[a] = st.aj[(tj + 16 * a) * kPitch + r];
       }
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-          const double d = f2<F>(xi[a], xj[b]) - z0[a][b];
+          const double d = pair_shifted<F>(xi[a], xj[b], z0[a][b]);
           s1[a][b] += d;
           s2[a][b] = fma(d, d, s2[a][b]);
           sy[a][b] = fma(d, y, sy[a][b]);
         }
+    };
+    if (rmax == kRows && F <= GBM_F2_ADDNORM) {  // exp / pow bodies are long enough on their own
+#pragma unroll 4
+      for (int r = 0; r < kRows; ++r) row_step(r);
+    } else {
+      for (int r = 0; r < rmax; ++r) row_step(r);
     }
     __syncthreads();
   }
@@ -309,8 +351,8 @@ void launch_transform1_scan(int f, const double* A, int64_t n, int64_t p, int64_
 }
 
 template <int F>
-static void launch_t2(const double* A, int64_t n, int64_t l, int64_t lda, const double* yc, double ybar,
-                      const double* colvar, double eps, int use_abs, double var_thr, int commutative, double* beta,
+static void launch_t2(const double* Xi, const double* Xj, int64_t n, int64_t l, int64_t ldx, const double* yc,
+                      double ybar, const double* colvar, double var_thr, int commutative, double* beta,
                       cudaStream_t stream) {
   const size_t smem = 2 * sizeof(T2Stage);
   static bool configured = false;
@@ -319,7 +361,7 @@ static void launch_t2(const double* A, int64_t n, int64_t l, int64_t lda, const 
     configured = true;
   }
   const unsigned nb = static_cast<unsigned>((l + kTile - 1) / kTile);
-  transform2_scan_kernel<F><<<dim3(nb, nb), 256, smem, stream>>>(A, n, l, lda, yc, ybar, colvar, eps, use_abs, var_thr,
+  transform2_scan_kernel<F><<<dim3(nb, nb), 256, smem, stream>>>(Xi, Xj, n, l, ldx, yc, ybar, colvar, var_thr,
                                                                  commutative, beta);
 }
 
@@ -328,11 +370,33 @@ void launch_transform2_scan(int f, const double* A, int64_t n, int64_t l, int64_
                             double* beta, cudaStream_t stream) {
   if (l <= 0) return;
   if ((l + kTile - 1) / kTile > 65535) GBM_THROW(GBM_ERR_ARGUMENT, "transform2: too many loci for one pairwise screen");
+  if (f < GBM_F2_MULT || f > GBM_F2_RAISE) GBM_THROW(GBM_ERR_ARGUMENT, "unknown two-argument transformation");
+  // X' (and log X' for raise) once, so that the pair kernel only accumulates
+  const int64_t ldx = (n + 1) / 2 * 2;
+  const bool want_log = f == GBM_F2_RAISE;
+  Scratch<double> Xp(static_cast<size_t>(ldx) * l, stream), Lp(want_log ? static_cast<size_t>(ldx) * l : 0, stream);
+  Scratch<int> nonpos(1, stream);
+  GBM_CUDA(cudaMemsetAsync(nonpos.p, 0, sizeof(int), stream));
+  const unsigned gx = static_cast<unsigned>(std::min<int64_t>(32, (ldx + 255) / 256));
+  for (int64_t c0 = 0; c0 < l; c0 += 65535) {
+    const unsigned gy = static_cast<unsigned>(std::min<int64_t>(65535, l - c0));
+    transform_prep_kernel<<<dim3(gx, gy), 256, 0, stream>>>(A + c0 * lda, n, lda, eps, use_abs, Xp.p + c0 * ldx,
+                                                            want_log ? Lp.p + c0 * ldx : nullptr, ldx, nonpos.p);
+  }
+  GBM_CUDA(cudaGetLastError());
+  int h_nonpos = 0;
+  if (want_log) {
+    GBM_CUDA(cudaMemcpyAsync(&h_nonpos, nonpos.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    GBM_CUDA(cudaStreamSynchronize(stream));
+  }
   switch (f) {
-    case GBM_F2_MULT: launch_t2<GBM_F2_MULT>(A, n, l, lda, yc, ybar, colvar, eps, use_abs, var_thr, commutative, beta, stream); break;
-    case GBM_F2_ADDNORM: launch_t2<GBM_F2_ADDNORM>(A, n, l, lda, yc, ybar, colvar, eps, use_abs, var_thr, commutative, beta, stream); break;
-    case GBM_F2_RAISE: launch_t2<GBM_F2_RAISE>(A, n, l, lda, yc, ybar, colvar, eps, use_abs, var_thr, commutative, beta, stream); break;
-    default: GBM_THROW(GBM_ERR_ARGUMENT, "unknown two-argument transformation");
+    case GBM_F2_MULT: launch_t2<GBM_F2_MULT>(Xp.p, Xp.p, n, l, ldx, yc, ybar, colvar, var_thr, commutative, beta, stream); break;
+    case GBM_F2_ADDNORM: launch_t2<GBM_F2_ADDNORM>(Xp.p, Xp.p, n, l, ldx, yc, ybar, colvar, var_thr, commutative, beta, stream); break;
+    default:
+      if (h_nonpos)  // zero / negative / non-finite bases: pow() itself decides (NaN where Julia throws DomainError)
+        launch_t2<GBM_F2_RAISE>(Xp.p, Xp.p, n, l, ldx, yc, ybar, colvar, var_thr, commutative, beta, stream);
+      else
+        launch_t2<kRaiseFast>(Lp.p, Xp.p, n, l, ldx, yc, ybar, colvar, var_thr, commutative, beta, stream);
   }
   GBM_CUDA(cudaGetLastError());
 }

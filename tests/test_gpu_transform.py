@@ -94,7 +94,7 @@ def test_exactly_rounded_features_are_bit_exact_and_cleaned(gbm):
     for fd, fo in ((tr.square, to.square), (tr.invoneplus, to.invoneplus)):
         T = tr.transform1_apply(dm, fd, idx)
         assert np.array_equal(T, to._clean(fo(X), to.EPS))
-    assert (tr.transform1_apply(dm, tr.square, idx) == 1.0).any()
+    assert (tr.transform1_apply(dm, tr.square, idx) == 0.0).any()  # (0 + eps)^2 < eps: cleaned to exact 0
     cnt = np.array([1, 2, 21, 47, 400], dtype=np.int64)
     for fd, fo in ((tr.mult, to.mult), (tr.addnorm, to.addnorm)):
         T = tr.transform2_apply(dm, fd, cnt)
