@@ -15,6 +15,7 @@ using GenomicBreedingCore
 using Statistics
 
 export gwasprep, gwasols, gwaslmm, gwasreml, grmsimple_b200, grmploidyaware_b200
+export transform1, transform2, epistasisfeatures, square, invoneplus, log10epsdivlog10eps, mult, addnorm, raise
 
 const LIBGBM = get(ENV, "GBM_B200_LIB", joinpath(@__DIR__, "..", "libgbm_b200.so"))
 
@@ -290,6 +291,114 @@ end
 function grmploidyaware_b200(genomes::Genomes; ploidy::Int64 = 2, idx_entries = nothing, idx_loci_alleles = nothing, verbose::Bool = false)
     dm = upload(Matrix{Float64}(genomes.allele_frequencies), idx_entries, idx_loci_alleles)
     K = grm(dm, GBM_GRM_PLOIDY_AWARE, ploidy); free!(dm); K
+end
+
+# ---- transformation screens (src/transformation.jl:130-239, :319-466, :540-651) -----------------
+# The l (transform1) / l^2 (transform2) regressions `ols(genomes = g, phenomes = p).b_hat[2]` run in
+# libgbm_b200.so.  `f` must be one of the package's named endofunctions (src/transformation.jl:1-55):
+# a closure cannot cross the C ABI and there is no CPU fallback.
+square(x) = x^2
+invoneplus(x) = 1 / (1 + x)
+log10epsdivlog10eps(x) = (log10(x + eps(Float64))) / log10(eps(Float64))
+mult(x, y) = x * y
+addnorm(x, y) = (x + y) / 2.0
+raise(x, y) = x^y
+const F1_CODES = IdDict{Any,Cint}(square => 0, invoneplus => 1, log10epsdivlog10eps => 2)
+const F2_CODES = IdDict{Any,Cint}(mult => 0, addnorm => 1, raise => 2)
+function fcode(f, table, arity)
+    haskey(table, f) || throw(ArgumentError("`" * string(f) * "` is not one of the named endofunctions of " * string(arity) *
+                                            " argument(s); only those run on the device (no CPU fallback)."))
+    table[f]
+end
+
+function extractdevice(genomes, phenomes, idx_trait, idx_entries, idx_loci_alleles)
+    rows, cols, y = selectrows(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait)
+    A = genomes.allele_frequencies
+    any(ismissing, A) && throw(ErrorException("cannot convert a value of type Missing to Float64"))
+    dm = upload(Matrix{Float64}(A), rows, cols)
+    r = isnothing(rows) ? collect(1:size(A, 1)) : rows
+    c = isnothing(cols) ? collect(1:size(A, 2)) : cols
+    (dm, y, genomes.entries[r], genomes.populations[r], genomes.loci_alleles[c])
+end
+
+function transform1(f::Function, genomes::Genomes, phenomes::Phenomes; idx_trait::Int64 = 1,
+                    idx_entries::Union{Nothing,Vector{Int64}} = nothing, idx_loci_alleles::Union{Nothing,Vector{Int64}} = nothing,
+                    n_new_features_per_transformation::Int64 = 1_000, ϵ::Float64 = eps(Float64), use_abs::Bool = false,
+                    σ²_threshold::Float64 = 0.01, verbose::Bool = false)::Genomes
+    code = fcode(f, F1_CODES, 1)
+    dm, y, entries, populations, loci_alleles = extractdevice(genomes, phenomes, idx_trait, idx_entries, idx_loci_alleles)
+    idx = Vector{Int64}(undef, max(n_new_features_per_transformation, 1))
+    count = Ref{Int64}(0)
+    check(ccall((:gbm_transform1_screen, LIBGBM), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Cint, Float64, Cint, Float64, Int64, Ptr{Float64}, Ptr{Int64}, Ref{Int64}),
+                dm.handle, y, code, ϵ, use_abs, σ²_threshold, n_new_features_per_transformation, C_NULL, idx, count))
+    resize!(idx, count[])
+    T = Matrix{Float64}(undef, dm.n, length(idx))
+    check(ccall((:gbm_transform1_apply, LIBGBM), Cint,
+                (Ptr{Cvoid}, Cint, Float64, Cint, Ptr{Int64}, Int64, Ptr{Float64}, Int64),
+                dm.handle, code, ϵ, use_abs, idx, length(idx), T, dm.n))
+    free!(dm)
+    out = Genomes(n = size(T, 1), p = length(idx))
+    out.entries = entries
+    out.populations = populations
+    out.allele_frequencies = T
+    out.loci_alleles = string.(f, "(", loci_alleles[idx], ")")  # src/transformation.jl:235
+    checkdims(out) || throw(ErrorException("Error transforming each locus using the function `" * string(f) * "`."))
+    out
+end
+
+function transform2(f::Function, genomes::Genomes, phenomes::Phenomes; idx_trait::Int64 = 1,
+                    idx_entries::Union{Nothing,Vector{Int64}} = nothing, idx_loci_alleles::Union{Nothing,Vector{Int64}} = nothing,
+                    n_new_features_per_transformation::Int64 = 1_000, ϵ::Float64 = eps(Float64), use_abs::Bool = false,
+                    σ²_threshold::Float64 = 0.01, commutative::Bool = false, verbose::Bool = false)::Genomes
+    code = fcode(f, F2_CODES, 2)
+    dm, y, entries, populations, loci_alleles = extractdevice(genomes, phenomes, idx_trait, idx_entries, idx_loci_alleles)
+    l = dm.p
+    counters = Vector{Int64}(undef, max(n_new_features_per_transformation, 1))
+    count = Ref{Int64}(0)
+    check(ccall((:gbm_transform2_screen, LIBGBM), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Cint, Float64, Cint, Float64, Cint, Int64, Ptr{Float64}, Ptr{Int64}, Ptr{Float64}, Ref{Int64}),
+                dm.handle, y, code, ϵ, use_abs, σ²_threshold, commutative, n_new_features_per_transformation, C_NULL,
+                counters, C_NULL, count))
+    resize!(counters, count[])
+    T = Matrix{Float64}(undef, dm.n, length(counters))
+    check(ccall((:gbm_transform2_apply, LIBGBM), Cint,
+                (Ptr{Cvoid}, Cint, Float64, Cint, Ptr{Int64}, Int64, Ptr{Float64}, Int64),
+                dm.handle, code, ϵ, use_abs, counters, length(counters), T, dm.n))
+    free!(dm)
+    out = Genomes(n = size(T, 1), p = length(counters))
+    out.entries = entries
+    out.populations = populations
+    out.allele_frequencies = T
+    out.loci_alleles = [string(f, "(", loci_alleles[1+div(c - 1, l)], ",", loci_alleles[1+(c-1)%l], ")") for c in counters]  # :445-451
+    checkdims(out) || throw(ErrorException("Error transforming each locus using the function `" * string(f) * "`."))
+    out
+end
+
+function epistasisfeatures(genomes::Genomes, phenomes::Phenomes; idx_trait::Int64 = 1,
+                           idx_entries::Union{Nothing,Vector{Int64}} = nothing,
+                           idx_loci_alleles::Union{Nothing,Vector{Int64}} = nothing,
+                           transformations1 = [square, invoneplus, log10epsdivlog10eps], transformations2 = [mult, addnorm, raise],
+                           n_new_features_per_transformation::Int64 = 1_000, n_reps::Int64 = 3, verbose::Bool = false)::Genomes
+    selectrows(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait)  # the argument checks of :552-601
+    idx_entries = isnothing(idx_entries) ? collect(1:length(genomes.entries)) : idx_entries
+    idx_loci_alleles = isnothing(idx_loci_alleles) ? collect(1:length(genomes.loci_alleles)) : idx_loci_alleles
+    genomes = slice(genomes, idx_entries = idx_entries, idx_loci_alleles = idx_loci_alleles)
+    phenomes = slice(phenomes, idx_entries = idx_entries, idx_traits = [idx_trait])
+    for r = 1:n_reps, f in vcat(transformations1, transformations2)
+        g = f ∈ transformations1 ?
+            transform1(f, genomes, phenomes, n_new_features_per_transformation = n_new_features_per_transformation) :
+            transform2(f, genomes, phenomes, n_new_features_per_transformation = n_new_features_per_transformation)
+        idx_new = [findall(g.loci_alleles .== x)[1] for x in setdiff(g.loci_alleles, genomes.loci_alleles)]
+        append!(genomes.loci_alleles, g.loci_alleles[idx_new])
+        genomes.allele_frequencies = hcat(genomes.allele_frequencies, g.allele_frequencies[:, idx_new])
+        genomes.mask = hcat(genomes.mask, g.mask[:, idx_new])
+        if (minimum(genomes.allele_frequencies) < 0.0) || (abs(maximum(genomes.allele_frequencies) - 1) > 1e-12)
+            throw(ErrorException("The function `" * string(f) * "` generates values outside the expected range of zero to one. Please replace with an appropriate transforamtion function."))
+        end
+    end
+    checkdims(genomes) || throw(ErrorException("Error generating new features."))
+    genomes
 end
 
 end # module
