@@ -499,7 +499,11 @@ def main():
     if rank == 0 and not args.no_transform:
         line["transform2"] = run_transform2(gbm_b200, n, args.transform_l)
 
-    if rank == 0 and args.pipeline:
+    if args.pipeline and world > 1:  # every rank takes part
+        res = run_pipeline_sharded(gbm_b200, _lib, n, p, j0, p_loc, ys, world)
+        if rank == 0:
+            line["pipeline_sharded"] = res
+    elif rank == 0 and args.pipeline:
         line["pipeline"] = run_pipeline(gbm_b200, _lib, n, p_loc, j0, ys)
 
     if rank == 0 and args.lmm_markers > 0:
@@ -595,6 +599,85 @@ def run_pipeline(gbm_b200, _lib, n, p_loc, j0, ys):
         out["packed_int8"] = pkd
         pk.free()
     dm.free()
+    return out
+
+
+def run_pipeline_sharded(gbm_b200, _lib, n, p, j0, p_loc, ys, world):
+    """Whole gwaslmm on all ranks (north_star's target run): each rank holds its column block; colstats and
+    filter local, GRM partials summed with ONE NCCL all-reduce, K standardisation + PC1 on every rank
+    (deterministic, no broadcast), scan local, statistics gathered in locus order on every rank.  Uses the
+    packed (1-byte) copy when the block packs.  Times are max over ranks (barrier on both sides)."""
+    import torch
+    import torch.distributed as dist
+
+    from gbm_b200 import sharded
+
+    def sync():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    wm = gbm_b200.DeviceMatrix.generate(SEED, 256, 512, KIND_DIPLOID)  # one-off library initialisation
+    wK, _ = wm.grm(_lib.GRM_SIMPLE, 2, 0)
+    gbm_b200.kstd_pc1(wK, want_kstd=False)
+    wm.free()
+    dm = gbm_b200.DeviceMatrix.generate(SEED, n, p_loc, KIND_DIPLOID, col0=j0)
+    out = {"world": world, "n": n, "p": p}
+    for storage in ("float64", "packed"):
+        m = dm
+        if storage == "packed":
+            sync()
+            t0 = time.perf_counter()
+            m = dm.pack()
+            sync()
+            if m is None:
+                break
+            out_pack_s = time.perf_counter() - t0
+            dm.free()
+        sg = sharded.ShardedGWAS(m, p, j0)
+        ph = {}
+        for attempt in ("cold", "warm"):
+            sync()
+            t_all = time.perf_counter()
+            t0 = time.perf_counter()
+            st = m.colstats()
+            sync()
+            ph["colstats_s"] = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            dK = sg.grm("simple")
+            sync()
+            ph["grm_incl_allreduce_s"] = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            pc, eig_ms = gbm_b200.kstd_pc1_device(dK.data_ptr(), n)
+            sync()
+            ph["kstd_pc1_s"] = time.perf_counter() - t0
+            ph["cusolver_eig_s"] = eig_ms * 1e-3
+            del dK
+            t0 = time.perf_counter()
+            res = m.scan(ys, pc[:, None], model=_lib.MODEL_LMM)
+            sync()
+            ph["scan_s"] = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            idx = sharded.global_idx_cols(st["idx_cols"], j0)
+            z = sharded.gather_marker_results(res["stat"][:, 0], p)
+            nlp = sharded.gather_marker_results(res["neglog10p"][:, 0], p)
+            sync()
+            ph["gather_s"] = time.perf_counter() - t0
+            ph["total_s"] = time.perf_counter() - t_all
+        tt = torch.tensor([ph[k] for k in sorted(ph)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ph = {k: float(v) for k, v in zip(sorted(ph), tt.cpu())}
+        ph["markers_per_s_whole_gwaslmm"] = p / ph["total_s"]
+        ph["markers_kept"] = int(idx.size)
+        ph["max_neglog10p"] = float(np.nanmax(nlp[idx - 1]))
+        ph["sum_abs_z"] = float(np.nansum(np.abs(z[idx - 1])))  # a checksum to compare across GPU counts
+        if storage == "packed":
+            ph["pack_s"] = out_pack_s
+        out[storage] = ph
+    if m is not None:
+        m.free()
+    else:
+        dm.free()
     return out
 
 
