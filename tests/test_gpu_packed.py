@@ -121,3 +121,46 @@ def test_scan_host_pack_flag(gbm, kind, expect_packed):
     for key in ("beta", "se", "stat", "mean", "sd"):
         x, y = a[key][keep], b[key][keep]
         assert np.nanmax(np.abs(x - y)) <= tol * max(1.0, np.nanmax(np.abs(x))), key
+
+
+def test_scan_host_lanes_agree_bit_for_bit_on_mixed_data(gbm, monkeypatch):
+    """gbm_scan_host hands ~128 MB column blocks to the host-packer lane and/or the copy-engine lane
+    (GBM_SCAN_HOST_LANES).  A block that is all dosage codes is scanned as codes, any other block as
+    Float64, whichever lane carried it -- so every lane configuration must give the same bits, also when
+    the host packer meets a non-code block half way (hand-back to the copy-engine lane) and when the
+    source is page-locked."""
+    import torch
+
+    n, p = 1000, 56_000  # 3.5 blocks of 16,000 columns
+    A, ys, pc = _problem(21, n, p, synth.KIND_DIPLOID)
+    C = synth.block(22, n, 0, 3000, synth.KIND_CONTINUOUS)
+    A[:, 35_000:38_000] = C  # the third block is not dosage data
+    pinned = torch.empty((p, n), dtype=torch.float64, pin_memory=True)
+    pinned.numpy()[:] = A.T
+    ref = None
+    seen = set()
+    for src in (A, pinned):
+        for lanes in (None, "host", "copy", "both"):
+            if lanes is None:
+                monkeypatch.delenv("GBM_SCAN_HOST_LANES", raising=False)
+            else:
+                monkeypatch.setenv("GBM_SCAN_HOST_LANES", lanes)
+            out = gbm.scan_host(src, ys, pc[:, None], model=1)
+            tm = gbm.last_timing()
+            assert tm["packed_blocks"] == 3  # blocks 1, 2 and the ragged 4th are codes, block 3 is not
+            seen.add(tm["host_packed_blocks"])
+            if ref is None:
+                ref = out
+                continue
+            for key in ("beta", "se", "stat", "neglog10p", "mean", "sd", "keep"):
+                assert np.array_equal(ref[key], out[key], equal_nan=True), (lanes, key)
+    monkeypatch.delenv("GBM_SCAN_HOST_LANES", raising=False)
+    assert 0 in seen and max(seen) >= 2  # both the copy-engine-only and the host-lane paths ran
+    dm = gbm.DeviceMatrix.upload(A)
+    want = dm.scan(ys, pc[:, None], model=1)
+    dm.free()
+    keep = want["keep"]
+    assert np.array_equal(keep, ref["keep"])
+    for key in ("beta", "se", "stat"):
+        x, y = want[key][keep], ref[key][keep]
+        assert np.nanmax(np.abs(x - y)) <= 1e-11 * max(1.0, np.nanmax(np.abs(x))), key
