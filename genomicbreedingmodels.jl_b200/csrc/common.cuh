@@ -50,6 +50,10 @@ struct State {
   unsigned long long* raw_flag_host = nullptr;  // pinned mirror
   cudaEvent_t raw_copied[kRawSlots] = {}, raw_packed[kRawSlots] = {}, raw_consumed[kRawSlots] = {};
   cudaStream_t raw_stream = nullptr;
+  // pinned Float64 staging ring for uploads from pageable host memory (filled by the host workers)
+  void* up_stage[kHostSlots] = {};
+  size_t up_bytes = 0;
+  cudaEvent_t up_copied[kHostSlots] = {};
   double h2d_ms = 0, kernel_ms = 0, main_ms = 0, d2h_ms = 0;
   int64_t launches = 0;
   int64_t packed_blocks = 0, host_packed_blocks = 0, h2d_bytes = 0;

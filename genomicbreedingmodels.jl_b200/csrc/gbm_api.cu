@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <deque>
 #include <functional>
 #include <memory>
@@ -99,6 +100,17 @@ void make_tensor_map_2d_u8_sw128(CUtensorMap* map, const void* base, uint64_t ro
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) GBM_THROW(GBM_ERR_CUDA, "cuTensorMapEncodeTiled (u8, swizzle 128B) failed with code " + std::to_string((int)r));
 }
+
+// host_pack.cpp: worker queue of the calling process' cores (packing to dosage codes, staging copies)
+struct PackJob;
+PackJob* pack_submit(const double* A, int64_t n, int64_t lda, int64_t pc, uint8_t* out, int64_t ldo);
+bool pack_wait(PackJob* job, const std::function<void()>* idle);
+bool pack_block_host(const double* A, int64_t n, int64_t lda, int64_t pc, uint8_t* out, int64_t ldo,
+                     const std::function<void()>* idle);
+int64_t count_inexact_host(const double* A, int64_t n, int64_t lda, int64_t pc);
+bool pack_check_columns(const double* A, int64_t n, int64_t lda, int64_t pc, int isa, uint8_t* col_ok);
+int host_threads();
+PackJob* copy_submit(const double* A, int64_t n, int64_t lda, int64_t pc, double* out, int64_t ldo);
 
 static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
@@ -217,6 +229,13 @@ static void free_scan_host_staging(State& st) {
     if (st.raw_consumed[b]) cudaEventDestroy(st.raw_consumed[b]);
     st.raw_copied[b] = st.raw_packed[b] = st.raw_consumed[b] = nullptr;
   }
+  for (int b = 0; b < State::kHostSlots; ++b) {
+    if (st.up_stage[b]) cudaFreeHost(st.up_stage[b]);
+    st.up_stage[b] = nullptr;
+    if (st.up_copied[b]) cudaEventDestroy(st.up_copied[b]);
+    st.up_copied[b] = nullptr;
+  }
+  st.up_bytes = 0;
   if (st.raw_flag_dev) cudaFree(st.raw_flag_dev);
   if (st.raw_flag_host) cudaFreeHost(st.raw_flag_host);
   st.raw_flag_dev = st.raw_flag_host = nullptr;
@@ -382,6 +401,124 @@ static void scan_block(const gbm_matrix& mat, int64_t p_blk, const std::vector<s
   }
 }
 
+// ------------------------------------------------------------------------------------
+// host -> device ingestion of a column-major Float64 matrix
+// ------------------------------------------------------------------------------------
+// Up to kHostSlots column blocks are queued with the host workers ahead of the one being waited for.
+// submit(slot, j0, pc) queues the block's job, consume(slot, j0, pc, ok) runs in block order; consume
+// returning false stops the pipeline (queued jobs are drained first).  Returns true when every block
+// was consumed.
+template <typename Submit, typename Consume>
+static bool run_block_pipeline(int64_t p, int64_t blk, Submit submit, Consume consume) {
+  constexpr int K = State::kHostSlots;
+  struct Ring {
+    PackJob* job[K] = {};
+    int64_t j0[K] = {};
+    int head = 0, fill = 0, count = 0;
+    ~Ring() {
+      for (PackJob*& j : job)
+        if (j) pack_wait(j, nullptr), j = nullptr;
+    }
+  } ring;
+  int64_t next = 0;
+  for (;;) {
+    while (ring.count < K && next < p) {
+      const int s = ring.fill;
+      const int64_t pc = std::min(blk, p - next);
+      ring.job[s] = submit(s, next, pc);
+      ring.j0[s] = next;
+      ring.fill = (s + 1) % K;
+      ++ring.count;
+      next += pc;
+    }
+    if (ring.count == 0) return true;
+    const int s = ring.head;
+    PackJob* job = ring.job[s];
+    ring.job[s] = nullptr;
+    ring.head = (s + 1) % K;
+    --ring.count;
+    const bool ok = pack_wait(job, nullptr);
+    if (!consume(s, ring.j0[s], std::min(blk, p - ring.j0[s]), ok)) return false;
+  }
+}
+
+// A (host or device, pitch lda) -> dst (device, pitch ldd >= n, pad rows zeroed).  Page-locked and device
+// sources go through the copy engine directly.  Pageable sources are copied (and re-pitched) by the host
+// workers into a ring of pinned staging blocks that the copy engine drains, instead of the driver's
+// single-threaded bounce buffer.
+static void upload_f64(const double* A, int64_t n, int64_t p, int64_t lda, double* dst, int64_t ldd) {
+  State& st = state();
+  if (is_device_ptr(A) || is_pinned_host_ptr(A) || host_threads() < 2) {
+    if (ldd != n) GBM_CUDA(cudaMemsetAsync(dst, 0, sizeof(double) * ldd * p, st.stream));
+    GBM_CUDA(cudaMemcpy2DAsync(dst, ldd * sizeof(double), A, lda * sizeof(double), n * sizeof(double), p,
+                               cudaMemcpyDefault, st.stream));
+    GBM_CUDA(cudaStreamSynchronize(st.stream));
+    return;
+  }
+  constexpr int K = State::kHostSlots;
+  const int64_t blk = std::max<int64_t>(16, ((int64_t(64) << 20) / (8 * ldd)) / 16 * 16);
+  const size_t need = sizeof(double) * ldd * std::min(blk, p);
+  if (st.up_bytes < need) {
+    for (int b = 0; b < K; ++b) {
+      if (st.up_stage[b]) cudaFreeHost(st.up_stage[b]);
+      st.up_stage[b] = nullptr;
+      GBM_CUDA(cudaMallocHost(&st.up_stage[b], need));
+    }
+    st.up_bytes = need;
+  }
+  for (int b = 0; b < K; ++b)
+    if (!st.up_copied[b]) GBM_CUDA(cudaEventCreateWithFlags(&st.up_copied[b], cudaEventDisableTiming));
+  run_block_pipeline(
+      p, blk,
+      [&](int s, int64_t j0, int64_t pc) {
+        GBM_CUDA(cudaEventSynchronize(st.up_copied[s]));  // the staging block's previous H2D has drained
+        return copy_submit(A + j0 * lda, n, lda, pc, static_cast<double*>(st.up_stage[s]), ldd);
+      },
+      [&](int s, int64_t j0, int64_t pc, bool) {
+        GBM_CUDA(cudaMemcpyAsync(dst + j0 * ldd, st.up_stage[s], sizeof(double) * ldd * pc, cudaMemcpyHostToDevice,
+                                 st.copy_stream));
+        GBM_CUDA(cudaEventRecord(st.up_copied[s], st.copy_stream));
+        return true;
+      });
+  GBM_CUDA(cudaStreamSynchronize(st.copy_stream));
+}
+
+// A (host, pitch lda) -> one-byte codes at d8 (device, pitch ld8), packed by the host workers.  Returns false
+// (d8 incomplete) as soon as a block holds an element that is not exactly a code.
+static bool upload_codes(const double* A, int64_t n, int64_t p, int64_t lda, uint8_t* d8, int64_t ld8) {
+  State& st = state();
+  constexpr int K = State::kHostSlots;
+  const int64_t blk = std::max<int64_t>(16, ((int64_t(128) << 20) / (8 * n)) / 16 * 16);
+  const size_t need8 = static_cast<size_t>(ld8) * std::min(blk, round_up(p, 16));
+  if (st.code_bytes < need8) {
+    for (int b = 0; b < K; ++b) {
+      if (st.host_codes[b]) cudaFreeHost(st.host_codes[b]);
+      if (st.dev_codes[b]) cudaFree(st.dev_codes[b]);
+      st.host_codes[b] = st.dev_codes[b] = nullptr;
+      GBM_CUDA(cudaMallocHost(&st.host_codes[b], need8));
+      GBM_CUDA(cudaMalloc(&st.dev_codes[b], need8));
+    }
+    st.code_bytes = need8;
+  }
+  for (int b = 0; b < K; ++b)
+    if (!st.hl_copied[b]) GBM_CUDA(cudaEventCreateWithFlags(&st.hl_copied[b], cudaEventDisableTiming));
+  const bool all = run_block_pipeline(
+      p, blk,
+      [&](int s, int64_t j0, int64_t pc) {
+        GBM_CUDA(cudaEventSynchronize(st.hl_copied[s]));
+        return pack_submit(A + j0 * lda, n, lda, pc, static_cast<uint8_t*>(st.host_codes[s]), ld8);
+      },
+      [&](int s, int64_t j0, int64_t pc, bool ok) {
+        if (!ok) return false;
+        GBM_CUDA(cudaMemcpyAsync(d8 + j0 * ld8, st.host_codes[s], static_cast<size_t>(ld8) * pc, cudaMemcpyHostToDevice,
+                                 st.copy_stream));
+        GBM_CUDA(cudaEventRecord(st.hl_copied[s], st.copy_stream));
+        return true;
+      });
+  GBM_CUDA(cudaStreamSynchronize(st.copy_stream));
+  return all;
+}
+
 }  // namespace gbm
 
 using namespace gbm;
@@ -528,13 +665,72 @@ int gbm_matrix_upload(const double* A, int64_t n, int64_t p, int64_t lda, gbm_ma
     delete m;
     GBM_THROW(GBM_ERR_CUDA, std::string("cudaMalloc of the genotype slab failed: ") + cudaGetErrorString(e));
   }
-  Span sp(st.stream);
-  sp.start();
-  if (m->lda != n) GBM_CUDA(cudaMemsetAsync(m->d, 0, sizeof(double) * m->lda * p, st.stream));
-  GBM_CUDA(cudaMemcpy2DAsync(m->d, m->lda * sizeof(double), A, lda * sizeof(double), n * sizeof(double), p,
-                             cudaMemcpyDefault, st.stream));
-  sp.stop();
-  st.h2d_ms = sp.ms();
+  const auto t0 = std::chrono::steady_clock::now();
+  try {
+    upload_f64(A, n, p, lda, m->d, m->lda);
+  } catch (...) {
+    cudaFree(m->d);
+    delete m;
+    throw;
+  }
+  st.h2d_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  *out = m;
+  GBM_API_END
+}
+
+int gbm_matrix_upload_compact(const double* A, int64_t n, int64_t p, int64_t lda, gbm_matrix** out, int* packed) {
+  GBM_API_BEGIN
+  require_ready();
+  if (!A || !out || !packed) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_matrix_upload_compact: null pointer");
+  check_dims(n, p, lda);
+  State& st = state();
+  reset_timing();
+  *packed = 0;
+  const auto t0 = std::chrono::steady_clock::now();
+  if (!is_device_ptr(A) && host_threads() >= 2) {
+    std::unique_ptr<gbm_matrix> q(new gbm_matrix);
+    q->n = n;
+    q->p = p;
+    q->dtype = 1;
+    q->owned = true;
+    q->ld8 = round_up(n, 128);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&q->d8), static_cast<size_t>(q->ld8) * p);
+    if (e != cudaSuccess) GBM_THROW(GBM_ERR_CUDA, std::string("cudaMalloc of the code slab failed: ") + cudaGetErrorString(e));
+    bool all = false;
+    try {
+      all = upload_codes(A, n, p, lda, q->d8, q->ld8);
+    } catch (...) {
+      cudaFree(q->d8);
+      throw;
+    }
+    if (all) {
+      st.h2d_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      st.h2d_bytes = q->ld8 * p;
+      *packed = 1;
+      *out = q.release();
+      return GBM_OK;
+    }
+    cudaFree(q->d8);  // not dosage data: Float64 slab below
+  }
+  gbm_matrix* m = new gbm_matrix;
+  m->n = n;
+  m->p = p;
+  m->lda = round_up(n, 16);
+  m->owned = true;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&m->d), sizeof(double) * m->lda * p);
+  if (e != cudaSuccess) {
+    delete m;
+    GBM_THROW(GBM_ERR_CUDA, std::string("cudaMalloc of the genotype slab failed: ") + cudaGetErrorString(e));
+  }
+  try {
+    upload_f64(A, n, p, lda, m->d, m->lda);
+  } catch (...) {
+    cudaFree(m->d);
+    delete m;
+    throw;
+  }
+  st.h2d_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  st.h2d_bytes = static_cast<int64_t>(sizeof(double)) * n * p;
   *out = m;
   GBM_API_END
 }
@@ -733,7 +929,6 @@ int gbm_matrix_download_cols(const gbm_matrix* m, const int64_t* idx_cols, int64
   GBM_API_BEGIN
   require_ready();
   if (!m || !dst || ncols < 0 || ldd < m->n) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_matrix_download_cols: bad arguments");
-  if (m->dtype != 0) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_matrix_download_cols: Float64 matrices only");
   if (!idx_cols && ncols != m->p) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_matrix_download_cols: ncols must be p without an index");
   if (ncols == 0) return GBM_OK;
   State& st = state();
@@ -760,9 +955,14 @@ int gbm_matrix_download_cols(const gbm_matrix* m, const int64_t* idx_cols, int64
   DevBuf<double> tmp(static_cast<size_t>(ldt) * PB, st.stream);
   for (int64_t c0 = 0; c0 < ncols; c0 += PB) {
     const int64_t pc = std::min(PB, ncols - c0);
-    launch_gather_standardise(idx_cols ? m->d : m->d + c0 * m->lda, m->lda, n, idx_cols ? dcols.p + c0 : nullptr, pc,
-                              standardise ? (idx_cols ? dmean.p : dmean.p + c0) : nullptr,
-                              standardise ? (idx_cols ? dsd.p : dsd.p + c0) : nullptr, tmp.p, ldt, st.stream);
+    const double* mu = standardise ? (idx_cols ? dmean.p : dmean.p + c0) : nullptr;
+    const double* sdv = standardise ? (idx_cols ? dsd.p : dsd.p + c0) : nullptr;
+    if (m->dtype == 1)
+      launch_gather_standardise_u8(idx_cols ? m->d8 : m->d8 + c0 * m->ld8, m->ld8, n, idx_cols ? dcols.p + c0 : nullptr,
+                                   pc, mu, sdv, tmp.p, ldt, st.stream);
+    else
+      launch_gather_standardise(idx_cols ? m->d : m->d + c0 * m->lda, m->lda, n, idx_cols ? dcols.p + c0 : nullptr, pc,
+                                mu, sdv, tmp.p, ldt, st.stream);
     GBM_CUDA(cudaMemcpy2DAsync(dst + c0 * ldd, ldd * sizeof(double), tmp.p, ldt * sizeof(double), n * sizeof(double),
                                pc, cudaMemcpyDefault, st.stream));
     GBM_CUDA(cudaStreamSynchronize(st.stream));
@@ -1235,22 +1435,7 @@ int gbm_scan(const gbm_matrix* m, const double* Y, int64_t T, int64_t ldy, const
   return rc;
 }
 
-// ---- host-side packer (host_pack.cpp): Float64 -> dosage codes with the exactness check ----
-}  // extern "C"
-
-namespace gbm {
-struct PackJob;
-PackJob* pack_submit(const double* A, int64_t n, int64_t lda, int64_t pc, uint8_t* out, int64_t ldo);
-bool pack_wait(PackJob* job, const std::function<void()>* idle);
-bool pack_block_host(const double* A, int64_t n, int64_t lda, int64_t pc, uint8_t* out, int64_t ldo,
-                     const std::function<void()>* idle);
-int64_t count_inexact_host(const double* A, int64_t n, int64_t lda, int64_t pc);
-bool pack_check_columns(const double* A, int64_t n, int64_t lda, int64_t pc, int isa, uint8_t* col_ok);
-int host_threads();
-}  // namespace gbm
-
-extern "C" {
-
+// ---- host-side packer entry points ----
 int gbm_pack_host(const double* A, int64_t n, int64_t p, int64_t lda, uint8_t* out, int64_t ldo, int64_t* n_inexact) {
   GBM_API_BEGIN
   if (!A || !out || !n_inexact || n < 1 || p < 1 || lda < n || ldo < n)
@@ -1363,6 +1548,19 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
     if (ldd != n) GBM_CUDA(cudaMemsetAsync(st.raw_f64[b], 0, need, st.raw_stream));  // pad rows stay zero
   }
   const bool contiguous = (lda == n && ldd == n);
+  const bool stage_pageable = !pinned && host_threads() >= 2;
+  if (stage_pageable) {
+    static_assert(State::kRawSlots <= State::kHostSlots, "one pinned staging block per copy-engine slot");
+    if (st.up_bytes < need) {
+      for (int b = 0; b < State::kHostSlots; ++b) {
+        if (st.up_stage[b]) cudaFreeHost(st.up_stage[b]);
+        st.up_stage[b] = nullptr;
+        GBM_CUDA(cudaMallocHost(&st.up_stage[b], need));
+      }
+      st.up_bytes = need;
+    }
+    for (int b = 0; b < State::kHostSlots; ++b) make_event(&st.up_copied[b]);
+  }
 
   int64_t next = 0;              // next unassigned block
   std::deque<int64_t> handback;  // blocks the host lane could not pack
@@ -1391,12 +1589,22 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
     if (bi < 0) return;
     const int64_t j0 = bi * blk, pc = std::min(blk, p - j0);
     double* dst = static_cast<double*>(st.raw_f64[s]);
-    GBM_CUDA(cudaStreamWaitEvent(st.raw_stream, st.raw_consumed[s], 0));
-    if (contiguous)
+    if (stage_pageable) {
+      // pageable source: the host workers copy (and re-pitch) the block into pinned staging, the copy engine
+      // takes it from there -- not the driver's single-threaded bounce buffer
+      GBM_CUDA(cudaEventSynchronize(st.up_copied[s]));
+      pack_wait(copy_submit(A + j0 * lda, n, lda, pc, static_cast<double*>(st.up_stage[s]), ldd), nullptr);
+      GBM_CUDA(cudaStreamWaitEvent(st.raw_stream, st.raw_consumed[s], 0));
+      GBM_CUDA(cudaMemcpyAsync(dst, st.up_stage[s], sizeof(double) * ldd * pc, cudaMemcpyHostToDevice, st.raw_stream));
+      GBM_CUDA(cudaEventRecord(st.up_copied[s], st.raw_stream));
+    } else if (contiguous) {
+      GBM_CUDA(cudaStreamWaitEvent(st.raw_stream, st.raw_consumed[s], 0));
       GBM_CUDA(cudaMemcpyAsync(dst, A + j0 * lda, sizeof(double) * n * pc, cudaMemcpyDefault, st.raw_stream));
-    else
+    } else {
+      GBM_CUDA(cudaStreamWaitEvent(st.raw_stream, st.raw_consumed[s], 0));
       GBM_CUDA(cudaMemcpy2DAsync(dst, ldd * sizeof(double), A + j0 * lda, lda * sizeof(double), n * sizeof(double),
                                  pc, cudaMemcpyDefault, st.raw_stream));
+    }
     GBM_CUDA(cudaEventRecord(st.raw_copied[s], st.raw_stream));
     h2d_bytes += static_cast<int64_t>(sizeof(double)) * n * pc;
     slot[s].state = 1;

@@ -8,6 +8,7 @@
 #include <immintrin.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <atomic>
 #include <chrono>
@@ -153,6 +154,15 @@ static bool pack_columns(const double* A, int64_t n, int64_t lda, int64_t c0, in
   return false;
 }
 
+// copies columns [c0, c1) into a staging block of pitch ldo doubles (rows n..ldo-1 zeroed): how pageable
+// host memory reaches pinned staging on all cores instead of through the driver's single-threaded bounce
+static void copy_columns(const double* A, int64_t n, int64_t lda, int64_t c0, int64_t c1, double* out, int64_t ldo) {
+  for (int64_t j = c0; j < c1; ++j) {
+    memcpy(out + j * ldo, A + j * lda, sizeof(double) * n);
+    for (int64_t i = n; i < ldo; ++i) out[j * ldo + i] = 0.0;
+  }
+}
+
 int host_threads() {
   int t = 0;
 #ifdef __linux__
@@ -174,8 +184,9 @@ int host_threads() {
 struct PackJob {
   const double* A;
   int64_t n, lda, pc;
-  uint8_t* out;
-  int64_t ldo;
+  uint8_t* out;   // codes (mode 0) or Float64 staging (mode 1)
+  int64_t ldo;    // pitch of out in elements of its type
+  int mode = 0;   // 0: pack to codes with the exactness check; 1: plain re-pitching copy
   int64_t chunk, nchunks;
   int64_t next = 0, done = 0;  // guarded by the queue mutex
   std::atomic<int> bad{0};
@@ -248,7 +259,10 @@ class PackQueue {
       lk.unlock();
       if (!job->bad.load(std::memory_order_relaxed)) {
         const int64_t c0 = c * job->chunk, c1 = std::min(job->pc, c0 + job->chunk);
-        if (pack_columns(job->A, job->n, job->lda, c0, c1, job->out, job->ldo)) job->bad.store(1, std::memory_order_relaxed);
+        if (job->mode == 1)
+          copy_columns(job->A, job->n, job->lda, c0, c1, reinterpret_cast<double*>(job->out), job->ldo);
+        else if (pack_columns(job->A, job->n, job->lda, c0, c1, job->out, job->ldo))
+          job->bad.store(1, std::memory_order_relaxed);
       }
       lk.lock();
       if (++job->done == job->nchunks) done_.notify_all();
@@ -275,6 +289,22 @@ PackJob* pack_submit(const double* A, int64_t n, int64_t lda, int64_t pc, uint8_
   job->pc = pc;
   job->out = out;
   job->ldo = ldo;
+  job->chunk = std::max<int64_t>(1, (int64_t(256) << 10) / (8 * n));
+  job->nchunks = (pc + job->chunk - 1) / job->chunk;
+  pack_queue().submit(job);
+  return job;
+}
+
+// Queues a plain copy of the n x pc block at A (pitch lda) into out (pitch ldo doubles, rows n..ldo-1 zeroed).
+PackJob* copy_submit(const double* A, int64_t n, int64_t lda, int64_t pc, double* out, int64_t ldo) {
+  PackJob* job = new PackJob;
+  job->A = A;
+  job->n = n;
+  job->lda = lda;
+  job->pc = pc;
+  job->out = reinterpret_cast<uint8_t*>(out);
+  job->ldo = ldo;
+  job->mode = 1;
   job->chunk = std::max<int64_t>(1, (int64_t(256) << 10) / (8 * n));
   job->nchunks = (pc + job->chunk - 1) / job->chunk;
   pack_queue().submit(job);

@@ -80,6 +80,9 @@ void launch_gather(const double* src, int64_t lds, const int64_t* rows, int64_t 
 void launch_gather_standardise(const double* src, int64_t lds, int64_t n, const int64_t* cols, int64_t ncols,
                                const double* mean, const double* sd, double* dst, int64_t ldd, cudaStream_t stream);
 
+void launch_gather_standardise_u8(const uint8_t* src, int64_t lds, int64_t n, const int64_t* cols, int64_t ncols,
+                                  const double* mean, const double* sd, double* dst, int64_t ldd, cudaStream_t stream);
+
 // grm_i8.cu ---------------------------------------------------------------------------
 // dG (n x n, zeroed by the caller) += lower-triangle tiles of C C' for the code matrix C (exact integers)
 void launch_grm_i8_accumulate(const uint8_t* A8, int64_t n, int64_t p, int64_t ld8, double* dG, int sm_count,

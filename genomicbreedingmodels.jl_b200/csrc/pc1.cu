@@ -102,6 +102,38 @@ __global__ void __launch_bounds__(256)
     d[i] = (mean || sd) ? (s[i] - mu) / v : s[i];
 }
 
+// the same from one-byte dosage codes (a = code / 240, correctly rounded: exactly the packed matrix' values)
+__global__ void __launch_bounds__(256)
+    gather_standardise_u8_kernel(const uint8_t* __restrict__ src, int64_t lds, int64_t n,
+                                 const int64_t* __restrict__ cols, const double* __restrict__ mean,
+                                 const double* __restrict__ sd, double* __restrict__ dst, int64_t ldd) {
+  const int64_t c = blockIdx.y;
+  const int64_t sj = cols ? cols[c] - 1 : c;
+  const double mu = mean ? mean[sj] : 0.0, v = sd ? sd[sj] : 1.0;
+  const uint8_t* s = src + sj * lds;
+  double* d = dst + c * ldd;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const double a = static_cast<double>(s[i]) / 240.0;
+    d[i] = (mean || sd) ? (a - mu) / v : a;
+  }
+}
+
+void launch_gather_standardise_u8(const uint8_t* src, int64_t lds, int64_t n, const int64_t* cols, int64_t ncols,
+                                  const double* mean, const double* sd, double* dst, int64_t ldd,
+                                  cudaStream_t stream) {
+  if (n <= 0 || ncols <= 0) return;
+  unsigned gx = static_cast<unsigned>((n + 255) / 256);
+  if (gx > 16) gx = 16;
+  for (int64_t c0 = 0; c0 < ncols; c0 += 65535) {
+    const unsigned gy = static_cast<unsigned>(ncols - c0 < 65535 ? ncols - c0 : 65535);
+    gather_standardise_u8_kernel<<<dim3(gx, gy), 256, 0, stream>>>(src, lds, n, cols ? cols + c0 : nullptr, mean, sd,
+                                                                    dst + c0 * ldd, ldd);
+    if (!cols) src += 65535 * lds;
+  }
+  GBM_CUDA(cudaGetLastError());
+}
+
 void launch_gather_standardise(const double* src, int64_t lds, int64_t n, const int64_t* cols, int64_t ncols,
                                const double* mean, const double* sd, double* dst, int64_t ldd, cudaStream_t stream) {
   if (n <= 0 || ncols <= 0) return;

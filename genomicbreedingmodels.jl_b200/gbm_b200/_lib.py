@@ -60,6 +60,7 @@ SIGNATURES = {
     "gbm_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int64), c_char_p, c_int]),
     "gbm_last_timing": (c_int, [POINTER(Timing)]),
     "gbm_matrix_upload": (c_int, [_P, c_int64, c_int64, c_int64, POINTER(c_void_p)]),
+    "gbm_matrix_upload_compact": (c_int, [_P, c_int64, c_int64, c_int64, POINTER(c_void_p), POINTER(c_int)]),
     "gbm_matrix_upload_indexed": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, POINTER(c_void_p)]),
     "gbm_matrix_wrap": (c_int, [_P, c_int64, c_int64, c_int64, POINTER(c_void_p)]),
     "gbm_matrix_generate": (c_int, [c_uint64, c_int64, c_int64, c_int64, c_int, POINTER(c_void_p)]),

@@ -2,7 +2,7 @@
 that run on it.  All arithmetic happens in libgbm_b200.so on the GPU."""
 from __future__ import annotations
 
-from ctypes import byref, c_double, c_int64, c_void_p
+from ctypes import byref, c_double, c_int, c_int64, c_void_p
 
 import numpy as np
 
@@ -50,6 +50,26 @@ class DeviceMatrix:
         p = p0 if c is None else c.size
         check(lib.gbm_matrix_upload_indexed(ptr(A), n0, p0, lda, ptr(r), n, ptr(c), p, byref(h)))
         return cls(h, n, p)
+
+    @classmethod
+    def upload_compact(cls, A) -> "DeviceMatrix":
+        """``gbm_matrix_upload_compact``: the host cores pack the matrix to one-byte dosage codes on the
+        way to the device when every element is an exact dosage level (``.packed`` is then True: 1/8 of the
+        bytes cross PCIe, the Float64 matrix never exists in HBM); otherwise a Float64 upload."""
+        lib = _lib.lib()
+        if isinstance(A, np.ndarray):
+            if A.ndim != 2:
+                raise _lib.ArgumentError("allele frequencies must be a matrix")
+            A = _f64(A)
+            n, p = A.shape
+        else:  # torch CPU tensor of shape (p, n), contiguous == n x p column-major (e.g. pinned)
+            p, n = A.shape
+        h = c_void_p()
+        packed = c_int()
+        check(lib.gbm_matrix_upload_compact(ptr(A), n, p, n, byref(h), byref(packed)))
+        m = cls(h, n, p)
+        m.packed = bool(packed.value)
+        return m
 
     @classmethod
     def wrap_device(cls, data_ptr: int, n: int, p: int, lda: int, keepalive=None) -> "DeviceMatrix":

@@ -149,7 +149,8 @@ class _Prep:
     def free(self):
         if getattr(self, "packed", None) is not None:
             self.packed.free()
-        self.dm.free()
+        if getattr(self, "dm", None) is not None:
+            self.dm.free()
 
 
 def _prepare(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type, standardise, need_kstd,
@@ -164,11 +165,17 @@ def _prepare(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_ty
     pr = _Prep()
     pr.rows1, pr.cols1 = rows1, cols1
     subset = rows1 is not None or cols1 is not None
-    # G = allele_frequencies[rows, cols] goes straight to the device (prediction.jl:129)
-    pr.dm = DeviceMatrix.upload(A, rows1, cols1)
-    # dosage data (every element an exact ploidy level) also gets a one-byte-per-genotype copy:
-    # the scan then reads 1/8 of the bytes and the GRM runs exactly on the INT8 tensor cores
-    pr.packed = pr.dm.pack() if use_packed else None
+    # G = allele_frequencies[rows, cols] goes straight to the device (prediction.jl:129).  Dosage data (every
+    # element an exact ploidy level) is stored as one byte per genotype: the scan then reads 1/8 of the bytes
+    # and the GRM runs exactly on the INT8 tensor cores.  Without subsetting the host cores pack on the way
+    # (gbm_matrix_upload_compact: the Float64 matrix never crosses PCIe); with subsetting the gather runs on
+    # the device and the gathered matrix is packed there.
+    if not subset and use_packed:
+        m = DeviceMatrix.upload_compact(A)
+        pr.dm, pr.packed = (None, m) if m.packed else (m, None)
+    else:
+        pr.dm = DeviceMatrix.upload(A, rows1, cols1)
+        pr.packed = pr.dm.pack() if use_packed else None
     pr.scan_dm = pr.packed if pr.packed is not None else pr.dm
     pr.stats = pr.scan_dm.colstats()  # v = std(G, dims=1); idx_cols (:112-113)
     if np.isnan(pr.stats["sd"]).any():
@@ -228,7 +235,7 @@ def gwasprep(*, genomes: Genomes, phenomes: Phenomes, idx_entries=None, idx_loci
     pr = _prepare(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type, standardise,
                   need_kstd=True, need_pc1=False)
     try:
-        G = pr.dm.download_cols(pr.idx_cols, standardise=standardise)  # :114, :129 on the device
+        G = pr.scan_dm.download_cols(pr.idx_cols, standardise=standardise)  # :114, :129 on the device
         K = pr.K
         fit = _new_fit(pr)
     finally:

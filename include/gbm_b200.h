@@ -88,8 +88,15 @@ int gbm_last_timing(gbm_timing* t);
  *      genomes.allele_frequencies[rows, cols]` of extractxyetc
  *      (/root/reference/src/prediction.jl:129) -------------------------------------- */
 /* A: n x p column-major with leading dimension lda (host or device). The device copy is
- * re-pitched to a 128-byte multiple. */
+ * re-pitched to a 128-byte multiple.  Page-locked and device sources go through the copy engine
+ * directly; a PAGEABLE source (a Julia Array) is copied by the calling process' cores into a ring of
+ * pinned staging blocks that the copy engine drains. */
 int gbm_matrix_upload(const double* A, int64_t n, int64_t p, int64_t lda, gbm_matrix** out);
+/* Same, but the host cores first try to pack the matrix to 1-byte dosage codes (exactness-checked,
+ * see "Compact storage" below): when EVERY element is a code the handle holds the codes (*packed = 1;
+ * 1/8 of the bytes cross PCIe and live in HBM, results equal the Float64 path's), otherwise the
+ * Float64 slab as gbm_matrix_upload (*packed = 0; the attempt stops at the first non-code element). */
+int gbm_matrix_upload_compact(const double* A, int64_t n, int64_t p, int64_t lda, gbm_matrix** out, int* packed);
 /* gather upload: rows[i] / cols[j] are 1-based indices into the n0 x p0 source (either may
  * be NULL = all); this is allele_frequencies[idx_entries[idx], idx_loci_alleles]. */
 int gbm_matrix_upload_indexed(const double* A, int64_t n0, int64_t p0, int64_t lda, const int64_t* rows,

@@ -131,7 +131,7 @@ def test_scan_host_lanes_agree_bit_for_bit_on_mixed_data(gbm, monkeypatch):
     source is page-locked."""
     import torch
 
-    n, p = 1000, 56_000  # 3.5 blocks of 16,000 columns
+    n, p = 1000, 56_000  # 3.5 blocks of 16,640 columns (n off the 16-row pitch: blocks are re-pitched)
     A, ys, pc = _problem(21, n, p, synth.KIND_DIPLOID)
     C = synth.block(22, n, 0, 3000, synth.KIND_CONTINUOUS)
     A[:, 35_000:38_000] = C  # the third block is not dosage data
@@ -164,3 +164,55 @@ def test_scan_host_lanes_agree_bit_for_bit_on_mixed_data(gbm, monkeypatch):
     for key in ("beta", "se", "stat"):
         x, y = want[key][keep], ref[key][keep]
         assert np.nanmax(np.abs(x - y)) <= 1e-11 * max(1.0, np.nanmax(np.abs(x))), key
+
+
+@pytest.mark.parametrize("n,p", [(1000, 9000), (1008, 5000), (37, 11), (4097, 2100)])
+def test_upload_paths_roundtrip(gbm, n, p):
+    """gbm_matrix_upload from pageable memory (host workers -> pinned staging ring -> copy engine) and from
+    page-locked memory (copy engine directly), with and without re-pitching: bit-exact round trips."""
+    import torch
+
+    A = synth.block(31, n, 0, p, synth.KIND_CONTINUOUS)
+    dm = gbm.DeviceMatrix.upload(A)
+    assert np.array_equal(dm.download(), A)
+    dm.free()
+    pinned = torch.empty((p, n), dtype=torch.float64, pin_memory=True)
+    pinned.numpy()[:] = A.T
+    m = gbm.DeviceMatrix.upload_compact(pinned)  # continuous data: Float64 slab
+    assert not m.packed and np.array_equal(m.download(), A)
+    m.free()
+
+
+@pytest.mark.parametrize("kind,packs", [(synth.KIND_TETRAPLOID, True), (synth.KIND_DIPLOID, True),
+                                        (synth.KIND_CONTINUOUS, False)])
+def test_upload_compact(gbm, kind, packs):
+    """The host cores pack on the way to the device when every element is a dosage code; the handle then
+    behaves like the device-packed one (same codes, same scan results, Float64 downloads)."""
+    n, p = 1500, 20_000  # two 128 MB-equivalent blocks
+    A, ys, pc = _problem(5, n, p, kind)
+    m = gbm.DeviceMatrix.upload_compact(A)
+    assert m.packed == packs
+    assert np.array_equal(m.download(), A)
+    dm = gbm.DeviceMatrix.upload(A)
+    ref = dm.pack() if packs else dm
+    a = ref.scan(ys, pc[:, None], model=1)
+    b = m.scan(ys, pc[:, None], model=1)
+    for key in ("beta", "se", "stat", "neglog10p", "mean", "sd", "keep"):
+        assert np.array_equal(a[key], b[key], equal_nan=True), key
+    # G[:, idx_cols] standardised on the device, also from codes (gwas.jl:114, :129)
+    idx = np.flatnonzero(a["keep"])[:700] + 1
+    G1 = dm.download_cols(idx, standardise=True)
+    G2 = m.download_cols(idx, standardise=True)
+    np.testing.assert_allclose(G2, G1, rtol=1e-12, atol=1e-13)
+    want = (A[:, idx - 1] - A[:, idx - 1].mean(axis=0)) / A[:, idx - 1].std(axis=0, ddof=1)
+    np.testing.assert_allclose(G2, want, rtol=1e-10, atol=1e-12)
+    if packs:
+        ref.free()
+        # a single element that is not a code anywhere in the matrix: Float64 slab, nothing lost
+        B = A.copy()
+        B[n - 1, p - 1] = 0.123
+        mb = gbm.DeviceMatrix.upload_compact(B)
+        assert not mb.packed and np.array_equal(mb.download(), B)
+        mb.free()
+    dm.free()
+    m.free()
