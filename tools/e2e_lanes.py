@@ -58,7 +58,8 @@ ref = None
 for name, lanes, flags in (("float64 copies, Float64 kernel (NO_PACK)", None, _lib.SCAN_HOST_NO_PACK),
                            ("copy-engine lane only (device pack)", "copy", 0),
                            ("host lane only (host pack)", "host", 0),
-                           ("both lanes (default)", None, 0)):
+                           ("both lanes", "both", 0),
+                           ("default (host lane with >= 8 host threads, else copy-engine lane)", None, 0)):
     if lanes:
         os.environ["GBM_SCAN_HOST_LANES"] = lanes
     else:
@@ -111,3 +112,19 @@ res["h2d_GBps"] = copied / (time.perf_counter() - t0) / 1e9
 th.join()
 res["what"] = "gbm_pack_host and plain pinned H2D copies at the same time"
 print(json.dumps(res), flush=True)
+
+# ingestion: gbm_matrix_upload / gbm_matrix_upload_compact from pageable and page-locked memory
+pag = np.empty((n, pe // 2), order="F")
+pag[:] = host.numpy()[: pe // 2].T
+pin = host[: pe // 2]
+for name, src, fn in (("upload pageable (staged by host workers)", pag, gbm_b200.DeviceMatrix.upload),
+                      ("upload_compact pageable (packed by host workers)", pag, gbm_b200.DeviceMatrix.upload_compact),
+                      ("upload_compact page-locked", pin, gbm_b200.DeviceMatrix.upload_compact)):
+    best = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter()
+        m = fn(src)
+        best = min(best, time.perf_counter() - t0)
+        packed = bool(getattr(m, "packed", False))
+        m.free()
+    print(json.dumps({"what": name, "GBps_f64_equiv": 8.0 * n * (pe // 2) / best / 1e9, "packed": packed}), flush=True)
