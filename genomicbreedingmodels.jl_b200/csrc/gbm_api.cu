@@ -1236,7 +1236,31 @@ int gbm_kstd_pc1(const double* K, int64_t n, double* Kstd, double* pc1, double* 
     launch_grm_accumulate(dZ.p, n, n, ld, dzero.p, dB.p, st.sm_count, st.stream, false);
     launch_grm_finalize(dB.p, n, 1.0, st.stream);
     st.launches += 3;
-    // largest eigenpair of B through cuSOLVER (timed separately, as BASELINE.json asks)
+    // PC1 = the eigenvector of the largest eigenvalue of B.  n >= 1024: Lanczos with full reorthogonalisation
+    // (csrc/lanczos.cu; only ONE eigenvector is needed, not the decomposition); below that, when it does not
+    // converge, or with GBM_PC1_SOLVER=cusolver: cusolverDnDsyevdx.  Timed separately either way (eig_ms).
+    const char* solver_env = getenv("GBM_PC1_SOLVER");
+    const bool force_cusolver = solver_env && !strcmp(solver_env, "cusolver");
+    const bool force_lanczos = solver_env && !strcmp(solver_env, "lanczos");
+    bool have_pc1 = false;
+    if (!force_cusolver && (n >= 1024 || force_lanczos) && (n & 1) == 0) {
+      DevBuf<double> dx(static_cast<size_t>(n), st.stream);
+      Span eig(st.stream);
+      eig.start();
+      int iters = 0;
+      double theta = 0.0;
+      have_pc1 = lanczos_top_eigenpair(dB.p, n, n, 1e-14, 3000, dx.p, &theta, &iters, st.sm_count, st.stream);
+      eig.stop();
+      if (have_pc1) {
+        copy_out(pc1, dx.p, sizeof(double) * n, st.stream);
+        GBM_CUDA(cudaStreamSynchronize(st.stream));
+        if (eig_ms) *eig_ms = eig.ms();
+        st.main_ms = eig.ms();
+        st.launches += iters;
+      }
+    }
+    if (!have_pc1) {
+    // largest eigenpair of B through cuSOLVER
     if (!st.cusolver) {
       cusolverDnHandle_t h;
       if (cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS) GBM_THROW(GBM_ERR_CUDA, "cusolverDnCreate failed");
@@ -1265,6 +1289,7 @@ int gbm_kstd_pc1(const double* K, int64_t n, double* Kstd, double* pc1, double* 
     if (info != 0 || meig != 1) GBM_THROW(GBM_ERR_RUNTIME, "PCA of the GRM failed (syevdx info " + std::to_string(info) + ")");
     copy_out(pc1, dB.p, sizeof(double) * n, st.stream);  // first column = the eigenvector
     if (eig_ms) *eig_ms = eig.ms();
+    }
   }
   all.stop();
   GBM_CUDA(cudaStreamSynchronize(st.stream));

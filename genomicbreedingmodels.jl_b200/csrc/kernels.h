@@ -107,6 +107,13 @@ void launch_lmm_delta(int Q0, const double* Ar, int64_t n, int64_t pb, int64_t l
 // null-model log(delta) on the host from rotated vectors
 double lmm_null_lam0(int Q0, const double* S, const double* Cr, int64_t ldcr, const double* Yr, int64_t n);
 
+// lanczos.cu --------------------------------------------------------------------------
+// Largest eigenpair of the symmetric PSD matrix B (n x n, pitch ldb even, 16-byte aligned, device) by Lanczos with
+// full reorthogonalisation; x_dev (device, n) gets the unit eigenvector.  Returns false when the explicit residual
+// ||B x - theta x|| <= max(20 tol, 2e-13) theta was not reached within max_iter steps (the caller then uses cuSOLVER).
+bool lanczos_top_eigenpair(const double* B, int64_t n, int64_t ldb, double tol, int max_iter, double* x_dev,
+                           double* theta, int* iters, int sm_count, cudaStream_t stream);
+
 // transform.cu -------------------------------------------------------------------------
 // Per-locus OLS screen of f(x): beta[j] (0 when var(x) < var_thr) and colvar[j] = var(x) (nullable).
 // f = -1: variance pass only.  yc = y - ybar (device, n).

@@ -1,0 +1,298 @@
+// Largest eigenpair of a symmetric positive semi-definite matrix by Lanczos with full
+// reorthogonalisation -- the PC1 step of gwasols / gwaslmm (/root/reference/src/gwas.jl:234, :357:
+// `fit(PCA, GRM; maxoutdim = 1)`, `E.proj[:, 1]`), which needs ONE eigenvector of B = Z Z', not the
+// n x n decomposition cuSOLVER's syevdx computes on the way (tridiagonalisation of the whole matrix:
+// 0.71 s at n = 10,000 against ~0.1 s here).  gbm_kstd_pc1 falls back to cuSOLVER when this does not
+// converge, and GBM_PC1_SOLVER=cusolver forces it.
+//
+// Per step: w = B v_j (one pass over B, HBM-bound: 8 n^2 bytes), classical Gram-Schmidt twice against
+// all previous vectors (alpha_j falls out of the projections), beta_j = ||w||, v_{j+1} = w / beta_j.
+// alpha / beta stay on the device; every few steps the host solves the small tridiagonal problem
+// (bisection + inverse iteration) and tests the residual estimate beta_j |s_j| <= tol theta.  All
+// reductions have a fixed order: the result is deterministic (every rank of a sharded run computes the
+// same PC1 bit for bit).
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gbm {
+
+namespace {
+
+__device__ __forceinline__ double block_sum_256(double v, double* sh) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += sh[w];  // fixed order
+  return t;  // valid in thread 0
+}
+
+// y[j] = B[:, j] . v   (B symmetric, column-major, pitch ld): one warp per column
+__global__ void __launch_bounds__(256) symv_kernel(const double* __restrict__ B, int64_t n, int64_t ld,
+                                                   const double* __restrict__ v, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * 8;
+  const int64_t n2 = n >> 1;
+  const double2* __restrict__ v2 = reinterpret_cast<const double2*>(v);
+  for (int64_t j = (static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x) >> 5; j < n; j += nwarps) {
+    const double2* __restrict__ c2 = reinterpret_cast<const double2*>(B + j * ld);
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll 4
+    for (int64_t i = lane; i < n2; i += 32) {
+      const double2 a = c2[i], b = v2[i];
+      s0 = fma(a.x, b.x, s0);
+      s1 = fma(a.y, b.y, s1);
+    }
+    double s = s0 + s1;
+    if ((n & 1) && lane == 0) s = fma(B[j * ld + n - 1], v[n - 1], s);
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+    if (lane == 0) y[j] = s;
+  }
+}
+
+// c[k] = V[:, k] . w for k < cols: one CTA per column, fixed-order reduction
+__global__ void __launch_bounds__(256) dots_kernel(const double* __restrict__ V, int64_t n, int64_t ldv,
+                                                   const double* __restrict__ w, double* __restrict__ c) {
+  __shared__ double sh[8];
+  const double* col = V + static_cast<int64_t>(blockIdx.x) * ldv;
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 256) s = fma(col[i], w[i], s);
+  const double t = block_sum_256(s, sh);
+  if (threadIdx.x == 0) c[blockIdx.x] = t;
+}
+
+// w -= V[:, 0..cols) c ; alpha[j] (+)= c[j] (the projection on the current vector is the Lanczos alpha)
+__global__ void __launch_bounds__(256) project_out_kernel(const double* __restrict__ V, int64_t n, int64_t ldv, int cols,
+                                                          const double* __restrict__ c, double* __restrict__ w,
+                                                          double* __restrict__ alpha, int j, int accumulate) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i < n) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int k = 0;
+    for (; k + 4 <= cols; k += 4) {
+      a0 = fma(V[(k + 0) * ldv + i], c[k + 0], a0);
+      a1 = fma(V[(k + 1) * ldv + i], c[k + 1], a1);
+      a2 = fma(V[(k + 2) * ldv + i], c[k + 2], a2);
+      a3 = fma(V[(k + 3) * ldv + i], c[k + 3], a3);
+    }
+    for (; k < cols; ++k) a0 = fma(V[k * ldv + i], c[k], a0);
+    w[i] -= (a0 + a1) + (a2 + a3);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) alpha[j] = accumulate ? alpha[j] + c[j] : c[j];
+}
+
+// beta[j] = ||w||, V[:, j+1] = w / beta[j]   (single CTA)
+__global__ void __launch_bounds__(256) norm_next_kernel(const double* __restrict__ w, int64_t n, double* __restrict__ vnext,
+                                                        double* __restrict__ beta, int j) {
+  __shared__ double sh[8];
+  __shared__ double inv;
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 256) s = fma(w[i], w[i], s);
+  const double t = block_sum_256(s, sh);
+  if (threadIdx.x == 0) {
+    const double b = sqrt(t);
+    beta[j] = b;
+    inv = b > 0.0 ? 1.0 / b : 0.0;
+  }
+  __syncthreads();
+  for (int64_t i = threadIdx.x; i < n; i += 256) vnext[i] = w[i] * inv;
+}
+
+// deterministic start vector: splitmix64 of the row index, mapped to (-1, 1), normalised by norm_next_kernel
+__global__ void __launch_bounds__(256) start_vector_kernel(double* __restrict__ w, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  uint64_t z = static_cast<uint64_t>(i) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  w[i] = static_cast<double>(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+}
+
+// x = V[:, 0..cols) s
+__global__ void __launch_bounds__(256) combine_kernel(const double* __restrict__ V, int64_t n, int64_t ldv, int cols,
+                                                      const double* __restrict__ s, double* __restrict__ x) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  double a0 = 0.0, a1 = 0.0;
+  int k = 0;
+  for (; k + 2 <= cols; k += 2) {
+    a0 = fma(V[k * ldv + i], s[k], a0);
+    a1 = fma(V[(k + 1) * ldv + i], s[k + 1], a1);
+  }
+  if (k < cols) a0 = fma(V[k * ldv + i], s[k], a0);
+  x[i] = a0 + a1;
+}
+
+// ---- host: largest eigenpair of the m x m symmetric tridiagonal (a, b) ----------------------------
+int sturm_count_below(const std::vector<double>& a, const std::vector<double>& b, int m, double x) {
+  int cnt = 0;
+  double q = a[0] - x;
+  if (q < 0) ++cnt;
+  for (int i = 1; i < m; ++i) {
+    if (q == 0.0) q = 1e-300;
+    q = a[i] - x - b[i - 1] * b[i - 1] / q;
+    if (q < 0) ++cnt;
+  }
+  return cnt;
+}
+
+void tridiag_top(const std::vector<double>& a, const std::vector<double>& b, int m, double* theta, std::vector<double>* s) {
+  double lo = a[0], hi = a[0];
+  for (int i = 0; i < m; ++i) {
+    const double r = (i > 0 ? fabs(b[i - 1]) : 0.0) + (i + 1 < m ? fabs(b[i]) : 0.0);
+    lo = std::min(lo, a[i] - r);
+    hi = std::max(hi, a[i] + r);
+  }
+  // largest eigenvalue: the smallest x with count(x) == m is just above it
+  for (int it = 0; it < 200; ++it) {
+    const double mid = 0.5 * (lo + hi);
+    if (mid <= lo || mid >= hi) break;
+    if (sturm_count_below(a, b, m, mid) == m) hi = mid; else lo = mid;
+  }
+  *theta = 0.5 * (lo + hi);
+  // inverse iteration with a pivoted tridiagonal solve
+  s->assign(m, 1.0 / sqrt(static_cast<double>(m)));
+  if (m == 1) {
+    (*s)[0] = 1.0;
+    return;
+  }
+  const double scale = std::max(fabs(lo), fabs(hi));
+  const double shift = *theta + 4.0 * 2.220446049250313e-16 * (scale > 0 ? scale : 1.0);
+  std::vector<double> d(m), du(m), du2(m), dl(m), rhs(m);
+  for (int iter = 0; iter < 4; ++iter) {
+    for (int i = 0; i < m; ++i) {
+      d[i] = a[i] - shift;
+      du[i] = i + 1 < m ? b[i] : 0.0;
+      dl[i] = i + 1 < m ? b[i] : 0.0;  // dl[i] couples row i+1 to column i
+      du2[i] = 0.0;
+      rhs[i] = (*s)[i];
+    }
+    for (int i = 0; i + 1 < m; ++i) {  // elimination with partial pivoting (as LAPACK dgtsv)
+      if (fabs(d[i]) >= fabs(dl[i])) {
+        const double piv = d[i] != 0.0 ? d[i] : 1e-300;
+        const double f = dl[i] / piv;
+        d[i] = piv;
+        d[i + 1] -= f * du[i];
+        rhs[i + 1] -= f * rhs[i];
+        du2[i] = 0.0;
+      } else {
+        const double f = d[i] / dl[i];
+        d[i] = dl[i];
+        const double t = d[i + 1];
+        d[i + 1] = du[i] - f * t;
+        du2[i] = i + 2 < m ? du[i + 1] : 0.0;
+        if (i + 2 < m) du[i + 1] = -f * du2[i];
+        du[i] = t;
+        std::swap(rhs[i], rhs[i + 1]);
+        rhs[i + 1] -= f * rhs[i];
+      }
+    }
+    if (d[m - 1] == 0.0) d[m - 1] = 1e-300;
+    rhs[m - 1] /= d[m - 1];
+    if (m > 1) rhs[m - 2] = (rhs[m - 2] - du[m - 2] * rhs[m - 1]) / d[m - 2];
+    for (int i = m - 3; i >= 0; --i) rhs[i] = (rhs[i] - du[i] * rhs[i + 1] - du2[i] * rhs[i + 2]) / d[i];
+    double nrm = 0.0;
+    for (int i = 0; i < m; ++i) nrm += rhs[i] * rhs[i];
+    nrm = sqrt(nrm);
+    if (!(nrm > 0.0) || !std::isfinite(nrm)) break;
+    for (int i = 0; i < m; ++i) (*s)[i] = rhs[i] / nrm;
+  }
+}
+
+}  // namespace
+
+bool lanczos_top_eigenpair(const double* B, int64_t n, int64_t ldb, double tol, int max_iter, double* x_dev,
+                           double* theta_out, int* iters_out, int sm_count, cudaStream_t stream) {
+  if ((ldb & 1) != 0 || (reinterpret_cast<uintptr_t>(B) & 15u) != 0) return false;
+  const int m_max = static_cast<int>(std::min<int64_t>(max_iter, n - 1));
+  if (m_max < 2) return false;
+  const int64_t ldv = (n + 1) / 2 * 2;
+  double *V = nullptr, *w = nullptr, *c = nullptr, *alpha = nullptr, *beta = nullptr, *sdev = nullptr;
+  auto release = [&] {
+    for (double* p : {V, w, c, alpha, beta, sdev})
+      if (p) cudaFreeAsync(p, stream);
+  };
+  try {
+    GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&V), sizeof(double) * ldv * (m_max + 1), stream));
+    GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&w), sizeof(double) * ldv, stream));
+    GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&c), sizeof(double) * (m_max + 1), stream));
+    GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&alpha), sizeof(double) * (m_max + 1), stream));
+    GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&beta), sizeof(double) * (m_max + 1), stream));
+    GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&sdev), sizeof(double) * (m_max + 1), stream));
+    GBM_CUDA(cudaMemsetAsync(w, 0, sizeof(double) * ldv, stream));
+    const unsigned row_blocks = static_cast<unsigned>((n + 255) / 256);
+    const unsigned symv_grid = static_cast<unsigned>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(sm_count) * 8));
+    start_vector_kernel<<<row_blocks, 256, 0, stream>>>(w, n);
+    norm_next_kernel<<<1, 256, 0, stream>>>(w, n, V, beta, m_max);  // V[:, 0] = unit start vector (beta slot unused)
+
+    std::vector<double> ha, hb, s;
+    bool converged = false;
+    int m = 0;
+    double theta = 0.0;
+    int next_check = 30;
+    for (int j = 0; j < m_max; ++j) {
+      const double* vj = V + static_cast<int64_t>(j) * ldv;
+      symv_kernel<<<symv_grid, 256, 0, stream>>>(B, n, ldb, vj, w);
+      for (int pass = 0; pass < 2; ++pass) {  // classical Gram-Schmidt, twice
+        dots_kernel<<<j + 1, 256, 0, stream>>>(V, n, ldv, w, c);
+        project_out_kernel<<<row_blocks, 256, 0, stream>>>(V, n, ldv, j + 1, c, w, alpha, j, pass);
+      }
+      norm_next_kernel<<<1, 256, 0, stream>>>(w, n, V + static_cast<int64_t>(j + 1) * ldv, beta, j);
+      m = j + 1;
+      if (m == next_check || m == m_max) {
+        GBM_CUDA(cudaGetLastError());
+        ha.resize(m);
+        hb.resize(m);
+        GBM_CUDA(cudaMemcpyAsync(ha.data(), alpha, sizeof(double) * m, cudaMemcpyDeviceToHost, stream));
+        GBM_CUDA(cudaMemcpyAsync(hb.data(), beta, sizeof(double) * m, cudaMemcpyDeviceToHost, stream));
+        GBM_CUDA(cudaStreamSynchronize(stream));
+        tridiag_top(ha, hb, m, &theta, &s);
+        const double resid = fabs(hb[m - 1] * s[m - 1]);
+        if (resid <= tol * fabs(theta) || !(hb[m - 1] > 1e-14 * fabs(theta))) {
+          converged = true;
+          break;
+        }
+        next_check = m + std::max(10, m / 8);
+      }
+    }
+    if (converged) {
+      GBM_CUDA(cudaMemcpyAsync(sdev, s.data(), sizeof(double) * m, cudaMemcpyHostToDevice, stream));
+      combine_kernel<<<row_blocks, 256, 0, stream>>>(V, n, ldv, m, sdev, w);
+      norm_next_kernel<<<1, 256, 0, stream>>>(w, n, x_dev, beta, 0);  // unit norm
+      // explicit residual ||B x - theta x|| as the final word
+      symv_kernel<<<symv_grid, 256, 0, stream>>>(B, n, ldb, x_dev, w);
+      GBM_CUDA(cudaGetLastError());
+      std::vector<double> hx(n), hy(n);
+      GBM_CUDA(cudaMemcpyAsync(hx.data(), x_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
+      GBM_CUDA(cudaMemcpyAsync(hy.data(), w, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
+      GBM_CUDA(cudaStreamSynchronize(stream));
+      long double rq = 0, r2 = 0;
+      for (int64_t i = 0; i < n; ++i) rq += static_cast<long double>(hx[i]) * hy[i];
+      for (int64_t i = 0; i < n; ++i) {
+        const long double r = hy[i] - rq * hx[i];
+        r2 += r * r;
+      }
+      theta = static_cast<double>(rq);
+      converged = sqrt(static_cast<double>(r2)) <= std::max(20.0 * tol, 2e-13) * fabs(theta);
+    }
+    release();
+    if (theta_out) *theta_out = theta;
+    if (iters_out) *iters_out = m;
+    return converged;
+  } catch (...) {
+    release();
+    throw;
+  }
+}
+
+}  // namespace gbm

@@ -244,3 +244,63 @@ def test_host_packer_vector_predicate_equals_the_division():
     for isa, ok in got.items():
         bad = np.nonzero(ok != want)[0]
         assert bad.size == 0, (isa, v[bad[:5]], ok[bad[:5]], want[bad[:5]])
+
+
+def test_lanczos_tridiagonal_solver_on_the_host():
+    """csrc/lanczos.cu solves the small tridiagonal problem on the host (bisection + inverse iteration with a
+    pivoted solve): largest eigenpair against scipy on random, graded, nearly-degenerate and tiny cases."""
+    import subprocess
+    import tempfile
+
+    from scipy.linalg import eigh_tridiagonal
+
+    csrc = os.path.join(ROOT, "genomicbreedingmodels.jl_b200", "csrc")
+    src = r"""
+#include "lanczos.cu"
+#include <stdio.h>
+int main() {
+  int m;
+  while (scanf("%d", &m) == 1) {
+    std::vector<double> a(m), b(m), s;
+    for (int i = 0; i < m; ++i) scanf("%lf", &a[i]);
+    for (int i = 0; i + 1 < m; ++i) scanf("%lf", &b[i]);
+    double theta;
+    gbm::tridiag_top(a, b, m, &theta, &s);
+    printf("%.17g", theta);
+    for (int i = 0; i < m; ++i) printf(" %.17g", s[i]);
+    printf("\n");
+  }
+  return 0;
+}
+"""
+    rng = np.random.default_rng(3)
+    cases = []
+    for m in (1, 2, 3, 7, 40, 333):
+        cases.append((rng.normal(size=m) * 3 + 10, np.abs(rng.normal(size=max(m - 1, 0))) + 0.1))
+    cases.append((np.linspace(1, 2, 50) ** 8, np.full(49, 1e-3)))           # graded
+    cases.append((np.full(60, 5.0), np.full(59, 1e-9)))                      # nearly degenerate
+    cases.append((np.array([4.0, 4.0, 1.0]), np.array([0.0, 0.5])))          # a zero coupling
+    cases.append((rng.normal(size=200) * 1e3, rng.normal(size=199) * 1e3))   # negative couplings, large scale
+    text = ""
+    for a, b in cases:
+        text += f"{a.size} " + " ".join(repr(float(x)) for x in a) + " " + " ".join(repr(float(x)) for x in b) + "\n"
+    with tempfile.TemporaryDirectory() as td:
+        cu = os.path.join(td, "tri.cu")
+        open(cu, "w").write(src)
+        exe = os.path.join(td, "tri")
+        subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-ccbin", "/usr/bin/g++", "-O2", "-std=c++17",
+                               "-gencode", "arch=compute_100a,code=sm_100a", "-I", csrc, "-o", exe, cu])
+        out = subprocess.run([exe], input=text, capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    assert len(out) == len(cases)
+    for (a, b), line in zip(cases, out):
+        vals = np.array([float(v) for v in line.split()])
+        theta, s = vals[0], vals[1:]
+        if a.size == 1:
+            assert theta == a[0] and s[0] == 1.0
+            continue
+        w, v = eigh_tridiagonal(a, b)
+        scale = max(np.abs(w).max(), 1e-300)
+        assert abs(theta - w[-1]) <= 4e-15 * scale, (a.size, theta, w[-1])
+        T = np.diag(a) + np.diag(b, 1) + np.diag(b, -1)
+        assert abs(np.linalg.norm(s) - 1.0) < 1e-12
+        assert np.linalg.norm(T @ s - theta * s) <= 1e-13 * scale * np.sqrt(a.size), a.size

@@ -209,6 +209,36 @@ def test_kstd_pc1_matches_oracle(gbm, n):
     assert np.max(np.abs(sgn * pc - want_pc)) < 1e-9
 
 
+@pytest.mark.parametrize("n,kind", [(1024, synth.KIND_DIPLOID), (1500, synth.KIND_CONTINUOUS), (2600, synth.KIND_TETRAPLOID)])
+def test_pc1_lanczos_matches_oracle_and_cusolver(gbm, n, kind, monkeypatch):
+    """n >= 1024: PC1 comes from the Lanczos solver (csrc/lanczos.cu).  The spectrum of the standardised GRM
+    is a near-degenerate bulk (relative gap of the top eigenvalue ~3e-3), the hard case for an iterative
+    solver: the vector must still match the oracle's LAPACK SVD and cuSOLVER's syevdx to 1e-9, and the scan
+    statistics computed with it must match to 1e-9 relative."""
+    A = synth.block(12, n, 0, 3 * n, kind)
+    K = go.grm_simple(A)
+    want_pc = go.pca_pc1(go.standardise_K(K))
+    monkeypatch.delenv("GBM_PC1_SOLVER", raising=False)
+    _, pc, eig_ms = gbm.kstd_pc1(K, want_kstd=False)
+    assert gbm.last_timing()["launches"] > 20  # the iterative solver ran (its steps are counted as launches)
+    monkeypatch.setenv("GBM_PC1_SOLVER", "cusolver")
+    _, pc_cs, _ = gbm.kstd_pc1(K, want_kstd=False)
+    monkeypatch.delenv("GBM_PC1_SOLVER", raising=False)
+    _, pc_again, _ = gbm.kstd_pc1(K, want_kstd=False)
+    assert np.array_equal(pc, pc_again)  # deterministic
+    assert abs(np.linalg.norm(pc) - 1) < 1e-12 and abs(pc.sum()) < 1e-9
+    for other in (want_pc, pc_cs):
+        sgn = np.sign(pc @ other)
+        assert np.max(np.abs(sgn * pc - other)) < 1e-9
+    y = synth.phenotype(12, n, 3 * n, kind)
+    ys = (y - y.mean()) / y.std(ddof=1)
+    dm = gbm.DeviceMatrix.upload(A[:, :500])
+    a = dm.scan(ys, pc[:, None], model=1)["stat"]
+    b = dm.scan(ys, want_pc[:, None], model=1)["stat"]
+    dm.free()
+    assert rel_err(a, b) < RTOL
+
+
 # ---------------------------------------------------------------------------------------
 def _structs(gbm, n, p, kind, seed=42):
     A = synth.block(seed, n, 0, p, kind)
