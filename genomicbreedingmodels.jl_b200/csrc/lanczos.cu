@@ -9,8 +9,7 @@
 // all previous vectors (alpha_j falls out of the projections), beta_j = ||w||, v_{j+1} = w / beta_j.
 // alpha / beta stay on the device; every few steps the host solves the small tridiagonal problem
 // (bisection + inverse iteration) and tests the residual estimate beta_j |s_j| <= tol theta.  All
-// reductions have a fixed order: the result is deterministic (every rank of a sharded run computes the
-// same PC1 bit for bit).
+// reductions have a fixed order: the result is a deterministic function of B.
 #include <math.h>
 
 #include <algorithm>
