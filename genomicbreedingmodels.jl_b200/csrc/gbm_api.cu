@@ -1402,8 +1402,10 @@ int gbm_scan_plan_create(const gbm_matrix* m, const double* Y, int64_t T, int64_
   pl->flags = flags;
   pl->passes = build_passes(sv, m->n, T);
   for (const auto& ps : pl->passes) {
+    // stream-ordered pool allocation: a plain cudaMalloc / cudaFree pair per gbm_scan call cost between
+    // 20 ms and more than a second of host time at p = 1,000,000 (tools/diag_scan.py)
     double* r = nullptr;
-    GBM_CUDA(cudaMalloc(reinterpret_cast<void**>(&r), sizeof(double) * m->p * ps->stride));
+    GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&r), sizeof(double) * m->p * ps->stride, st.stream));
     pl->rec.push_back(r);
   }
   pl->out.reset(new OutTargets(st.stream));
@@ -1440,8 +1442,12 @@ int gbm_scan_plan_run(gbm_scan_plan* pl, double* beta, double* se, double* stat,
 int gbm_scan_plan_free(gbm_scan_plan* pl) {
   GBM_API_BEGIN
   if (pl) {
-    if (state().ready) cudaStreamSynchronize(state().stream);
-    for (double* r : pl->rec) cudaFree(r);
+    if (state().ready) {
+      for (double* r : pl->rec) cudaFreeAsync(r, state().stream);
+      cudaStreamSynchronize(state().stream);
+    } else {
+      for (double* r : pl->rec) cudaFree(r);
+    }
     delete pl;
   }
   GBM_API_END
