@@ -598,7 +598,35 @@ def run_pipeline(gbm_b200, _lib, n, p_loc, j0, ys):
         pkd["filter_identical"] = bool(np.array_equal(st2["idx_cols"], st["idx_cols"]))
         out["packed_int8"] = pkd
         pk.free()
-    dm.free()
+    # the same from HOST memory (what the drop-in API gets: a pageable Float64 matrix): ingestion by
+    # gbm_matrix_upload_compact (host cores pack on the way) + the packed pipeline above
+    fh = {}
+    try:
+        host = np.empty((p_loc, n))  # C-order (p, n) == n x p column-major; pageable, like a Julia Array
+        dm.download_into(host)
+        dm.free()
+        dm = None
+        A = host.T  # F-contiguous view n x p
+        for attempt in ("cold", "warm"):
+            t_all = time.perf_counter()
+            m = gbm_b200.DeviceMatrix.upload_compact(A)
+            fh["upload_s"] = time.perf_counter() - t_all
+            fh["packed"] = bool(m.packed)
+            st3 = m.colstats()
+            _, tf = m.grm(_lib.GRM_SIMPLE, 2, 0, out=dK)
+            pc3, eig_ms = gbm_b200.kstd_pc1_device(dK.data_ptr(), n)
+            res3 = m.scan(ys, pc3[:, None], model=_lib.MODEL_LMM)
+            fh["total_s"] = time.perf_counter() - t_all
+            m.free()
+        fh["markers_per_s_whole_gwaslmm_from_host"] = p_loc / fh["total_s"]
+        fh["upload_GBps_f64_equiv"] = 8.0 * n * p_loc / fh["upload_s"] / 1e9
+        fh["max_neglog10p"] = float(np.nanmax(res3["neglog10p"]))
+        del host, A
+    except MemoryError as e:
+        fh["skipped"] = f"host matrix does not fit: {e}"
+    out["from_host"] = fh
+    if dm is not None:
+        dm.free()
     return out
 
 

@@ -118,6 +118,12 @@ class DeviceMatrix:
         check(_lib.load().gbm_matrix_download(self._h, j0, ncols, ptr(out), self.n))
         return out
 
+    def download_into(self, out: np.ndarray, j0: int = 0):
+        """Columns j0 .. j0 + out.shape[0] - 1 into ``out``, a C-contiguous (ncols, n) array (= n x ncols
+        column-major), without allocating."""
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape[1] == self.n
+        check(_lib.load().gbm_matrix_download(self._h, j0, out.shape[0], ptr(out), self.n))
+
     def download_cols(self, idx_cols=None, standardise: bool = False) -> np.ndarray:
         """G[:, idx_cols] (1-based), optionally column-standardised on the device
         (/root/reference/src/gwas.jl:114, :129)."""
