@@ -17,6 +17,7 @@
 //   transform_select        sortperm(abs.(beta), rev = true)[1:n_new] + abs(beta) > eps (stable radix sort)
 #include <cub/device/device_radix_sort.cuh>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -174,18 +175,23 @@ __device__ __forceinline__ double pair_shifted(double ai, double aj, double z0) 
 }
 
 // Xi: operand matrix of the i side (X', or log X' for kRaiseFast); Xj: X'.  Both n x l, pitch ldx.
-template <int F>
-__global__ void __launch_bounds__(256, 1)
+// Register tile per thread: 4 (i) x TJ (j) pairs; 64 / TJ lanes run along j, so TJ = 2 is 512 threads
+// (16 warps / SM, ~110 registers) and TJ = 4 is 256 threads (8 warps / SM, ~230 registers).
+template <int F, int TJ>
+__global__ void __launch_bounds__(1024 / TJ, 1)
     transform2_scan_kernel(const double* __restrict__ Xi, const double* __restrict__ Xj, int64_t n, int64_t l,
                            int64_t ldx, const double* __restrict__ yc, double ybar,
                            const double* __restrict__ colvar, double var_thr, int commutative,
                            double* __restrict__ beta) {
+  constexpr int NJ = kTile / TJ;        // threads along j (16 or 32)
+  constexpr int THREADS = 16 * NJ;      // 16 threads along i
+  constexpr int LOADS = 2 * kTile * kRows / THREADS;  // cp.async per thread and stage (ai + aj)
   const int bi = blockIdx.y, bj = blockIdx.x;
   if (commutative && bj < bi) return;  // every pair of the tile has j < i (transformation.jl:373)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T2Stage* stage = reinterpret_cast<T2Stage*>(smem_raw);
   const int tid = threadIdx.x;
-  const int tj = tid & 15, ti = tid >> 4;  // lanes run along j: coalesced beta stores, conflict-free aj reads
+  const int tj = tid % NJ, ti = tid / NJ;  // lanes run along j: coalesced beta stores, conflict-free aj reads
   const int64_t i0 = static_cast<int64_t>(bi) * kTile, j0 = static_cast<int64_t>(bj) * kTile;
   // loci beyond l are clamped for loading (finite values, never stored)
   auto icol = [&](int c) { return min(i0 + c, l - 1); };
@@ -196,8 +202,8 @@ __global__ void __launch_bounds__(256, 1)
     const int row = tid & 31;
     if (r0 + row < n) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int c = (tid >> 5) + 8 * k;
+      for (int k = 0; k < LOADS / 2; ++k) {
+        const int c = (tid >> 5) + (THREADS / 32) * k;
         cp_async8(&st.ai[c * kPitch + row], Xi + icol(c) * ldx + r0 + row);
         cp_async8(&st.aj[c * kPitch + row], Xj + jcol(c) * ldx + r0 + row);
       }
@@ -206,18 +212,17 @@ __global__ void __launch_bounds__(256, 1)
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  double z0[4][4], s1[4][4], s2[4][4], sy[4][4];
+  double z0[4][TJ], s1[4][TJ], s2[4][TJ], sy[4][TJ];
   {
-    double xi[4], xj[4];
+    double xi[4], xj[TJ];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      xi[a] = Xi[icol(ti + 16 * a) * ldx];
-      xj[a] = Xj[jcol(tj + 16 * a) * ldx];
-    }
+    for (int a = 0; a < 4; ++a) xi[a] = Xi[icol(ti + 16 * a) * ldx];
+#pragma unroll
+    for (int b = 0; b < TJ; ++b) xj[b] = Xj[jcol(tj + NJ * b) * ldx];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
+      for (int b = 0; b < TJ; ++b) {
         z0[a][b] = pair_feature<F>(xi[a], xj[b]);
         s1[a][b] = s2[a][b] = sy[a][b] = 0.0;
       }
@@ -236,17 +241,16 @@ __global__ void __launch_bounds__(256, 1)
     const T2Stage& st = stage[c & 1];
     const int rmax = static_cast<int>(min(static_cast<int64_t>(kRows), n - c * kRows));
     auto row_step = [&](int r) {
-      double xi[4], xj[4];
+      double xi[4], xj[TJ];
       const double y = st.y[r];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        xi[a] = st.ai[(ti + 16 * a) * kPitch + r];
-        xj[a] = st.aj[(tj + 16 * a) * kPitch + r];
-      }
+      for (int a = 0; a < 4; ++a) xi[a] = st.ai[(ti + 16 * a) * kPitch + r];
+#pragma unroll
+      for (int b = 0; b < TJ; ++b) xj[b] = st.aj[(tj + NJ * b) * kPitch + r];
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < TJ; ++b) {
           const double d = pair_shifted<F>(xi[a], xj[b], z0[a][b]);
           s1[a][b] += d;
           s2[a][b] = fma(d, d, s2[a][b]);
@@ -268,8 +272,8 @@ __global__ void __launch_bounds__(256, 1)
     const int64_t i = i0 + ti + 16 * a;
     if (i >= l || colvar[i] < var_thr) continue;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int64_t j = j0 + tj + 16 * b;
+    for (int b = 0; b < TJ; ++b) {
+      const int64_t j = j0 + tj + NJ * b;
       if (j >= l || colvar[j] < var_thr || (commutative && j < i)) continue;
       beta[i * l + j] = slope_from_sums(dn, z0[a][b], s1[a][b], s2[a][b], sy[a][b], ybar);
     }
@@ -350,19 +354,32 @@ void launch_transform1_scan(int f, const double* A, int64_t n, int64_t p, int64_
   GBM_CUDA(cudaGetLastError());
 }
 
+template <int F, int TJ>
+static void launch_t2_tj(const double* Xi, const double* Xj, int64_t n, int64_t l, int64_t ldx, const double* yc,
+                         double ybar, const double* colvar, double var_thr, int commutative, double* beta,
+                         cudaStream_t stream) {
+  const size_t smem = 2 * sizeof(T2Stage);
+  static bool configured = false;
+  if (!configured) {
+    GBM_CUDA(cudaFuncSetAttribute(transform2_scan_kernel<F, TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = true;
+  }
+  const unsigned nb = static_cast<unsigned>((l + kTile - 1) / kTile);
+  transform2_scan_kernel<F, TJ><<<dim3(nb, nb), 1024 / TJ, smem, stream>>>(Xi, Xj, n, l, ldx, yc, ybar, colvar, var_thr,
+                                                                          commutative, beta);
+}
 template <int F>
 static void launch_t2(const double* Xi, const double* Xj, int64_t n, int64_t l, int64_t ldx, const double* yc,
                       double ybar, const double* colvar, double var_thr, int commutative, double* beta,
                       cudaStream_t stream) {
-  const size_t smem = 2 * sizeof(T2Stage);
-  static bool configured = false;
-  if (!configured) {
-    GBM_CUDA(cudaFuncSetAttribute(transform2_scan_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = true;
-  }
-  const unsigned nb = static_cast<unsigned>((l + kTile - 1) / kTile);
-  transform2_scan_kernel<F><<<dim3(nb, nb), 256, smem, stream>>>(Xi, Xj, n, l, ldx, yc, ybar, colvar, var_thr,
-                                                                 commutative, beta);
+  static const int tj = [] {
+    const char* e = getenv("GBM_T2_TJ");  // measurement switch: register tile 4 x TJ
+    return e && atoi(e) == 4 ? 4 : 2;
+  }();
+  if (tj == 4)
+    launch_t2_tj<F, 4>(Xi, Xj, n, l, ldx, yc, ybar, colvar, var_thr, commutative, beta, stream);
+  else
+    launch_t2_tj<F, 2>(Xi, Xj, n, l, ldx, yc, ybar, colvar, var_thr, commutative, beta, stream);
 }
 
 void launch_transform2_scan(int f, const double* A, int64_t n, int64_t l, int64_t lda, const double* yc, double ybar,

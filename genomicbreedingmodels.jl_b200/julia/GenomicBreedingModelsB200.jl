@@ -68,8 +68,11 @@ function upload(A::Matrix{Float64}, rows::Union{Nothing,Vector{Int64}}, cols::Un
     h = Ref{Ptr{Cvoid}}(C_NULL)
     n0, p0 = size(A)
     if isnothing(rows) && isnothing(cols)
-        check(ccall((:gbm_matrix_upload, LIBGBM), Cint, (Ptr{Float64}, Int64, Int64, Int64, Ref{Ptr{Cvoid}}),
-                    A, n0, p0, n0, h))
+        # the host cores pack dosage data to one byte per genotype on the way (exactness-checked); anything
+        # else arrives as Float64, staged through pinned memory by the same cores (a Julia Array is pageable)
+        packed = Ref{Cint}(0)
+        check(ccall((:gbm_matrix_upload_compact, LIBGBM), Cint,
+                    (Ptr{Float64}, Int64, Int64, Int64, Ref{Ptr{Cvoid}}, Ref{Cint}), A, n0, p0, n0, h, packed))
         return DeviceMatrix(h[], n0, p0)
     end
     n = isnothing(rows) ? n0 : length(rows)

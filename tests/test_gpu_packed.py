@@ -216,3 +216,30 @@ def test_upload_compact(gbm, kind, packs):
         mb.free()
     dm.free()
     m.free()
+
+
+@pytest.mark.parametrize("kind", [synth.KIND_TETRAPLOID, synth.KIND_CONTINUOUS])
+def test_config5_reduced_multi_trait_from_host(gbm, kind):
+    """BASELINE configs[4] reduced (20 traits, host-resident matrix streamed in blocks): gbm_scan_host with
+    T = 20 and one covariate needs two passes of side vectors per block (13 + 7 traits); every trait column
+    must equal the resident multi-trait scan and the oracle's closed form."""
+    n, p, T = 1200, 30_000, 20
+    A = synth.block(8, n, 0, p, kind)
+    rng = np.random.default_rng(8)
+    Y = rng.normal(size=(n, T)) + A[:, :T] * 0.5
+    pc = rng.normal(size=n)
+    host = gbm.scan_host(A, Y, pc[:, None], model=0)
+    dm = gbm.DeviceMatrix.upload(A)
+    res = dm.scan(Y, pc[:, None], model=0)
+    dm.free()
+    keep = res["keep"]
+    assert np.array_equal(keep, host["keep"])
+    for key in ("beta", "se", "stat", "neglog10p"):
+        x, y = res[key][keep], host[key][keep]
+        assert x.shape[1] == T and np.nanmax(np.abs(x - y)) <= 1e-10 * max(1.0, np.nanmax(np.abs(x))), key
+    sub = np.flatnonzero(keep)[:300]
+    for t in (0, 12, 13, 19):  # both passes
+        ys = Y[:, t]
+        cf = go.scan_closed_form(A[:, sub], ys, pc)
+        err = np.abs(host["stat"][sub, t] - cf["stat_ols"]) / np.maximum(np.abs(cf["stat_ols"]), 1e-3 * np.abs(cf["stat_ols"]).max())
+        assert err.max() < 1e-9, (t, err.max())
