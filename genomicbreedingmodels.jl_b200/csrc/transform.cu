@@ -372,9 +372,12 @@ template <int F>
 static void launch_t2(const double* Xi, const double* Xj, int64_t n, int64_t l, int64_t ldx, const double* yc,
                       double ybar, const double* colvar, double var_thr, int commutative, double* beta,
                       cudaStream_t stream) {
+  // measured (n = 10,000, l = 8,192): the 4 x 4 tile (256 threads) is as fast or faster for the short bodies
+  // (mult 189 ms, addnorm 215 vs 218 ms), the 4 x 2 tile (512 threads, 16 warps / SM) for exp (975 vs 1093 ms)
   static const int tj = [] {
-    const char* e = getenv("GBM_T2_TJ");  // measurement switch: register tile 4 x TJ
-    return e && atoi(e) == 4 ? 4 : 2;
+    const char* e = getenv("GBM_T2_TJ");  // measurement switch
+    if (e && (atoi(e) == 2 || atoi(e) == 4)) return atoi(e);
+    return F >= GBM_F2_RAISE ? 2 : 4;
   }();
   if (tj == 4)
     launch_t2_tj<F, 4>(Xi, Xj, n, l, ldx, yc, ybar, colvar, var_thr, commutative, beta, stream);
