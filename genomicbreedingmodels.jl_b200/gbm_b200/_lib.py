@@ -17,6 +17,7 @@ _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(_PKG_DIR, "libgbm_b200.so")
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 
+ABI_VERSION = 2  # GBM_ABI_VERSION of include/gbm_b200.h
 GBM_OK = 0
 GBM_ERR_ARGUMENT = 1
 GBM_ERR_RUNTIME = 2
@@ -124,7 +125,7 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.gbm_abi_version() != 2:
+        if lib.gbm_abi_version() != ABI_VERSION:
             raise CudaError("libgbm_b200.so ABI version mismatch")
         _lib = lib
     return _lib

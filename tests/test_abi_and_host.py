@@ -31,7 +31,9 @@ def test_library_builds_and_exports_every_declared_symbol():
     # the ctypes harness binds exactly the header's symbols
     assert sorted(gbm_b200._lib.SIGNATURES) == decl
     lib = gbm_b200.load()
-    assert lib.gbm_abi_version() == 2
+    from gbm_b200 import _lib as L
+
+    assert lib.gbm_abi_version() == L.ABI_VERSION == 2
 
 
 def test_library_is_sm100a_with_tma_and_dmma():
@@ -304,3 +306,12 @@ int main() {
         T = np.diag(a) + np.diag(b, 1) + np.diag(b, -1)
         assert abs(np.linalg.norm(s) - 1.0) < 1e-12
         assert np.linalg.norm(T @ s - theta * s) <= 1e-13 * scale * np.sqrt(a.size), a.size
+
+
+def test_graft_entry_build_runs_without_a_gpu():
+    """The driver's build check: __graft_entry__.build() compiles (or finds up to date) every CUDA source
+    for sm_100a, loads the library and builds the oracle's C twin."""
+    import importlib
+
+    entry = importlib.import_module("__graft_entry__")
+    entry.build()
