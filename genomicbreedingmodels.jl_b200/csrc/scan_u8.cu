@@ -20,6 +20,8 @@
 //
 // Algorithmic bytes: n per marker.
 #include <math.h>
+
+#include <algorithm>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -363,18 +365,15 @@ void launch_scan_sums_u8(const uint8_t* A8, int64_t n, int64_t p, int64_t ld8, c
 // ------------------------------------------------------------------------------------
 // pack (Float64 -> codes, with the exactness check) and decode (codes -> Float64)
 // ------------------------------------------------------------------------------------
-// One thread per row: 8-byte loads and 1-byte stores, both fully coalesced (a warp reads 256 contiguous
-// bytes and writes 32), four rows in flight per thread.  The earlier layout (one thread = 8 consecutive rows,
+// Persistent CTAs walk the columns; within a column one thread per row: 8-byte loads and 1-byte stores, both
+// fully coalesced (a warp reads 256 contiguous bytes and writes 32), four rows in flight per thread.  The earlier layout (one thread = 8 consecutive rows,
 // one 64-bit store) read with a 64-byte lane stride and reached 2.4 TB/s; this one is HBM-bound.
 __global__ void __launch_bounds__(256)
-    pack_u8_kernel(const double* __restrict__ A, int64_t n, int64_t lda, uint8_t* __restrict__ out, int64_t ld8,
-                   unsigned long long* __restrict__ inexact) {
+    pack_u8_kernel(const double* __restrict__ A, int64_t n, int64_t p, int64_t lda, uint8_t* __restrict__ out,
+                   int64_t ld8, unsigned long long* __restrict__ inexact) {
   __shared__ double lut[241];
   for (int i = threadIdx.x; i < 241; i += blockDim.x) lut[i] = static_cast<double>(i) / kLevels;
   __syncthreads();
-  const int64_t j = blockIdx.y;
-  const double* col = A + j * lda;
-  uint8_t* dst = out + j * ld8;
   unsigned bad = 0;
   auto encode = [&](double a) -> uint8_t {
     const double s = rint(a * kLevels);
@@ -383,29 +382,30 @@ __global__ void __launch_bounds__(256)
     if (!in_range || lut[code] != a) ++bad;
     return static_cast<uint8_t>(code);
   };
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * 256;
-  int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-  for (; i + 3 * stride < n; i += 4 * stride) {
-    const double a0 = col[i], a1 = col[i + stride], a2 = col[i + 2 * stride], a3 = col[i + 3 * stride];
-    dst[i] = encode(a0);
-    dst[i + stride] = encode(a1);
-    dst[i + 2 * stride] = encode(a2);
-    dst[i + 3 * stride] = encode(a3);
+  for (int64_t j = blockIdx.x; j < p; j += gridDim.x) {  // persistent CTAs, one column at a time
+    const double* col = A + j * lda;
+    uint8_t* dst = out + j * ld8;
+    int64_t i = threadIdx.x;
+    for (; i + 3 * 256 < n; i += 4 * 256) {
+      const double a0 = col[i], a1 = col[i + 256], a2 = col[i + 512], a3 = col[i + 768];
+      dst[i] = encode(a0);
+      dst[i + 256] = encode(a1);
+      dst[i + 512] = encode(a2);
+      dst[i + 768] = encode(a3);
+    }
+    for (; i < ld8; i += 256) dst[i] = i < n ? encode(col[i]) : static_cast<uint8_t>(0);
   }
-  for (; i < ld8; i += stride) dst[i] = i < n ? encode(col[i]) : static_cast<uint8_t>(0);
   if (bad) atomicAdd(inexact, static_cast<unsigned long long>(bad));
 }
 
 void launch_pack_u8(const double* A, int64_t n, int64_t p, int64_t lda, uint8_t* out, int64_t ld8,
                     unsigned long long* inexact, cudaStream_t stream) {
   if (n <= 0 || p <= 0) return;
-  unsigned gx = static_cast<unsigned>((ld8 + 1023) / 1024);  // four rows per thread
-  if (gx < 1) gx = 1;
-  if (gx > 8) gx = 8;
-  for (int64_t j0 = 0; j0 < p; j0 += 65535) {
-    const unsigned gy = static_cast<unsigned>(p - j0 < 65535 ? p - j0 : 65535);
-    pack_u8_kernel<<<dim3(gx, gy), 256, 0, stream>>>(A + j0 * lda, n, lda, out + j0 * ld8, ld8, inexact);
-  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p, static_cast<int64_t>(sms) * 8));
+  pack_u8_kernel<<<grid, 256, 0, stream>>>(A, n, p, lda, out, ld8, inexact);
   GBM_CUDA(cudaGetLastError());
 }
 
