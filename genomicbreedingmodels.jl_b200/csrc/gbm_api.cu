@@ -150,16 +150,21 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
 };
 
-// streaming sums over a resident matrix of either storage type
+// streaming sums over a resident matrix of either storage type.  mt: Q is [1 | side vectors] (M + 1 columns)
+// and the FP64 tensor-pipe kernel of scan_mt.cu runs (records of `stride` doubles); otherwise the streaming
+// kernels of scan.cu / scan_u8.cu with their own record stride.
 static void scan_sums_any(const gbm_matrix* m, int64_t j0, int64_t pb, const double* Q, int M, int64_t ldq,
-                          double* rec) {
+                          double* rec, bool mt = false, int mt_stride = 0) {
   State& st = state();
   if (m->dtype == 0) {
-    launch_scan_sums(m->d + j0 * m->lda, m->n, pb, m->lda, Q, M, ldq, M == 0, rec, st.sm_count, st.stream);
+    if (mt)
+      launch_scan_sums_mt(m->d + j0 * m->lda, m->n, pb, m->lda, Q, M, ldq, rec, mt_stride, st.sm_count, st.stream);
+    else
+      launch_scan_sums(m->d + j0 * m->lda, m->n, pb, m->lda, Q, M, ldq, M == 0, rec, st.sm_count, st.stream);
   } else {
-    const int stride = scan_record_stride(M, false);
+    const int stride = mt ? mt_stride : scan_record_stride(M, false);
     const int Mp = stride - 2 - (M == 0 ? 1 : 0);
-    if (Mp <= 2) {
+    if (!mt && Mp <= 2) {
       launch_scan_sums_u8(m->d8 + j0 * m->ld8, m->n, pb, m->ld8, Q, Mp, ldq, rec, st.sm_count, st.stream);
     } else {
       // many side vectors (multi-trait) on packed codes: decode column blocks, Float64 kernel
@@ -170,7 +175,10 @@ static void scan_sums_any(const gbm_matrix* m, int64_t j0, int64_t pb, const dou
       for (int64_t b0 = 0; b0 < pb; b0 += PB) {
         const int64_t pc = std::min(PB, pb - b0);
         launch_decode_u8(m->d8 + (j0 + b0) * m->ld8, m->n, pc, m->ld8, tmp.p, ldt, st.stream);
-        launch_scan_sums(tmp.p, m->n, pc, ldt, Q, M, ldq, false, rec + b0 * stride, st.sm_count, st.stream);
+        if (mt)
+          launch_scan_sums_mt(tmp.p, m->n, pc, ldt, Q, M, ldq, rec + b0 * stride, stride, st.sm_count, st.stream);
+        else
+          launch_scan_sums(tmp.p, m->n, pc, ldt, Q, M, ldq, false, rec + b0 * stride, st.sm_count, st.stream);
       }
     }
   }
@@ -314,43 +322,52 @@ static SideVectors prepare_side_vectors(const double* Y, int64_t n, int64_t T, i
   return sv;
 }
 
-// Device copies of the side vectors, one per pass over the matrix (a pass carries the k
-// covariate vectors plus up to 14 - k traits).
+// Device copies of the side vectors, one per pass over the matrix.  Up to two side vectors (the reference case:
+// PC1 + one trait) use the streaming FMA kernels with Q = [W | R]; more go through the FP64 tensor-pipe kernel
+// (scan_mt.cu) with Q = [1 | W | R], the k covariate vectors plus up to 31 - k traits per pass.
 struct Pass {
   int64_t t0;
   int tcount, M, stride;
+  bool mt;
   DevBuf<double> dQ, dyMy;
-  Pass(int64_t t0_, int tcount_, int M_, int stride_, size_t qcount, cudaStream_t s)
-      : t0(t0_), tcount(tcount_), M(M_), stride(stride_), dQ(qcount, s), dyMy(tcount_ > 0 ? tcount_ : 1, s) {}
+  Pass(int64_t t0_, int tcount_, int M_, int stride_, bool mt_, size_t qcount, cudaStream_t s)
+      : t0(t0_), tcount(tcount_), M(M_), stride(stride_), mt(mt_), dQ(qcount, s), dyMy(tcount_ > 0 ? tcount_ : 1, s) {}
 };
 
 static std::vector<std::unique_ptr<Pass>> build_passes(const SideVectors& sv, int64_t n, int64_t T) {
   State& st = state();
   const int k = sv.k_eff;
-  const int max_m = scan_max_side_vectors();
-  if (k >= max_m) GBM_THROW(GBM_ERR_ARGUMENT, "too many covariates (at most 13)");
+  const bool mt = k + T > 2 && getenv("GBM_SCAN_NO_DMMA") == nullptr;
+  const int max_m = mt ? scan_mt_max_side_vectors() : scan_max_side_vectors();
+  if (k >= max_m) GBM_THROW(GBM_ERR_ARGUMENT, "too many covariates (at most " + std::to_string(max_m - 1) + ")");
   const int t_per_pass = max_m - k;
   const int64_t ldq = round_up(n, 2);
   std::vector<std::unique_ptr<Pass>> passes;
   for (int64_t t0 = 0; t0 < T; t0 += t_per_pass) {
     const int tcount = static_cast<int>(std::min<int64_t>(t_per_pass, T - t0));
     const int M = k + tcount;
-    const int stride = scan_record_stride(M, false);
-    const int Mp = stride - 2;
-    std::unique_ptr<Pass> ps(new Pass(t0, tcount, M, stride, static_cast<size_t>(ldq) * Mp, st.stream));
-    GBM_CUDA(cudaMemsetAsync(ps->dQ.p, 0, sizeof(double) * ldq * Mp, st.stream));
+    const int stride = mt ? 2 + M : scan_record_stride(M, false);
+    const int ncols = mt ? M + 1 : stride - 2;  // columns of the device Q (padded for the FMA kernels)
+    const int first = mt ? 1 : 0;               // [1 | W | R] for the tensor-pipe kernel
+    std::unique_ptr<Pass> ps(new Pass(t0, tcount, M, stride, mt, static_cast<size_t>(ldq) * ncols, st.stream));
+    GBM_CUDA(cudaMemsetAsync(ps->dQ.p, 0, sizeof(double) * ldq * ncols, st.stream));
+    std::vector<double> ones;
+    if (mt) {
+      ones.assign(static_cast<size_t>(n), 1.0);
+      GBM_CUDA(cudaMemcpyAsync(ps->dQ.p, ones.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st.stream));
+    }
     if (k > 0)
-      GBM_CUDA(cudaMemcpy2DAsync(ps->dQ.p, ldq * sizeof(double), sv.W.data(), n * sizeof(double), n * sizeof(double),
-                                 k, cudaMemcpyHostToDevice, st.stream));
-    GBM_CUDA(cudaMemcpy2DAsync(ps->dQ.p + static_cast<size_t>(k) * ldq, ldq * sizeof(double),
+      GBM_CUDA(cudaMemcpy2DAsync(ps->dQ.p + static_cast<size_t>(first) * ldq, ldq * sizeof(double), sv.W.data(),
+                                 n * sizeof(double), n * sizeof(double), k, cudaMemcpyHostToDevice, st.stream));
+    GBM_CUDA(cudaMemcpy2DAsync(ps->dQ.p + static_cast<size_t>(first + k) * ldq, ldq * sizeof(double),
                                sv.R.data() + static_cast<size_t>(t0) * n, n * sizeof(double), n * sizeof(double),
                                tcount, cudaMemcpyHostToDevice, st.stream));
     GBM_CUDA(cudaMemcpyAsync(ps->dyMy.p, sv.yMy.data() + t0, sizeof(double) * tcount, cudaMemcpyHostToDevice,
                              st.stream));
+    // the host vectors are pageable: make sure the copies have drained before they go away
+    GBM_CUDA(cudaStreamSynchronize(st.stream));
     passes.push_back(std::move(ps));
   }
-  // the host vectors are pageable: make sure the copies have drained before sv can go away
-  GBM_CUDA(cudaStreamSynchronize(st.stream));
   return passes;
 }
 
@@ -374,7 +391,7 @@ static void scan_block(const gbm_matrix& mat, int64_t p_blk, const std::vector<s
     DevBuf<double> rec_tmp(own_rec ? static_cast<size_t>(p_blk) * ps->stride : 0, st.stream);
     struct { double* p; } rec{own_rec ? rec_tmp.p : rec_bufs[pi]};
     if (main_span) main_span->start();
-    scan_sums_any(&mat, 0, p_blk, ps->dQ.p, ps->M, ldq, rec.p);
+    scan_sums_any(&mat, 0, p_blk, ps->dQ.p, ps->M, ldq, rec.p, ps->mt, ps->stride);
     if (main_span) main_span->stop();
     FinalizeParams fp;
     fp.n = n;

@@ -20,6 +20,12 @@ int scan_max_side_vectors();
 void launch_scan_sums(const double* A, int64_t n, int64_t p, int64_t lda, const double* Q, int M, int64_t ldq,
                       bool minnz, double* rec, int sm_count, cudaStream_t stream);
 
+// scan_mt.cu: the same sums for up to 31 side vectors in one pass on the FP64 tensor pipe (DMMA).  Qx is
+// n x (M + 1) with the vector of ones in column 0; records are [mean, SS, dot_1 .. dot_M] with pitch rec_stride.
+int scan_mt_max_side_vectors();
+void launch_scan_sums_mt(const double* A, int64_t n, int64_t p, int64_t lda, const double* Qx, int M, int64_t ldq,
+                         double* rec, int rec_stride, int sm_count, cudaStream_t stream);
+
 struct FinalizeParams {
   int64_t n, p;
   int64_t ld_out;      // leading dimension of the p x T outputs

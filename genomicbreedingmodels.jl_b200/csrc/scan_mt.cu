@@ -1,0 +1,213 @@
+// Multi-trait marker scan: the same per-marker sums as scan.cu -- mean, SS and the dots a'q_m against the
+// M = k + T side vectors (covariates + residualised traits; /root/reference/src/gwas.jl:239-249 for every
+// trait of a batch, BASELINE configs[4]) -- for M > 2, where the dots are a skinny GEMM
+//     D (p x M) = X' Q,   X: n x p genotypes, Q: n x M,
+// and belong on the FP64 tensor pipe: at T = 20 the FMA formulation needs 45 flop per 8 bytes and
+// the CUDA-core kernel fell to 1.0 TB/s-equivalent in two passes; DMMA does the M <= 31 dots in ONE pass.
+//
+// Structure = gemm_tn.cu (persistent CTAs, one producer lane issuing TMA boxes into an mbarrier ring, eight
+// mma.sync m8n8k4.f64 warps), specialised: a CTA tile is 128 markers x 8 NT side-vector columns (NT = 1..4),
+// each warp owns 16 markers, a stage is 32 genotype rows (box of 36: the 288-byte pitch is 4 (mod 16)
+// doubles, so the fragment loads are conflict-free without a swizzle).  Column 0 of Q is the vector of ones:
+// with the operand shifted by the marker's first genotype, d = a - a[0], its dot is S1 = sum d; S2 = sum d^2
+// is one DFMA per loaded fragment element.  mean = a[0] + S1/n and SS = S2 - S1^2/n exactly as in scan.cu
+// (a constant marker gives SS = 0 exactly), the other columns are the dots (q_m is orthogonal to 1, so
+// d'q_m = a'q_m).  Records [mean, SS, dot_1 .. dot_M] feed the shared finalisation kernel.
+//
+// Algorithmic bytes: 8 n per marker, read once.  FP64-pipe work per marker: 2 n 8 NT flops of DMMA.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gbm {
+
+namespace {
+
+constexpr int kMtMarkers = 128;   // markers per CTA tile
+constexpr int kMtK = 32;          // genotype rows consumed per stage
+constexpr int kMtKBox = 36;       // rows fetched per stage (pitch = 4 mod 16 doubles)
+constexpr int kMtWarps = 8;       // DMMA warps, 16 markers each
+constexpr int kMtThreads = (kMtWarps + 1) * 32;
+constexpr int kMtABytes = kMtMarkers * kMtKBox * 8;  // 36,864
+
+template <int NT>
+struct MtCfg {
+  static constexpr int Q_BYTES = NT * 8 * kMtKBox * 8;
+  static constexpr int STAGE_BYTES = kMtABytes + Q_BYTES;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 128;
+};
+
+struct MtParams {
+  int64_t n, p;
+  int M;            // side vectors without the ones column
+  int rec_stride;   // doubles per marker record (>= 2 + M)
+  int num_tiles, ksteps;
+  double inv_n;
+  double* rec;
+};
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kMtThreads, 1)
+    scan_sums_mt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmQ,
+                        const MtParams prm) {
+  using Cfg = MtCfg<NT>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kMtWarps);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == kMtWarps) {  // producer
+    if (lane == 0) {
+      prefetch_tensormap(&tmA);
+      prefetch_tensormap(&tmQ);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
+        for (int s = 0; s < prm.ksteps; ++s) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* dst = smem + stage * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(dst, &tmA, s * kMtK, tile * kMtMarkers, &full_bar[stage], kEvictNormal);
+          tma_load_2d(dst + kMtABytes, &tmQ, s * kMtK, 0, &full_bar[stage], kEvictLast);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  const int g = lane >> 2, t = lane & 3;  // fragment coordinates: marker (or side vector) g, row t of the k4 step
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < prm.num_tiles; tile += gridDim.x) {
+    double acc[2][NT][2];
+    double s2[2] = {0.0, 0.0}, shift[2] = {0.0, 0.0};
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+
+    for (int s = 0; s < prm.ksteps; ++s) {
+      mbar_wait(&full_bar[stage], phase);
+      const double* sA = reinterpret_cast<const double*>(smem + stage * Cfg::STAGE_BYTES);
+      const double* sQ = sA + kMtMarkers * kMtKBox;
+      const double* pa = sA + (warp * 16 + g) * kMtKBox + t;
+      const double* pq = sQ + g * kMtKBox + t;
+      if (s == 0) {  // the marker's first genotype (row 0 of the first stage)
+        shift[0] = sA[(warp * 16 + g) * kMtKBox];
+        shift[1] = sA[(warp * 16 + 8 + g) * kMtKBox];
+      }
+      const int64_t row0 = static_cast<int64_t>(s) * kMtK + t;
+      const bool full = static_cast<int64_t>(s + 1) * kMtK <= prm.n;
+#pragma unroll
+      for (int kk = 0; kk < kMtK / 4; ++kk) {
+        double a[2], q[NT];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          a[mt] = pa[mt * 8 * kMtKBox + kk * 4] - shift[mt];
+          if (!full && row0 + kk * 4 >= prm.n) a[mt] = 0.0;  // rows past n are zero-filled by TMA: d must be 0 too
+          s2[mt] = fma(a[mt], a[mt], s2[mt]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) q[nt] = pq[nt * 8 * kMtKBox + kk * 4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], q[nt]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+
+    // epilogue: lane (g, t) holds D[marker g][columns 2t, 2t+1] of every 8 x 8 block; S2 is spread over the
+    // four t lanes of a marker (fixed-order butterfly)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      s2[mt] += __shfl_xor_sync(0xffffffffu, s2[mt], 1);
+      s2[mt] += __shfl_xor_sync(0xffffffffu, s2[mt], 2);
+      const double S1 = __shfl_sync(0xffffffffu, acc[mt][0][0], lane & ~3);  // column 0 (ones) lives in lane t = 0
+      const int64_t marker = static_cast<int64_t>(tile) * kMtMarkers + warp * 16 + mt * 8 + g;
+      if (marker >= prm.p) continue;
+      double* rec = prm.rec + marker * prm.rec_stride;
+      if (t == 0) {
+        rec[0] = shift[mt] + S1 * prm.inv_n;
+        rec[1] = fmax(s2[mt] - S1 * S1 * prm.inv_n, 0.0);
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = nt * 8 + 2 * t + e;  // column of [1 | Q]
+          if (col >= 1 && col <= prm.M) rec[1 + col] = acc[mt][nt][e];
+        }
+    }
+  }
+}
+
+template <int NT>
+void launch_mt(const double* A, int64_t n, int64_t p, int64_t lda, const double* Qx, int M, int64_t ldq, double* rec,
+               int rec_stride, int sm_count, cudaStream_t stream) {
+  using Cfg = MtCfg<NT>;
+  static_assert(Cfg::STAGES >= 3, "ring too shallow");
+  alignas(64) CUtensorMap tmA, tmQ;
+  // tensor maps are declared with exactly n rows and M + 1 columns: TMA zero-fills whatever a box reads beyond
+  make_tensor_map_2d_f64(&tmA, A, static_cast<uint64_t>(n), static_cast<uint64_t>(p), static_cast<uint64_t>(lda),
+                         kMtKBox, kMtMarkers);
+  make_tensor_map_2d_f64(&tmQ, Qx, static_cast<uint64_t>(n), static_cast<uint64_t>(M + 1), static_cast<uint64_t>(ldq),
+                         kMtKBox, NT * 8);
+  MtParams prm;
+  prm.n = n;
+  prm.p = p;
+  prm.M = M;
+  prm.rec_stride = rec_stride;
+  prm.num_tiles = static_cast<int>((p + kMtMarkers - 1) / kMtMarkers);
+  prm.ksteps = static_cast<int>((n + kMtK - 1) / kMtK);
+  prm.inv_n = 1.0 / static_cast<double>(n);
+  prm.rec = rec;
+  auto kern = scan_sums_mt_kernel<NT>;
+  GBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  const int grid = prm.num_tiles < sm_count ? prm.num_tiles : sm_count;
+  kern<<<grid, kMtThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmQ, prm);
+  GBM_CUDA(cudaGetLastError());
+}
+
+}  // namespace
+
+int scan_mt_max_side_vectors() { return 31; }
+
+void launch_scan_sums_mt(const double* A, int64_t n, int64_t p, int64_t lda, const double* Qx, int M, int64_t ldq,
+                         double* rec, int rec_stride, int sm_count, cudaStream_t stream) {
+  if (p <= 0 || n <= 0) return;
+  if (M < 1 || M > 31 || rec_stride < 2 + M) GBM_THROW(1, "multi-trait scan: 1..31 side vectors per pass");
+  const int nt = (M + 1 + 7) / 8;
+  switch (nt) {
+    case 1: launch_mt<1>(A, n, p, lda, Qx, M, ldq, rec, rec_stride, sm_count, stream); break;
+    case 2: launch_mt<2>(A, n, p, lda, Qx, M, ldq, rec, rec_stride, sm_count, stream); break;
+    case 3: launch_mt<3>(A, n, p, lda, Qx, M, ldq, rec, rec_stride, sm_count, stream); break;
+    default: launch_mt<4>(A, n, p, lda, Qx, M, ldq, rec, rec_stride, sm_count, stream); break;
+  }
+}
+
+}  // namespace gbm

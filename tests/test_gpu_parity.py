@@ -544,3 +544,60 @@ def test_full_size_config3_sampled_parity(gbm):
     got = K.index_select(0, rt).index_select(1, rt).cpu().numpy()
     assert np.max(np.abs(got - want)) < 1e-11 * np.abs(want).max()
     dm.free()
+
+
+@pytest.mark.parametrize("n,p,T,k", [(601, 300, 2, 1), (1027, 129, 7, 0), (32, 128, 30, 1), (35, 257, 45, 2), (4099, 77, 20, 1)])
+def test_multi_trait_tensor_pipe_kernel_edges(gbm, n, p, T, k, monkeypatch):
+    """More than two side vectors run on the FP64 tensor pipe (csrc/scan_mt.cu): ragged n (not a multiple of
+    the 32-row stage or the 4-row MMA step), ragged p (not a multiple of the 128-marker tile), 31 side vectors
+    in one pass and more than that in two, constant markers (SS exactly 0, filtered), and agreement with the
+    FMA kernels (GBM_SCAN_NO_DMMA) where those can run."""
+    A = synth.block(19, n, 0, p, synth.KIND_CONTINUOUS)
+    A[:, 5] = 0.25
+    A[:, p - 1] = 1.0 / 3.0  # constant, not dyadic
+    rng = np.random.default_rng(n + T)
+    Y = rng.normal(size=(n, T)) + 3.0
+    C = rng.normal(size=(n, k)) if k else None
+    dm = gbm.DeviceMatrix.upload(A)
+    res = dm.scan(Y, C, model=0)
+    mu, v = go.column_std(A)
+    keep = v > go.EPS
+    assert not keep[5] and not keep[p - 1]
+    assert np.array_equal(res["keep"], keep)
+    assert res["sd"][5] == 0.0 and res["sd"][p - 1] == 0.0
+    np.testing.assert_allclose(res["mean"], mu, rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(res["sd"][keep], v[keep], rtol=1e-11)
+    Q = np.hstack([np.ones((n, 1))] + ([C] if k else []))
+    Qo, _ = np.linalg.qr(Q)
+    d = A[:, keep] - mu[keep]
+    Md = d - Qo @ (Qo.T @ d)
+    xMx = np.einsum("ij,ij->j", Md, Md)
+    for t in range(T):
+        My = Y[:, t] - Qo @ (Qo.T @ Y[:, t])
+        s = (My @ Md) / np.sqrt(xMx)
+        assert rel_err(res["stat"][keep, t], s) < RTOL, t
+    if k + T <= 14:
+        monkeypatch.setenv("GBM_SCAN_NO_DMMA", "1")
+        ref = dm.scan(Y, C, model=0)
+        monkeypatch.delenv("GBM_SCAN_NO_DMMA")
+        assert np.array_equal(ref["keep"], res["keep"])
+        assert rel_err(res["stat"][keep], ref["stat"][keep]) < 1e-11
+    pk = None
+    dm.free()
+
+
+def test_multi_trait_on_packed_codes(gbm):
+    n, p, T = 900, 2100, 20
+    A = synth.block(4, n, 0, p, synth.KIND_TETRAPLOID)
+    rng = np.random.default_rng(2)
+    Y = rng.normal(size=(n, T))
+    pc = rng.normal(size=(n, 1))
+    dm = gbm.DeviceMatrix.upload(A)
+    pk = dm.pack()
+    a = dm.scan(Y, pc, model=1)
+    b = pk.scan(Y, pc, model=1)
+    assert np.array_equal(a["keep"], b["keep"])
+    for key in ("beta", "se", "stat", "neglog10p", "mean", "sd"):
+        assert np.array_equal(a[key], b[key], equal_nan=True), key  # decoded codes are the same doubles
+    dm.free()
+    pk.free()
