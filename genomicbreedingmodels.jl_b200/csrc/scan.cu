@@ -285,57 +285,60 @@ void launch_scan_sums(const double* A, int64_t n, int64_t p, int64_t lda, const 
 }
 
 // ------------------------------------------------------------------------------------
-// finalisation kernels (one thread per marker): statistics + log-space p-values
+// finalisation kernels: statistics + log-space p-values
 // ------------------------------------------------------------------------------------
 constexpr double kEps = 2.220446049250313e-16;
 
+// one thread per (marker, trait): blockIdx.y is the trait, so a batch of traits fills the machine instead of
+// looping serially in each marker's thread (the t-distribution tail is a continued fraction per value)
 __global__ void __launch_bounds__(256) scan_finalize_kernel(const FinalizeParams prm) {
   const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (j >= prm.p) return;
+  const int t = blockIdx.y;
   const double* rec = prm.rec + j * prm.rec_stride;
   const double mean = rec[0], ss = rec[1];
   const double sd = sqrt(ss / static_cast<double>(prm.n - 1));
   // fixed-locus filter: v > eps && finite   (gwas.jl:113)
   const bool keep = (sd > kEps) && isfinite(sd);
-  if (prm.mean) prm.mean[j] = mean;
-  if (prm.sd) prm.sd[j] = sd;
-  if (prm.keep) prm.keep[j] = keep ? 1 : 0;
+  if (t == 0) {
+    if (prm.mean) prm.mean[j] = mean;
+    if (prm.sd) prm.sd[j] = sd;
+    if (prm.keep) prm.keep[j] = keep ? 1 : 0;
+  }
   double uu = 0.0;
   for (int i = 0; i < prm.k; ++i) uu = fma(rec[2 + i], rec[2 + i], uu);
   const double xMx = ss - uu;  // x'Mx on the raw scale, M = projector off [1, C]
   const bool ok = keep && (xMx > 1e-12 * ss);
   const double dfres = static_cast<double>(prm.n - prm.k - 2);
-  for (int t = 0; t < prm.T; ++t) {
-    const int64_t o = static_cast<int64_t>(t) * prm.ld_out + j;
-    double beta = NAN, se = NAN, stat = NAN, nlp = NAN;
-    if (ok) {
-      const double xMy = rec[2 + prm.k + t];
-      const double s = xMy / sqrt(xMx);   // gwasols statistic (gwas.jl:245), SURVEY App. A.2
-      beta = xMy * sd / xMx;              // coefficient of the standardised column
-      const double se_ols = sd / sqrt(xMx);
-      if (prm.model == 0) {
-        stat = s;
-        se = se_ols;
-        nlp = -log_sf_t(s, static_cast<double>(prm.n - 1)) * 0.4342944819032518;
-      } else {
-        const double rss = prm.yMy[t] - s * s;
-        const double sigma2 = rss / dfres;  // REML sigma^2 (1 + theta^2), SURVEY App. A.3
-        stat = s / sqrt(sigma2);
-        se = se_ols * sqrt(sigma2);
-        nlp = -log_sf_normal(stat) * 0.4342944819032518;
-      }
-      if (prm.flags & 1) nlp -= 0.3010299956639812;  // two-sided
+  const int64_t o = static_cast<int64_t>(t) * prm.ld_out + j;
+  double beta = NAN, se = NAN, stat = NAN, nlp = NAN;
+  if (ok) {
+    const double xMy = rec[2 + prm.k + t];
+    const double s = xMy / sqrt(xMx);   // gwasols statistic (gwas.jl:245), SURVEY App. A.2
+    beta = xMy * sd / xMx;              // coefficient of the standardised column
+    const double se_ols = sd / sqrt(xMx);
+    if (prm.model == 0) {
+      stat = s;
+      se = se_ols;
+      nlp = -log_sf_t(s, static_cast<double>(prm.n - 1)) * 0.4342944819032518;
+    } else {
+      const double rss = prm.yMy[t] - s * s;
+      const double sigma2 = rss / dfres;  // REML sigma^2 (1 + theta^2), SURVEY App. A.3
+      stat = s / sqrt(sigma2);
+      se = se_ols * sqrt(sigma2);
+      nlp = -log_sf_normal(stat) * 0.4342944819032518;
     }
-    if (prm.beta) prm.beta[o] = beta;
-    if (prm.se) prm.se[o] = se;
-    if (prm.stat) prm.stat[o] = stat;
-    if (prm.nlp) prm.nlp[o] = nlp;
+    if (prm.flags & 1) nlp -= 0.3010299956639812;  // two-sided
   }
+  if (prm.beta) prm.beta[o] = beta;
+  if (prm.se) prm.se[o] = se;
+  if (prm.stat) prm.stat[o] = stat;
+  if (prm.nlp) prm.nlp[o] = nlp;
 }
 
 void launch_scan_finalize(const FinalizeParams& prm, cudaStream_t stream) {
-  if (prm.p <= 0) return;
-  const unsigned grid = static_cast<unsigned>((prm.p + 255) / 256);
+  if (prm.p <= 0 || prm.T <= 0) return;
+  const dim3 grid(static_cast<unsigned>((prm.p + 255) / 256), static_cast<unsigned>(prm.T));
   scan_finalize_kernel<<<grid, 256, 0, stream>>>(prm);
   GBM_CUDA(cudaGetLastError());
 }

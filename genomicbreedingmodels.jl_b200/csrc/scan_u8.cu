@@ -409,28 +409,28 @@ void launch_pack_u8(const double* A, int64_t n, int64_t p, int64_t lda, uint8_t*
   GBM_CUDA(cudaGetLastError());
 }
 
+// persistent CTAs walk the columns (one tiny CTA per column slice spent its time on launch overhead)
 __global__ void __launch_bounds__(256)
-    decode_u8_kernel(const uint8_t* __restrict__ A8, int64_t n, int64_t ld8, double* __restrict__ out, int64_t ldo) {
+    decode_u8_kernel(const uint8_t* __restrict__ A8, int64_t n, int64_t p, int64_t ld8, double* __restrict__ out,
+                     int64_t ldo) {
   __shared__ double lut[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = static_cast<double>(i) / kLevels;
   __syncthreads();
-  const int64_t j = blockIdx.y;
-  const uint8_t* col = A8 + j * ld8;
-  double* dst = out + j * ldo;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < ldo;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    dst[i] = i < n ? lut[col[i]] : 0.0;
+  for (int64_t j = blockIdx.x; j < p; j += gridDim.x) {
+    const uint8_t* col = A8 + j * ld8;
+    double* dst = out + j * ldo;
+    for (int64_t i = threadIdx.x; i < ldo; i += 256) dst[i] = i < n ? lut[col[i]] : 0.0;
+  }
 }
 
 void launch_decode_u8(const uint8_t* A8, int64_t n, int64_t p, int64_t ld8, double* out, int64_t ldo,
                       cudaStream_t stream) {
   if (n <= 0 || p <= 0) return;
-  unsigned gx = static_cast<unsigned>((ldo + 255) / 256);
-  if (gx > 16) gx = 16;
-  for (int64_t j0 = 0; j0 < p; j0 += 65535) {
-    const unsigned gy = static_cast<unsigned>(p - j0 < 65535 ? p - j0 : 65535);
-    decode_u8_kernel<<<dim3(gx, gy), 256, 0, stream>>>(A8 + j0 * ld8, n, ld8, out + j0 * ldo, ldo);
-  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p, static_cast<int64_t>(sms) * 8));
+  decode_u8_kernel<<<grid, 256, 0, stream>>>(A8, n, p, ld8, out, ldo);
   GBM_CUDA(cudaGetLastError());
 }
 
