@@ -48,11 +48,23 @@ __host__ __device__ inline double lgamma_half_diff(double a) {
   return 0.5 * log(a) + r * (-0.125 + r2 * (1.0 / 192.0 + r2 * (-1.0 / 640.0 + r2 * (17.0 / 14336.0))));
 }
 
+__host__ __device__ inline double log_sf_normal(double z);
+
 // ln P(T_nu > t) for t >= 0.
 __host__ __device__ inline double log_sf_t(double t, double nu) {
   if (!(t == t)) return t;  // NaN
   t = fabs(t);
   if (isinf(t)) return -INFINITY;
+  if (nu >= 200.0 && t <= 8.0) {
+    // Hill (1970, CACM Algorithm 395): the normal deviate z with P(Z > z) = P(T_nu > t), an expansion in
+    // 1/(nu - 1/2) of w = (nu - 1/2) ln(1 + t^2/nu).  In this region its error in -log10 p is below 3e-12
+    // (checked against the continued fraction for nu = 200 .. 1e6), and it replaces the slowest stretch of the
+    // continued fraction (up to 53 iterations around |t| = 1.75, which every warp of a marker batch pays).
+    const double a = nu - 0.5, b = 48.0 * a * a;
+    const double y = a * log1p(t * t / nu);
+    const double z = (((((-0.4 * y - 3.3) * y - 24.0) * y - 85.5) / (0.8 * y * y + 100.0 + b) + y + 3.0) / b + 1.0) * sqrt(y);
+    return log_sf_normal(z);
+  }
   const double a = 0.5 * nu, b = 0.5;
   const double t2 = t * t;
   const double omx = t2 / (nu + t2);  // 1 - x, x = nu/(nu+t^2)

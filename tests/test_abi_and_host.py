@@ -161,8 +161,10 @@ int main(int argc, char** argv) {
         open(cu, "w").write(src)
         exe = os.path.join(td, "pv")
         subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-ccbin", "/usr/bin/g++", "-O2", "-I", csrc, "-o", exe, cu])
-        t = [0.0, 0.1, 0.5, 1.0, 1.7, 1.75, 2.0, 3.0, 5.0, 8.3, 12.0, 19.9, 20.1, 37.0, 40.0, 100.0, 300.0]
-        for df in (1.0, 4.0, 99.0, 299.0, 9999.0, 19999.0):
+        # includes both sides of the switch to Hill's expansion (df >= 200 and |t| <= 8)
+        t = [0.0, 0.1, 0.5, 1.0, 1.7, 1.75, 2.0, 3.0, 5.0, 6.5, 7.99, 8.0, 8.01, 8.3, 12.0, 19.9, 20.1, 37.0, 40.0,
+             100.0, 300.0]
+        for df in (1.0, 4.0, 99.0, 199.0, 200.0, 299.0, 9999.0, 19999.0, 1e6):
             out = subprocess.run([exe, repr(df)] + [repr(x) for x in t], capture_output=True, text=True, check=True)
             got = np.array([[float(v) for v in line.split()] for line in out.stdout.strip().splitlines()])
             want_t = go.neglog10_sf_t(t, df)
