@@ -29,11 +29,16 @@ constexpr int kMtWarps = 8;       // DMMA warps, 16 markers each
 constexpr int kMtThreads = (kMtWarps + 1) * 32;
 constexpr int kMtABytes = kMtMarkers * kMtKBox * 8;  // 36,864
 
+// CPS = CTAs per SM.  Measured (n = 10,000, p = 400,000): with 8 or 16 side-vector columns one CTA with a deep
+// ring is HBM-bound (4.65 / 5.09 ms against 4.82 / 5.30 ms for two CTAs); with 24 or 32 columns the kernel is
+// DMMA-bound and two CTAs (4 warps per scheduler, two stages each) hide more latency (7.00 against 7.43 ms).
 template <int NT>
 struct MtCfg {
+  static constexpr int CPS = NT >= 3 ? 2 : 1;
+  static constexpr int kMtSmemBudget = (CPS == 1 ? 200 : 104) * 1024;
   static constexpr int Q_BYTES = NT * 8 * kMtKBox * 8;
   static constexpr int STAGE_BYTES = kMtABytes + Q_BYTES;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = (kMtSmemBudget / STAGE_BYTES) > 6 ? 6 : (kMtSmemBudget / STAGE_BYTES);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 128;
 };
 
@@ -53,7 +58,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 template <int NT>
-__global__ void __launch_bounds__(kMtThreads, 1)
+__global__ void __launch_bounds__(kMtThreads, MtCfg<NT>::CPS)
     scan_sums_mt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmQ,
                         const MtParams prm) {
   using Cfg = MtCfg<NT>;
@@ -170,7 +175,7 @@ template <int NT>
 void launch_mt(const double* A, int64_t n, int64_t p, int64_t lda, const double* Qx, int M, int64_t ldq, double* rec,
                int rec_stride, int sm_count, cudaStream_t stream) {
   using Cfg = MtCfg<NT>;
-  static_assert(Cfg::STAGES >= 3, "ring too shallow");
+  static_assert(Cfg::STAGES >= 2, "ring too shallow");
   alignas(64) CUtensorMap tmA, tmQ;
   // tensor maps are declared with exactly n rows and M + 1 columns: TMA zero-fills whatever a box reads beyond
   make_tensor_map_2d_f64(&tmA, A, static_cast<uint64_t>(n), static_cast<uint64_t>(p), static_cast<uint64_t>(lda),
@@ -188,7 +193,8 @@ void launch_mt(const double* A, int64_t n, int64_t p, int64_t lda, const double*
   prm.rec = rec;
   auto kern = scan_sums_mt_kernel<NT>;
   GBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  const int grid = prm.num_tiles < sm_count ? prm.num_tiles : sm_count;
+  const int max_grid = sm_count * Cfg::CPS;
+  const int grid = prm.num_tiles < max_grid ? prm.num_tiles : max_grid;
   kern<<<grid, kMtThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmQ, prm);
   GBM_CUDA(cudaGetLastError());
 }
