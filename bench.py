@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-packed", action="store_true")
     ap.add_argument("--cpu-markers", type=int, default=0, help="markers in the CPU sample (0: sized for ~10-20 s)")
+    ap.add_argument("--no-multitrait", action="store_true", help="skip the 20-trait batch on the resident shard")
     ap.add_argument("--no-transform", action="store_true", help="skip the pairwise transformation screen (SURVEY 8f-4)")
     ap.add_argument("--transform-l", type=int, default=8192, help="loci in the pairwise screen (l^2 regressions)")
     ap.add_argument("--pipeline", action="store_true", help="also time the whole gwaslmm pipeline (GRM + PC1) once")
@@ -358,6 +359,31 @@ def main():
                               "note": "not the graded Float64 path: algorithmic bytes are n per marker here"}
             pplan.free()
             pk.free()
+
+    # ---- multi-trait batch (BASELINE configs[4] shape: 20 traits, one covariate) on the resident shard:
+    #      21 side vectors in one pass on the FP64 tensor pipe (csrc/scan_mt.cu) ----
+    if rank == 0 and not args.no_multitrait:
+        T = 20
+        Ymt = np.asfortranarray(np.random.default_rng(7).normal(size=(n, T)))
+        mplan = gbm_b200.ScanPlan(dm, Ymt, C, model=_lib.MODEL_OLS)
+        mstat = torch.empty(p_loc * T, dtype=torch.float64, device="cuda")
+        for _ in range(2):
+            mplan.run(stat=mstat)
+        mk, mm = [], []
+        for _ in range(3):
+            tm = mplan.run(stat=mstat)
+            mk.append(tm["kernel_ms"])
+            mm.append(tm["main_ms"])
+        mplan.free()
+        del mstat
+        ms, main = float(np.median(mk)), float(np.median(mm))
+        nt = (T + 1 + 1 + 7) // 8  # [1 | PC1 | 20 traits] in 8-column MMA blocks
+        line["multi_trait"] = {
+            "workload": f"gwasols batch of {T} traits + 1 covariate on this rank's {p_loc} markers (n={n})",
+            "kernel_ms": ms, "sums_kernel_ms": main, "marker_trait_tests_per_s": p_loc * T / (ms * 1e-3),
+            "markers_per_s": p_loc / (ms * 1e-3), "hbm_GBps": 8.0 * n * p_loc / (main * 1e-3) / 1e9,
+            "dmma_tflops": 2.0 * n * p_loc * 8 * nt / (main * 1e-3) / 1e12,
+            "note": "one pass over the genotypes; FP64 tensor pipe (DMMA m8n8k4) for the 22 dots per marker"}
 
     if not args.no_e2e:
         pe = min(args.e2e_markers, p_loc)
