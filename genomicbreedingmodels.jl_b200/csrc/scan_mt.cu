@@ -15,6 +15,8 @@
 // d'q_m = a'q_m).  Records [mean, SS, dot_1 .. dot_M] feed the shared finalisation kernel.
 //
 // Algorithmic bytes: 8 n per marker, read once.  FP64-pipe work per marker: 2 n 8 NT flops of DMMA.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -22,23 +24,20 @@ namespace gbm {
 
 namespace {
 
-constexpr int kMtMarkers = 128;   // markers per CTA tile
-constexpr int kMtK = 32;          // genotype rows consumed per stage
-constexpr int kMtKBox = 36;       // rows fetched per stage (pitch = 4 mod 16 doubles)
-constexpr int kMtWarps = 8;       // DMMA warps, 16 markers each
-constexpr int kMtThreads = (kMtWarps + 1) * 32;
-constexpr int kMtABytes = kMtMarkers * kMtKBox * 8;  // 36,864
-
-// CPS = CTAs per SM.  Measured (n = 10,000, p = 400,000): with 8 or 16 side-vector columns one CTA with a deep
-// ring is HBM-bound (4.65 / 5.09 ms against 4.82 / 5.30 ms for two CTAs); with 24 or 32 columns the kernel is
-// DMMA-bound and two CTAs (4 warps per scheduler, two stages each) hide more latency (7.00 against 7.43 ms).
-template <int NT>
+// Two geometries (chosen per NT by measurement):
+//  V = 0: 128 markers x 32 rows per stage (36-row box), 8 DMMA warps, deep ring in one CTA per SM -- HBM-bound cases
+//  V = 1: 256 markers x 16 rows per stage (20-row box), 16 DMMA warps (4 per scheduler), 4 stages -- DMMA-bound cases
+template <int NT, int V>
 struct MtCfg {
-  static constexpr int CPS = NT >= 3 ? 2 : 1;
-  static constexpr int kMtSmemBudget = (CPS == 1 ? 200 : 104) * 1024;
-  static constexpr int Q_BYTES = NT * 8 * kMtKBox * 8;
-  static constexpr int STAGE_BYTES = kMtABytes + Q_BYTES;
-  static constexpr int STAGES = (kMtSmemBudget / STAGE_BYTES) > 6 ? 6 : (kMtSmemBudget / STAGE_BYTES);
+  static constexpr int MARKERS = V == 0 ? 128 : 256;  // markers per CTA tile, 16 per warp
+  static constexpr int K = V == 0 ? 32 : 16;          // genotype rows consumed per stage
+  static constexpr int KBOX = K + 4;                  // rows fetched per stage (pitch = 4 mod 16 doubles)
+  static constexpr int WARPS = MARKERS / 16;          // DMMA warps
+  static constexpr int THREADS = (WARPS + 1) * 32;
+  static constexpr int A_BYTES = MARKERS * KBOX * 8;
+  static constexpr int Q_BYTES = NT * 8 * KBOX * 8;
+  static constexpr int STAGE_BYTES = A_BYTES + Q_BYTES;
+  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 128;
 };
 
@@ -57,12 +56,14 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
       : "d"(a), "d"(b));
 }
 
-template <int NT>
-__global__ void __launch_bounds__(kMtThreads, MtCfg<NT>::CPS)
+template <int NT, int V>
+__global__ void __launch_bounds__(MtCfg<NT, V>::THREADS, 1)
     scan_sums_mt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmQ,
                         const MtParams prm) {
-  using Cfg = MtCfg<NT>;
+  using Cfg = MtCfg<NT, V>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int kMtMarkers = Cfg::MARKERS, kMtK = Cfg::K, kMtKBox = Cfg::KBOX, kMtWarps = Cfg::WARPS;
+  constexpr int kMtABytes = Cfg::A_BYTES;
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -171,32 +172,40 @@ __global__ void __launch_bounds__(kMtThreads, MtCfg<NT>::CPS)
   }
 }
 
-template <int NT>
+template <int NT, int V>
 void launch_mt(const double* A, int64_t n, int64_t p, int64_t lda, const double* Qx, int M, int64_t ldq, double* rec,
                int rec_stride, int sm_count, cudaStream_t stream) {
-  using Cfg = MtCfg<NT>;
-  static_assert(Cfg::STAGES >= 2, "ring too shallow");
+  using Cfg = MtCfg<NT, V>;
+  static_assert(Cfg::STAGES >= 3, "ring too shallow");
   alignas(64) CUtensorMap tmA, tmQ;
   // tensor maps are declared with exactly n rows and M + 1 columns: TMA zero-fills whatever a box reads beyond
   make_tensor_map_2d_f64(&tmA, A, static_cast<uint64_t>(n), static_cast<uint64_t>(p), static_cast<uint64_t>(lda),
-                         kMtKBox, kMtMarkers);
+                         Cfg::KBOX, Cfg::MARKERS);
   make_tensor_map_2d_f64(&tmQ, Qx, static_cast<uint64_t>(n), static_cast<uint64_t>(M + 1), static_cast<uint64_t>(ldq),
-                         kMtKBox, NT * 8);
+                         Cfg::KBOX, NT * 8);
   MtParams prm;
   prm.n = n;
   prm.p = p;
   prm.M = M;
   prm.rec_stride = rec_stride;
-  prm.num_tiles = static_cast<int>((p + kMtMarkers - 1) / kMtMarkers);
-  prm.ksteps = static_cast<int>((n + kMtK - 1) / kMtK);
+  prm.num_tiles = static_cast<int>((p + Cfg::MARKERS - 1) / Cfg::MARKERS);
+  prm.ksteps = static_cast<int>((n + Cfg::K - 1) / Cfg::K);
   prm.inv_n = 1.0 / static_cast<double>(n);
   prm.rec = rec;
-  auto kern = scan_sums_mt_kernel<NT>;
+  auto kern = scan_sums_mt_kernel<NT, V>;
   GBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-  const int max_grid = sm_count * Cfg::CPS;
-  const int grid = prm.num_tiles < max_grid ? prm.num_tiles : max_grid;
-  kern<<<grid, kMtThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmQ, prm);
+  const int grid = prm.num_tiles < sm_count ? prm.num_tiles : sm_count;
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmQ, prm);
   GBM_CUDA(cudaGetLastError());
+}
+
+static int mt_variant(int nt) {
+  static const int forced = [] {
+    const char* e = getenv("GBM_MT_VARIANT");  // measurement switch
+    return e ? atoi(e) : -1;
+  }();
+  if (forced == 0 || forced == 1) return forced;
+  return nt >= 3 ? 1 : 0;
 }
 
 }  // namespace
@@ -208,12 +217,21 @@ void launch_scan_sums_mt(const double* A, int64_t n, int64_t p, int64_t lda, con
   if (p <= 0 || n <= 0) return;
   if (M < 1 || M > 31 || rec_stride < 2 + M) GBM_THROW(1, "multi-trait scan: 1..31 side vectors per pass");
   const int nt = (M + 1 + 7) / 8;
+  const int v = mt_variant(nt);
+#define GBM_MT_CASE(NT_)                                                                                   \
+  case NT_:                                                                                                \
+    if (v == 0) launch_mt<NT_, 0>(A, n, p, lda, Qx, M, ldq, rec, rec_stride, sm_count, stream);            \
+    else launch_mt<NT_, 1>(A, n, p, lda, Qx, M, ldq, rec, rec_stride, sm_count, stream);                   \
+    break;
   switch (nt) {
-    case 1: launch_mt<1>(A, n, p, lda, Qx, M, ldq, rec, rec_stride, sm_count, stream); break;
-    case 2: launch_mt<2>(A, n, p, lda, Qx, M, ldq, rec, rec_stride, sm_count, stream); break;
-    case 3: launch_mt<3>(A, n, p, lda, Qx, M, ldq, rec, rec_stride, sm_count, stream); break;
-    default: launch_mt<4>(A, n, p, lda, Qx, M, ldq, rec, rec_stride, sm_count, stream); break;
+    GBM_MT_CASE(1)
+    GBM_MT_CASE(2)
+    GBM_MT_CASE(3)
+    default:
+      if (v == 0) launch_mt<4, 0>(A, n, p, lda, Qx, M, ldq, rec, rec_stride, sm_count, stream);
+      else launch_mt<4, 1>(A, n, p, lda, Qx, M, ldq, rec, rec_stride, sm_count, stream);
   }
+#undef GBM_MT_CASE
 }
 
 }  // namespace gbm
