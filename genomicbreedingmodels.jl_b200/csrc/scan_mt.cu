@@ -205,7 +205,8 @@ static int mt_variant(int nt) {
     return e ? atoi(e) : -1;
   }();
   if (forced == 0 || forced == 1) return forced;
-  return nt >= 3 ? 1 : 0;
+  // measured (n = 10,000, p = 400,000): T = 5: 4.64 (V0) / 4.70 ms (V1); T = 13: 5.10 / 5.00; T = 20: 7.43 / 6.76
+  return nt >= 2 ? 1 : 0;
 }
 
 }  // namespace
