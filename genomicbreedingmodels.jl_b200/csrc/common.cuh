@@ -68,6 +68,9 @@ void make_tensor_map_2d_f64(CUtensorMap* map, const double* base, uint64_t rows,
 // SWIZZLE_128B operand layout of tcgen05.mma for 8-bit types
 void make_tensor_map_2d_u8_sw128(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_bytes,
                                  uint32_t box_rows, uint32_t box_cols);
+// byte matrix, no swizzle: box_rows bytes (a multiple of 16) x box_cols columns
+void make_tensor_map_2d_u8(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_bytes,
+                           uint32_t box_rows, uint32_t box_cols);
 // byte matrix viewed as uint64 words: rows64 words per column, column pitch ld_bytes (multiple of 16)
 void make_tensor_map_2d_u64(CUtensorMap* map, const void* base, uint64_t rows64, uint64_t cols, uint64_t ld_bytes,
                             uint32_t box_rows64, uint32_t box_cols);

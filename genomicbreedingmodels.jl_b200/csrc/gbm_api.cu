@@ -87,6 +87,20 @@ void make_tensor_map_2d_u64(CUtensorMap* map, const void* base, uint64_t rows64,
   if (r != CUDA_SUCCESS) GBM_THROW(GBM_ERR_CUDA, "cuTensorMapEncodeTiled (u64) failed with code " + std::to_string((int)r));
 }
 
+void make_tensor_map_2d_u8(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_bytes,
+                           uint32_t box_rows, uint32_t box_cols) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (ld_bytes & 15u) != 0 || (box_rows & 15u) != 0)
+    GBM_THROW(GBM_ERR_ARGUMENT, "packed matrix must be 16-byte aligned with a pitch that is a multiple of 16");
+  cuuint64_t gdim[2] = {rows, cols};
+  cuuint64_t gstride[1] = {ld_bytes};
+  cuuint32_t box[2] = {box_rows, box_cols};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_tiled()(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) GBM_THROW(GBM_ERR_CUDA, "cuTensorMapEncodeTiled (u8) failed with code " + std::to_string((int)r));
+}
+
 void make_tensor_map_2d_u8_sw128(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_bytes,
                                  uint32_t box_rows, uint32_t box_cols) {
   if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (ld_bytes & 15u) != 0)
@@ -166,6 +180,8 @@ static void scan_sums_any(const gbm_matrix* m, int64_t j0, int64_t pb, const dou
     const int Mp = stride - 2 - (M == 0 ? 1 : 0);
     if (!mt && Mp <= 2) {
       launch_scan_sums_u8(m->d8 + j0 * m->ld8, m->n, pb, m->ld8, Q, Mp, ldq, rec, st.sm_count, st.stream);
+    } else if (mt) {
+      launch_scan_sums_mt_u8(m->d8 + j0 * m->ld8, m->n, pb, m->ld8, Q, M, ldq, rec, stride, st.sm_count, st.stream);
     } else {
       // many side vectors (multi-trait) on packed codes: decode column blocks, Float64 kernel
       const int64_t ldt = round_up(m->n, 16);

@@ -26,6 +26,9 @@ int scan_mt_max_side_vectors();
 void launch_scan_sums_mt(const double* A, int64_t n, int64_t p, int64_t lda, const double* Qx, int M, int64_t ldq,
                          double* rec, int rec_stride, int sm_count, cudaStream_t stream);
 
+void launch_scan_sums_mt_u8(const uint8_t* A8, int64_t n, int64_t p, int64_t ld8, const double* Qx, int M, int64_t ldq,
+                            double* rec, int rec_stride, int sm_count, cudaStream_t stream);
+
 struct FinalizeParams {
   int64_t n, p;
   int64_t ld_out;      // leading dimension of the p x T outputs

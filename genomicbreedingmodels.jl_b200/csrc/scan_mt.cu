@@ -14,7 +14,9 @@
 // (a constant marker gives SS = 0 exactly), the other columns are the dots (q_m is orthogonal to 1, so
 // d'q_m = a'q_m).  Records [mean, SS, dot_1 .. dot_M] feed the shared finalisation kernel.
 //
-// Algorithmic bytes: 8 n per marker, read once.  FP64-pipe work per marker: 2 n 8 NT flops of DMMA.
+// One-byte dosage codes (scan_u8.cu's storage) run the same kernel natively (geometry V = 2 below).
+//
+// Algorithmic bytes: 8 n per marker (n for codes), read once.  FP64-pipe work per marker: 2 n 8 NT flops of DMMA.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -27,14 +29,20 @@ namespace {
 // Two geometries (chosen per NT by measurement):
 //  V = 0: 128 markers x 32 rows per stage (36-row box), 8 DMMA warps, deep ring in one CTA per SM -- HBM-bound cases
 //  V = 1: 256 markers x 16 rows per stage (20-row box), 16 DMMA warps (4 per scheduler), 4 stages -- DMMA-bound cases
+//  V = 2: one-byte dosage codes (a = code / 240): 256 markers x 32 rows per stage, the code tile is a 48-byte box per
+//         marker (32 used; the 12-word pitch puts the 8 markers of a fragment in 8 different banks), codes become
+//         doubles by the 2^52 trick fused with the shift (one DADD, as in the Float64 variants), sums stay in code
+//         units (S1, S2 exact integers) and are scaled by 1/240 resp. 1/240^2 in the epilogue
 template <int NT, int V>
 struct MtCfg {
+  static constexpr bool U8 = V == 2;
   static constexpr int MARKERS = V == 0 ? 128 : 256;  // markers per CTA tile, 16 per warp
-  static constexpr int K = V == 0 ? 32 : 16;          // genotype rows consumed per stage
-  static constexpr int KBOX = K + 4;                  // rows fetched per stage (pitch = 4 mod 16 doubles)
+  static constexpr int K = V == 1 ? 16 : 32;          // genotype rows consumed per stage
+  static constexpr int KBOX = K + 4;                  // side-vector rows fetched per stage (pitch = 4 mod 16 doubles)
+  static constexpr int APITCH = U8 ? 48 : KBOX * 8;   // bytes per marker in the genotype tile
   static constexpr int WARPS = MARKERS / 16;          // DMMA warps
   static constexpr int THREADS = (WARPS + 1) * 32;
-  static constexpr int A_BYTES = MARKERS * KBOX * 8;
+  static constexpr int A_BYTES = MARKERS * APITCH;
   static constexpr int Q_BYTES = NT * 8 * KBOX * 8;
   static constexpr int STAGE_BYTES = A_BYTES + Q_BYTES;
   static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 6 ? 6 : (200 * 1024 / STAGE_BYTES);
@@ -113,13 +121,20 @@ __global__ void __launch_bounds__(MtCfg<NT, V>::THREADS, 1)
 
     for (int s = 0; s < prm.ksteps; ++s) {
       mbar_wait(&full_bar[stage], phase);
-      const double* sA = reinterpret_cast<const double*>(smem + stage * Cfg::STAGE_BYTES);
-      const double* sQ = sA + kMtMarkers * kMtKBox;
-      const double* pa = sA + (warp * 16 + g) * kMtKBox + t;
+      const uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+      const double* sQ = reinterpret_cast<const double*>(sA + kMtABytes);
+      const uint8_t* pa = sA + (warp * 16 + g) * Cfg::APITCH + t * (Cfg::U8 ? 1 : 8);
       const double* pq = sQ + g * kMtKBox + t;
+      // genotype (mt, kk) of this lane as a double: the Float64 itself, or 2^52 + code (exact) for codes
+      auto fetch = [&](const uint8_t* base) -> double {
+        if constexpr (Cfg::U8)
+          return __hiloint2double(0x43300000, static_cast<int>(*base));
+        else
+          return *reinterpret_cast<const double*>(base);
+      };
       if (s == 0) {  // the marker's first genotype (row 0 of the first stage)
-        shift[0] = sA[(warp * 16 + g) * kMtKBox];
-        shift[1] = sA[(warp * 16 + 8 + g) * kMtKBox];
+        shift[0] = fetch(sA + (warp * 16 + g) * Cfg::APITCH);
+        shift[1] = fetch(sA + (warp * 16 + 8 + g) * Cfg::APITCH);
       }
       const int64_t row0 = static_cast<int64_t>(s) * kMtK + t;
       const bool full = static_cast<int64_t>(s + 1) * kMtK <= prm.n;
@@ -128,7 +143,7 @@ __global__ void __launch_bounds__(MtCfg<NT, V>::THREADS, 1)
         double a[2], q[NT];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
-          a[mt] = pa[mt * 8 * kMtKBox + kk * 4] - shift[mt];
+          a[mt] = fetch(pa + mt * 8 * Cfg::APITCH + kk * 4 * (Cfg::U8 ? 1 : 8)) - shift[mt];
           if (!full && row0 + kk * 4 >= prm.n) a[mt] = 0.0;  // rows past n are zero-filled by TMA: d must be 0 too
           s2[mt] = fma(a[mt], a[mt], s2[mt]);
         }
@@ -157,30 +172,36 @@ __global__ void __launch_bounds__(MtCfg<NT, V>::THREADS, 1)
       const int64_t marker = static_cast<int64_t>(tile) * kMtMarkers + warp * 16 + mt * 8 + g;
       if (marker >= prm.p) continue;
       double* rec = prm.rec + marker * prm.rec_stride;
+      constexpr double denom = Cfg::U8 ? 240.0 : 1.0;  // codes -> allele frequencies (as scan_u8.cu: divisions)
+      const double first = Cfg::U8 ? shift[mt] - 4503599627370496.0 : shift[mt];
       if (t == 0) {
-        rec[0] = shift[mt] + S1 * prm.inv_n;
-        rec[1] = fmax(s2[mt] - S1 * S1 * prm.inv_n, 0.0);
+        rec[0] = (first + S1 * prm.inv_n) / denom;
+        rec[1] = fmax(s2[mt] - S1 * S1 * prm.inv_n, 0.0) / (denom * denom);
       }
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int col = nt * 8 + 2 * t + e;  // column of [1 | Q]
-          if (col >= 1 && col <= prm.M) rec[1 + col] = acc[mt][nt][e];
+          if (col >= 1 && col <= prm.M) rec[1 + col] = acc[mt][nt][e] / denom;
         }
     }
   }
 }
 
 template <int NT, int V>
-void launch_mt(const double* A, int64_t n, int64_t p, int64_t lda, const double* Qx, int M, int64_t ldq, double* rec,
+void launch_mt(const void* A, int64_t n, int64_t p, int64_t lda, const double* Qx, int M, int64_t ldq, double* rec,
                int rec_stride, int sm_count, cudaStream_t stream) {
   using Cfg = MtCfg<NT, V>;
   static_assert(Cfg::STAGES >= 3, "ring too shallow");
   alignas(64) CUtensorMap tmA, tmQ;
   // tensor maps are declared with exactly n rows and M + 1 columns: TMA zero-fills whatever a box reads beyond
-  make_tensor_map_2d_f64(&tmA, A, static_cast<uint64_t>(n), static_cast<uint64_t>(p), static_cast<uint64_t>(lda),
-                         Cfg::KBOX, Cfg::MARKERS);
+  if constexpr (Cfg::U8)
+    make_tensor_map_2d_u8(&tmA, A, static_cast<uint64_t>(n), static_cast<uint64_t>(p), static_cast<uint64_t>(lda),
+                          Cfg::APITCH, Cfg::MARKERS);
+  else
+    make_tensor_map_2d_f64(&tmA, static_cast<const double*>(A), static_cast<uint64_t>(n), static_cast<uint64_t>(p),
+                           static_cast<uint64_t>(lda), Cfg::KBOX, Cfg::MARKERS);
   make_tensor_map_2d_f64(&tmQ, Qx, static_cast<uint64_t>(n), static_cast<uint64_t>(M + 1), static_cast<uint64_t>(ldq),
                          Cfg::KBOX, NT * 8);
   MtParams prm;
@@ -233,6 +254,19 @@ void launch_scan_sums_mt(const double* A, int64_t n, int64_t p, int64_t lda, con
       else launch_mt<4, 1>(A, n, p, lda, Qx, M, ldq, rec, rec_stride, sm_count, stream);
   }
 #undef GBM_MT_CASE
+}
+
+// the same from one-byte dosage codes (a = code / 240): A8 is n x p bytes with column pitch ld8 (multiple of 16)
+void launch_scan_sums_mt_u8(const uint8_t* A8, int64_t n, int64_t p, int64_t ld8, const double* Qx, int M, int64_t ldq,
+                            double* rec, int rec_stride, int sm_count, cudaStream_t stream) {
+  if (p <= 0 || n <= 0) return;
+  if (M < 1 || M > 31 || rec_stride < 2 + M) GBM_THROW(1, "multi-trait scan: 1..31 side vectors per pass");
+  switch ((M + 1 + 7) / 8) {
+    case 1: launch_mt<1, 2>(A8, n, p, ld8, Qx, M, ldq, rec, rec_stride, sm_count, stream); break;
+    case 2: launch_mt<2, 2>(A8, n, p, ld8, Qx, M, ldq, rec, rec_stride, sm_count, stream); break;
+    case 3: launch_mt<3, 2>(A8, n, p, ld8, Qx, M, ldq, rec, rec_stride, sm_count, stream); break;
+    default: launch_mt<4, 2>(A8, n, p, ld8, Qx, M, ldq, rec, rec_stride, sm_count, stream); break;
+  }
 }
 
 }  // namespace gbm
