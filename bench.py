@@ -315,7 +315,10 @@ def main():
             traffic = tj["dram_bytes_per_marker"] * p_loc
     roofline = {"bound": "hbm", "kernel": "scan_sums_kernel<16,2>", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": main_avg_ms}
+                "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": main_avg_ms,
+                "note": "peak is MEASURED_PEAKS.json's copy bandwidth (a copy's read + write bytes); this kernel only "
+                        "reads, and a read-only stream runs above that figure -- ncu: dram__bytes_read = 1.0008 x the "
+                        "algorithmic bytes (profiles/r01_ncu_full_scan_final.md)"}
     keep_count = int(keep.sum().item())
 
     line = {
