@@ -1260,6 +1260,41 @@ int gbm_kstd_pc1(const double* K, int64_t n, double* Kstd, double* pc1, double* 
     DevBuf<double> dZ(static_cast<size_t>(ld) * n, st.stream);
     if (ld != n) GBM_CUDA(cudaMemsetAsync(dZ.p, 0, sizeof(double) * ld * n, st.stream));
     launch_row_centre(dKs.p, dZ.p, n, ld, st.stream);
+    // PC1 = the top left singular vector of Z = the eigenvector of the largest eigenvalue of B = Z Z'.  Only ONE
+    // eigenvector is needed, not the decomposition: Lanczos with full reorthogonalisation (csrc/lanczos.cu) --
+    //   n >= 12,000: on Z itself (two matrix-vector products per step; the n^3 SYRK for B costs more than it saves),
+    //   n >= 1,024 : on B, formed by the DMMA SYRK (one matrix-vector product per step),
+    // and cusolverDnDsyevdx on B below that, when Lanczos does not converge, or with GBM_PC1_SOLVER=cusolver.
+    // Timed separately either way (eig_ms).
+    const char* solver_env = getenv("GBM_PC1_SOLVER");
+    const bool force_cusolver = solver_env && !strcmp(solver_env, "cusolver");
+    const bool force_lanczos = solver_env && !strcmp(solver_env, "lanczos");
+    const bool force_gram = solver_env && !strcmp(solver_env, "lanczos-gram");
+    bool have_pc1 = false;
+    auto run_lanczos = [&](const double* mat, int64_t ldm, bool gram) {
+      DevBuf<double> dx(static_cast<size_t>(n), st.stream);
+      Span eig(st.stream);
+      eig.start();
+      int iters = 0;
+      double theta = 0.0;
+      have_pc1 = lanczos_top_eigenpair(mat, n, ldm, gram, 1e-14, 3000, dx.p, &theta, &iters, st.sm_count, st.stream);
+      eig.stop();
+      if (have_pc1) {
+        copy_out(pc1, dx.p, sizeof(double) * n, st.stream);
+        GBM_CUDA(cudaStreamSynchronize(st.stream));
+        if (eig_ms) *eig_ms = eig.ms();
+        st.main_ms = eig.ms();
+        st.launches += iters;
+      }
+    };
+    if (!force_cusolver && !force_lanczos && (n >= 12000 || force_gram)) run_lanczos(dZ.p, ld, true);
+    if (have_pc1) {
+      all.stop();
+      GBM_CUDA(cudaStreamSynchronize(st.stream));
+      st.h2d_ms = h2d.ms();
+      st.kernel_ms = all.ms();
+      return GBM_OK;
+    }
     // B = Z Z' through the DMMA SYRK (no centring), full symmetric
     DevBuf<double> dB(static_cast<size_t>(n) * n, st.stream);
     GBM_CUDA(cudaMemsetAsync(dB.p, 0, sizeof(double) * n * n, st.stream));
@@ -1269,29 +1304,7 @@ int gbm_kstd_pc1(const double* K, int64_t n, double* Kstd, double* pc1, double* 
     launch_grm_accumulate(dZ.p, n, n, ld, dzero.p, dB.p, st.sm_count, st.stream, false);
     launch_grm_finalize(dB.p, n, 1.0, st.stream);
     st.launches += 3;
-    // PC1 = the eigenvector of the largest eigenvalue of B.  n >= 1024: Lanczos with full reorthogonalisation
-    // (csrc/lanczos.cu; only ONE eigenvector is needed, not the decomposition); below that, when it does not
-    // converge, or with GBM_PC1_SOLVER=cusolver: cusolverDnDsyevdx.  Timed separately either way (eig_ms).
-    const char* solver_env = getenv("GBM_PC1_SOLVER");
-    const bool force_cusolver = solver_env && !strcmp(solver_env, "cusolver");
-    const bool force_lanczos = solver_env && !strcmp(solver_env, "lanczos");
-    bool have_pc1 = false;
-    if (!force_cusolver && (n >= 1024 || force_lanczos) && (n & 1) == 0) {
-      DevBuf<double> dx(static_cast<size_t>(n), st.stream);
-      Span eig(st.stream);
-      eig.start();
-      int iters = 0;
-      double theta = 0.0;
-      have_pc1 = lanczos_top_eigenpair(dB.p, n, n, 1e-14, 3000, dx.p, &theta, &iters, st.sm_count, st.stream);
-      eig.stop();
-      if (have_pc1) {
-        copy_out(pc1, dx.p, sizeof(double) * n, st.stream);
-        GBM_CUDA(cudaStreamSynchronize(st.stream));
-        if (eig_ms) *eig_ms = eig.ms();
-        st.main_ms = eig.ms();
-        st.launches += iters;
-      }
-    }
+    if (!force_cusolver && !force_gram && (n >= 1024 || force_lanczos) && (n & 1) == 0) run_lanczos(dB.p, n, false);
     if (!have_pc1) {
     // largest eigenpair of B through cuSOLVER
     if (!st.cusolver) {

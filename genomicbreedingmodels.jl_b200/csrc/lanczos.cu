@@ -58,6 +58,35 @@ __global__ void __launch_bounds__(256) symv_kernel(const double* __restrict__ B,
   }
 }
 
+// partial[c][i] = sum over the c-th chunk of columns of Z[i, j] u[j]   (Z column-major, pitch ld): thread = row,
+// so every load is coalesced; the chunks are summed in a fixed order by gemv_n_reduce_kernel (deterministic)
+constexpr int kGemvChunks = 64;
+__global__ void __launch_bounds__(256) gemv_n_partial_kernel(const double* __restrict__ Z, int64_t n, int64_t ld,
+                                                             const double* __restrict__ u, double* __restrict__ partial) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  const int64_t cw = (n + kGemvChunks - 1) / kGemvChunks;
+  const int64_t j0 = static_cast<int64_t>(blockIdx.y) * cw, j1 = min(n, j0 + cw);
+  if (i >= n) return;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int64_t j = j0;
+  for (; j + 4 <= j1; j += 4) {
+    a0 = fma(Z[(j + 0) * ld + i], u[j + 0], a0);
+    a1 = fma(Z[(j + 1) * ld + i], u[j + 1], a1);
+    a2 = fma(Z[(j + 2) * ld + i], u[j + 2], a2);
+    a3 = fma(Z[(j + 3) * ld + i], u[j + 3], a3);
+  }
+  for (; j < j1; ++j) a0 = fma(Z[j * ld + i], u[j], a0);
+  partial[static_cast<int64_t>(blockIdx.y) * n + i] = (a0 + a1) + (a2 + a3);
+}
+__global__ void __launch_bounds__(256) gemv_n_reduce_kernel(const double* __restrict__ partial, int64_t n,
+                                                            double* __restrict__ w) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int c = 0; c < kGemvChunks; ++c) s += partial[static_cast<int64_t>(c) * n + i];
+  w[i] = s;
+}
+
 // c[k] = V[:, k] . w for k < cols: one CTA per column, fixed-order reduction
 __global__ void __launch_bounds__(256) dots_kernel(const double* __restrict__ V, int64_t n, int64_t ldv,
                                                    const double* __restrict__ w, double* __restrict__ c) {
@@ -210,15 +239,16 @@ void tridiag_top(const std::vector<double>& a, const std::vector<double>& b, int
 
 }  // namespace
 
-bool lanczos_top_eigenpair(const double* B, int64_t n, int64_t ldb, double tol, int max_iter, double* x_dev,
+bool lanczos_top_eigenpair(const double* B, int64_t n, int64_t ldb, bool gram, double tol, int max_iter, double* x_dev,
                            double* theta_out, int* iters_out, int sm_count, cudaStream_t stream) {
   if ((ldb & 1) != 0 || (reinterpret_cast<uintptr_t>(B) & 15u) != 0) return false;
   const int m_max = static_cast<int>(std::min<int64_t>(max_iter, n - 1));
   if (m_max < 2) return false;
   const int64_t ldv = (n + 1) / 2 * 2;
   double *V = nullptr, *w = nullptr, *c = nullptr, *alpha = nullptr, *beta = nullptr, *sdev = nullptr;
+  double *u = nullptr, *partial = nullptr;  // gram operator: u = B' v, w = B u through chunk partials
   auto release = [&] {
-    for (double* p : {V, w, c, alpha, beta, sdev})
+    for (double* p : {V, w, c, alpha, beta, sdev, u, partial})
       if (p) cudaFreeAsync(p, stream);
   };
   try {
@@ -229,8 +259,23 @@ bool lanczos_top_eigenpair(const double* B, int64_t n, int64_t ldb, double tol, 
     GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&beta), sizeof(double) * (m_max + 1), stream));
     GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&sdev), sizeof(double) * (m_max + 1), stream));
     GBM_CUDA(cudaMemsetAsync(w, 0, sizeof(double) * ldv, stream));
+    if (gram) {
+      GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&u), sizeof(double) * ldv, stream));
+      GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&partial), sizeof(double) * n * kGemvChunks, stream));
+    }
     const unsigned row_blocks = static_cast<unsigned>((n + 255) / 256);
     const unsigned symv_grid = static_cast<unsigned>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(sm_count) * 8));
+    // out = Op v:  Op = B (symmetric), or Op = B B' for the gram operator (B = Z: the eigenvector of Z Z' without
+    // ever forming it: two passes over Z per step instead of one pass over Z Z' plus an n^3 SYRK up front)
+    auto apply = [&](const double* v, double* out) {
+      if (!gram) {
+        symv_kernel<<<symv_grid, 256, 0, stream>>>(B, n, ldb, v, out);
+      } else {
+        symv_kernel<<<symv_grid, 256, 0, stream>>>(B, n, ldb, v, u);  // u[j] = B[:, j] . v
+        gemv_n_partial_kernel<<<dim3(row_blocks, kGemvChunks), 256, 0, stream>>>(B, n, ldb, u, partial);
+        gemv_n_reduce_kernel<<<row_blocks, 256, 0, stream>>>(partial, n, out);
+      }
+    };
     start_vector_kernel<<<row_blocks, 256, 0, stream>>>(w, n);
     norm_next_kernel<<<1, 256, 0, stream>>>(w, n, V, beta, m_max);  // V[:, 0] = unit start vector (beta slot unused)
 
@@ -241,7 +286,7 @@ bool lanczos_top_eigenpair(const double* B, int64_t n, int64_t ldb, double tol, 
     int next_check = 30;
     for (int j = 0; j < m_max; ++j) {
       const double* vj = V + static_cast<int64_t>(j) * ldv;
-      symv_kernel<<<symv_grid, 256, 0, stream>>>(B, n, ldb, vj, w);
+      apply(vj, w);
       for (int pass = 0; pass < 2; ++pass) {  // classical Gram-Schmidt, twice
         dots_kernel<<<j + 1, 256, 0, stream>>>(V, n, ldv, w, c);
         project_out_kernel<<<row_blocks, 256, 0, stream>>>(V, n, ldv, j + 1, c, w, alpha, j, pass);
@@ -269,7 +314,7 @@ bool lanczos_top_eigenpair(const double* B, int64_t n, int64_t ldb, double tol, 
       combine_kernel<<<row_blocks, 256, 0, stream>>>(V, n, ldv, m, sdev, w);
       norm_next_kernel<<<1, 256, 0, stream>>>(w, n, x_dev, beta, 0);  // unit norm
       // explicit residual ||B x - theta x|| as the final word
-      symv_kernel<<<symv_grid, 256, 0, stream>>>(B, n, ldb, x_dev, w);
+      apply(x_dev, w);
       GBM_CUDA(cudaGetLastError());
       std::vector<double> hx(n), hy(n);
       GBM_CUDA(cudaMemcpyAsync(hx.data(), x_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));

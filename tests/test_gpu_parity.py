@@ -209,7 +209,8 @@ def test_kstd_pc1_matches_oracle(gbm, n):
     assert np.max(np.abs(sgn * pc - want_pc)) < 1e-9
 
 
-@pytest.mark.parametrize("n,kind", [(1024, synth.KIND_DIPLOID), (1500, synth.KIND_CONTINUOUS), (2600, synth.KIND_TETRAPLOID)])
+@pytest.mark.parametrize("n,kind", [(1024, synth.KIND_DIPLOID), (1500, synth.KIND_CONTINUOUS), (2600, synth.KIND_TETRAPLOID),
+                                    (1301, synth.KIND_DIPLOID)])
 def test_pc1_lanczos_matches_oracle_and_cusolver(gbm, n, kind, monkeypatch):
     """n >= 1024: PC1 comes from the Lanczos solver (csrc/lanczos.cu).  The spectrum of the standardised GRM
     is a near-degenerate bulk (relative gap of the top eigenvalue ~3e-3), the hard case for an iterative
@@ -220,9 +221,15 @@ def test_pc1_lanczos_matches_oracle_and_cusolver(gbm, n, kind, monkeypatch):
     want_pc = go.pca_pc1(go.standardise_K(K))
     monkeypatch.delenv("GBM_PC1_SOLVER", raising=False)
     _, pc, eig_ms = gbm.kstd_pc1(K, want_kstd=False)
-    assert gbm.last_timing()["launches"] > 20  # the iterative solver ran (its steps are counted as launches)
+    if n % 2 == 0:  # odd n below 12,000 goes to cuSOLVER (the symmetric matvec uses 16-byte loads on pitch n)
+        assert gbm.last_timing()["launches"] > 20  # the iterative solver ran (its steps are counted as launches)
     monkeypatch.setenv("GBM_PC1_SOLVER", "cusolver")
     _, pc_cs, _ = gbm.kstd_pc1(K, want_kstd=False)
+    # the variant used for n >= 12,000: Lanczos on Z itself (Z Z' never formed)
+    monkeypatch.setenv("GBM_PC1_SOLVER", "lanczos-gram")
+    _, pc_gram, _ = gbm.kstd_pc1(K, want_kstd=False)
+    assert gbm.last_timing()["launches"] > 20
+    assert np.max(np.abs(np.sign(pc_gram @ want_pc) * pc_gram - want_pc)) < 1e-9
     monkeypatch.delenv("GBM_PC1_SOLVER", raising=False)
     _, pc_again, _ = gbm.kstd_pc1(K, want_kstd=False)
     assert np.max(np.abs(pc - pc_again)) < 1e-12  # B = Z Z' itself carries last-bit noise (atomic tile slices)

@@ -12,7 +12,7 @@ for n, p in ((10000, 200000), (20000, 100000)):
     dm.free()
     dK = torch.empty(n * n, dtype=torch.float64, device="cuda")
     pk.grm(0, 2, 0, out=dK)
-    for solver in ("lanczos", "cusolver"):
+    for solver in ("lanczos", "lanczos-gram", "cusolver"):
         os.environ["GBM_PC1_SOLVER"] = solver
         for it in range(2):
             t0 = time.perf_counter()
