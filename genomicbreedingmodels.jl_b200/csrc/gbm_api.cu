@@ -1561,12 +1561,14 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
   //  * copy-engine lane: the block crosses PCIe as Float64 (cudaMemcpyAsync from the caller's pinned
   //    buffer) and is packed on the device.  Pageable memory would make those copies synchronous, so
   //    this lane then only takes what the host lane cannot.
-  // Default: the host lane alone when this process has >= 8 host threads (the packer then out-runs the
-  // PCIe link: ~110 GB/s of Float64 read by 16 cores against 55 GB/s), else the copy-engine lane alone.
+  // Default: the host lane alone when this process has >= 12 host threads, else the copy-engine lane alone.
+  // Measured on the pool's hosts (markers/s of the whole job, host lane / copy-engine lane): 1 GPU x 16 threads
+  // 1.75 M / 0.69 M; 2 GPUs x 24 threads 1.91 M / 1.38 M; 4 GPUs x 8 threads 1.85 M / 2.67 M; 8 GPUs x 4 threads
+  // 1.86 M / 2.33 M -- a packing core reads 4.6-8.8 GB/s of Float64, a GPU's link takes up to 55 GB/s.
   // Running both at once is a switch (GBM_SCAN_HOST_LANES=both): on the pool's hosts the copy engine's
   // reads slow the packing cores down by more than they add (measured 82 GB/s together, 100 GB/s host
   // lane alone), on a host with more memory bandwidth per core it pays.
-  bool host_lane = want_codes && !device_src && host_threads() >= 8;
+  bool host_lane = want_codes && !device_src && host_threads() >= 12;
   bool raw_lane = !host_lane;
   if (const char* e = getenv("GBM_SCAN_HOST_LANES")) {
     const bool can_host = want_codes && !device_src && host_threads() >= 2;
