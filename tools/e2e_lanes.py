@@ -59,7 +59,7 @@ for name, lanes, flags in (("float64 copies, Float64 kernel (NO_PACK)", None, _l
                            ("copy-engine lane only (device pack)", "copy", 0),
                            ("host lane only (host pack)", "host", 0),
                            ("both lanes", "both", 0),
-                           ("default (host lane with >= 8 host threads, else copy-engine lane)", None, 0)):
+                           ("default (host lane with >= 12 host threads per rank, else copy-engine lane)", None, 0)):
     if lanes:
         os.environ["GBM_SCAN_HOST_LANES"] = lanes
     else:
