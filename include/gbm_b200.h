@@ -152,8 +152,11 @@ int gbm_grm_finalize(double* dK, int64_t n, double scale);
 /* ---- K standardisation + PC1 ---------------------------------------------------------
  * Kstd = (K .- mean(K, dims=1)) ./ std(K, dims=1)               (gwas.jl:130)
  * pc1  = MultivariateStats.fit(PCA, Kstd; maxoutdim=1).proj[:,1] (gwas.jl:234, :357):
- *        rows centred, top left singular vector (unit norm, sign arbitrary), through
- *        cuSOLVER.  K host or device; Kstd nullable; eig_ms (nullable) = cuSOLVER time. */
+ *        rows centred, top left singular vector (unit norm, sign arbitrary).  Only this one vector is
+ *        needed, so n >= 1024 uses Lanczos with full reorthogonalisation on the device (csrc/lanczos.cu;
+ *        residual ||Bx - theta x|| <= 2e-13 theta), smaller or non-converging problems and
+ *        GBM_PC1_SOLVER=cusolver use cusolverDnDsyevdx.  K host or device; Kstd nullable; eig_ms (nullable) =
+ *        time of the eigen step alone. */
 int gbm_kstd_pc1(const double* K, int64_t n, double* Kstd, double* pc1, double* eig_ms);
 
 /* ---- the marker scan: the loops of gwasols (gwas.jl:239-249) and gwaslmm (:363-389) ---
