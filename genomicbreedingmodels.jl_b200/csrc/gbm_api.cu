@@ -1566,8 +1566,9 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
   // 1.75 M / 0.69 M; 2 GPUs x 24 threads 1.91 M / 1.38 M; 4 GPUs x 8 threads 1.85 M / 2.67 M; 8 GPUs x 4 threads
   // 1.86 M / 2.33 M -- a packing core reads 4.6-8.8 GB/s of Float64, a GPU's link takes up to 55 GB/s.
   // Running both at once is a switch (GBM_SCAN_HOST_LANES=both): on the pool's hosts the copy engine's
-  // reads slow the packing cores down by more than they add (measured 82 GB/s together, 100 GB/s host
-  // lane alone), on a host with more memory bandwidth per core it pays.
+  // reads slow the packing cores down by more than they add (1 GPU x 16 threads: 1.29 M markers/s together
+  // against 1.71-1.76 M for the host lane alone; 8 GPUs x 4 threads: 2.28 M together, 2.33 M copy lane
+  // alone), on a host with more memory bandwidth per core it pays.
   bool host_lane = want_codes && !device_src && host_threads() >= 12;
   bool raw_lane = !host_lane;
   if (const char* e = getenv("GBM_SCAN_HOST_LANES")) {
