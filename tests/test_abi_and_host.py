@@ -317,3 +317,38 @@ def test_graft_entry_build_runs_without_a_gpu():
 
     entry = importlib.import_module("__graft_entry__")
     entry.build()
+
+
+def test_public_header_is_plain_c_and_links_against_the_library():
+    """include/gbm_b200.h is the drop-in boundary: it must compile as C99 (no C++-isms, no torch types) and a
+    C program must link against libgbm_b200.so and call an entry point that needs no GPU."""
+    import subprocess
+    import tempfile
+
+    import gbm_b200
+
+    lib = gbm_b200.build()
+    src = r"""
+#include <stdio.h>
+#include "gbm_b200.h"
+int main(void) {
+  double a[4] = {0.0, 0.5, 1.0, 0.25};
+  unsigned char codes[4];
+  long long bad = -1;
+  int64_t inexact = -1;
+  (void)bad;
+  if (gbm_abi_version() != GBM_ABI_VERSION) return 2;
+  if (gbm_pack_host(a, 4, 1, 4, codes, 4, &inexact) != GBM_OK) return 3;
+  printf("%d %d %d %d %d\n", codes[0], codes[1], codes[2], codes[3], (int)inexact);
+  return gbm_scan(0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0) == GBM_ERR_NOT_INITIALISED ? 0 : 4;
+}
+"""
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "abi.c")
+        open(c, "w").write(src)
+        exe = os.path.join(td, "abi")
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                               c, "-o", exe, lib, "-Wl,-rpath," + os.path.dirname(lib), "-Wl,-rpath,/usr/local/cuda/lib64"])
+        out = subprocess.run([exe], capture_output=True, text=True)
+        assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+        assert out.stdout.split() == ["0", "120", "240", "60", "0"]
