@@ -2151,6 +2151,41 @@ int gbm_transform1_screen(const gbm_matrix* m, const double* y, int f, double ep
   GBM_API_END
 }
 
+// rows [row0, row1) of the pair matrix; sel / val in selection order (descending |beta|, ties by position), positions
+// are global one-based counters
+static int64_t transform2_rows(const gbm_matrix* m, const double* y, int f, double eps, int use_abs,
+                               double var_threshold, int commutative, int64_t row0, int64_t row1, int64_t n_new,
+                               double* beta, std::vector<int64_t>* sel, std::vector<double>* val, bool* has_nan) {
+  State& st = state();
+  reset_timing();
+  const int64_t l = m->p, rows = row1 - row0;
+  F64View A(m, st.stream);
+  CentredTrait yt(y, m->n, st.stream);
+  DevBuf<double> dvar(static_cast<size_t>(l), st.stream);
+  // beta on the device: the caller's buffer when it is device memory, else scratch
+  const bool user_dev = beta && is_device_ptr(beta);
+  DevBuf<double> dscratch(user_dev ? 0 : static_cast<size_t>(rows) * l, st.stream);
+  double* dbeta = user_dev ? beta : dscratch.p;
+  GBM_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(double) * rows * l, st.stream));
+  launch_transform1_scan(-1, A.d, m->n, l, A.lda, yt.dyc.p, yt.ybar, eps, use_abs, var_threshold, nullptr, dvar.p,
+                         st.sm_count, st.stream);
+  Span mainsp(st.stream);
+  mainsp.start();
+  launch_transform2_scan(f, A.d, m->n, l, A.lda, yt.dyc.p, yt.ybar, dvar.p, eps, use_abs, var_threshold, commutative,
+                         row0, row1, dbeta, st.stream);
+  mainsp.stop();
+  const int64_t take = std::min<int64_t>(n_new, rows * l);
+  sel->assign(static_cast<size_t>(std::max<int64_t>(take, 1)), 0);
+  val->assign(sel->size(), 0.0);
+  const int64_t cnt = transform_select(dbeta, rows * l, take, eps, sel->data(), val->data(), has_nan, st.sm_count, st.stream);
+  for (int64_t k = 0; k < cnt; ++k) (*sel)[k] += row0 * l;  // slab position -> global counter
+  if (beta && !user_dev) copy_out(beta, dbeta, sizeof(double) * rows * l, st.stream);
+  GBM_CUDA(cudaStreamSynchronize(st.stream));
+  st.main_ms = st.kernel_ms = mainsp.ms();
+  st.launches = 2;
+  return cnt;
+}
+
 int gbm_transform2_screen(const gbm_matrix* m, const double* y, int f, double eps, int use_abs, double var_threshold,
                           int commutative, int64_t n_new, double* beta, int64_t* counters, double* beta_sel,
                           int64_t* count) {
@@ -2163,27 +2198,10 @@ int gbm_transform2_screen(const gbm_matrix* m, const double* y, int f, double ep
   if (n_new > l * l)
     GBM_THROW(GBM_ERR_ARGUMENT, "BoundsError: attempt to access " + std::to_string(l * l) + "-element Vector{Int64} at index [1:" +
                                     std::to_string(n_new) + "]");
-  State& st = state();
-  reset_timing();
-  F64View A(m, st.stream);
-  CentredTrait yt(y, m->n, st.stream);
-  DevBuf<double> dvar(static_cast<size_t>(l), st.stream);
-  // beta on the device: the caller's buffer when it is device memory, else scratch
-  const bool user_dev = beta && is_device_ptr(beta);
-  DevBuf<double> dscratch(user_dev ? 0 : static_cast<size_t>(l) * l, st.stream);
-  double* dbeta = user_dev ? beta : dscratch.p;
-  GBM_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(double) * l * l, st.stream));
-  launch_transform1_scan(-1, A.d, m->n, l, A.lda, yt.dyc.p, yt.ybar, eps, use_abs, var_threshold, nullptr, dvar.p,
-                         st.sm_count, st.stream);
-  Span mainsp(st.stream);
-  mainsp.start();
-  launch_transform2_scan(f, A.d, m->n, l, A.lda, yt.dyc.p, yt.ybar, dvar.p, eps, use_abs, var_threshold, commutative,
-                         dbeta, st.stream);
-  mainsp.stop();
   bool has_nan = false;
-  std::vector<int64_t> sel(static_cast<size_t>(std::max<int64_t>(n_new, 1)));
-  std::vector<double> val(sel.size());
-  const int64_t cnt = transform_select(dbeta, l * l, n_new, eps, sel.data(), val.data(), &has_nan, st.sm_count, st.stream);
+  std::vector<int64_t> sel;
+  std::vector<double> val;
+  const int64_t cnt = transform2_rows(m, y, f, eps, use_abs, var_threshold, commutative, 0, l, n_new, beta, &sel, &val, &has_nan);
   // sort!(idx) (transformation.jl:430): ascending positions, values follow
   std::vector<int64_t> order(static_cast<size_t>(cnt));
   for (int64_t k = 0; k < cnt; ++k) order[k] = k;
@@ -2193,10 +2211,30 @@ int gbm_transform2_screen(const gbm_matrix* m, const double* y, int f, double ep
     if (beta_sel) beta_sel[k] = val[order[k]];
   }
   *count = cnt;
-  if (beta && !user_dev) copy_out(beta, dbeta, sizeof(double) * l * l, st.stream);
-  GBM_CUDA(cudaStreamSynchronize(st.stream));
-  st.main_ms = st.kernel_ms = mainsp.ms();
-  st.launches = 2;
+  if (has_nan) GBM_THROW(GBM_ERR_ARGUMENT, kCannotTransform);
+  GBM_API_END
+}
+
+int gbm_transform2_screen_rows(const gbm_matrix* m, const double* y, int f, double eps, int use_abs,
+                               double var_threshold, int commutative, int64_t row0, int64_t row1, int64_t n_new,
+                               double* beta_slab, int64_t* counters, double* beta_sel, int64_t* count) {
+  GBM_API_BEGIN
+  require_ready();
+  check_transform_args(m, y, n_new, counters, count);
+  if (f < GBM_F2_MULT || f > GBM_F2_RAISE) GBM_THROW(GBM_ERR_ARGUMENT, "transform2: unknown transformation code");
+  const int64_t l = m->p;
+  if (l > 3000000) GBM_THROW(GBM_ERR_ARGUMENT, "transform2: l^2 effects do not fit");
+  if (row0 < 0 || row1 > l || row0 >= row1) GBM_THROW(GBM_ERR_ARGUMENT, "transform2: row range out of bounds");
+  bool has_nan = false;
+  std::vector<int64_t> sel;
+  std::vector<double> val;
+  const int64_t cnt = transform2_rows(m, y, f, eps, use_abs, var_threshold, commutative, row0, row1, n_new, beta_slab, &sel,
+                                      &val, &has_nan);
+  for (int64_t k = 0; k < cnt; ++k) {  // selection order: descending |beta|, ties by ascending position
+    counters[k] = sel[k];
+    if (beta_sel) beta_sel[k] = val[k];
+  }
+  *count = cnt;
   if (has_nan) GBM_THROW(GBM_ERR_ARGUMENT, kCannotTransform);
   GBM_API_END
 }

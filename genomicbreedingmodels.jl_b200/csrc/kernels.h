@@ -131,10 +131,11 @@ bool lanczos_top_eigenpair(const double* B, int64_t n, int64_t ldb, bool gram, d
 void launch_transform1_scan(int f, const double* A, int64_t n, int64_t p, int64_t lda, const double* yc, double ybar,
                             double eps, int use_abs, double var_thr, double* beta, double* colvar, int sm_count,
                             cudaStream_t stream);
-// Pairwise screen: beta[(i-1) l + (j-1)] for every evaluated pair; beta must be zeroed by the caller.
+// Pairwise screen over rows [row0, row1) of the l x l pair matrix (0-based i; the whole screen is [0, l)):
+// beta[(i - row0) l + j] for every evaluated pair; beta ((row1 - row0) x l) must be zeroed by the caller.
 void launch_transform2_scan(int f, const double* A, int64_t n, int64_t l, int64_t lda, const double* yc, double ybar,
                             const double* colvar, double eps, int use_abs, double var_thr, int commutative,
-                            double* beta, cudaStream_t stream);
+                            int64_t row0, int64_t row1, double* beta, cudaStream_t stream);
 void launch_transform1_apply(int f, const double* A, int64_t n, int64_t lda, const int64_t* idx, int64_t count,
                              double eps, int use_abs, double* T, int64_t ldt, cudaStream_t stream);
 void launch_transform2_apply(int f, const double* A, int64_t n, int64_t l, int64_t lda, const int64_t* counters,

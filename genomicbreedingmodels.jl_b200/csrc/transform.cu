@@ -182,11 +182,12 @@ __global__ void __launch_bounds__(1024 / TJ, 1)
     transform2_scan_kernel(const double* __restrict__ Xi, const double* __restrict__ Xj, int64_t n, int64_t l,
                            int64_t ldx, const double* __restrict__ yc, double ybar,
                            const double* __restrict__ colvar, double var_thr, int commutative,
-                           double* __restrict__ beta) {
+                           int64_t row0, int64_t row1, double* __restrict__ beta) {
   constexpr int NJ = kTile / TJ;        // threads along j (16 or 32)
   constexpr int THREADS = 16 * NJ;      // 16 threads along i
   constexpr int LOADS = 2 * kTile * kRows / THREADS;  // cp.async per thread and stage (ai + aj)
-  const int bi = blockIdx.y, bj = blockIdx.x;
+  // rows [row0, row1) of the pair matrix (a marker shard of a multi-GPU screen); beta is that slab, (row1 - row0) x l
+  const int bi = blockIdx.y + static_cast<int>(row0 / kTile), bj = blockIdx.x;
   if (commutative && bj < bi) return;  // every pair of the tile has j < i (transformation.jl:373)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T2Stage* stage = reinterpret_cast<T2Stage*>(smem_raw);
@@ -270,12 +271,12 @@ __global__ void __launch_bounds__(1024 / TJ, 1)
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     const int64_t i = i0 + ti + 16 * a;
-    if (i >= l || colvar[i] < var_thr) continue;
+    if (i >= l || i < row0 || i >= row1 || colvar[i] < var_thr) continue;
 #pragma unroll
     for (int b = 0; b < TJ; ++b) {
       const int64_t j = j0 + tj + NJ * b;
       if (j >= l || colvar[j] < var_thr || (commutative && j < i)) continue;
-      beta[i * l + j] = slope_from_sums(dn, z0[a][b], s1[a][b], s2[a][b], sy[a][b], ybar);
+      beta[(i - row0) * l + j] = slope_from_sums(dn, z0[a][b], s1[a][b], s2[a][b], sy[a][b], ybar);
     }
   }
 }
@@ -356,8 +357,8 @@ void launch_transform1_scan(int f, const double* A, int64_t n, int64_t p, int64_
 
 template <int F, int TJ>
 static void launch_t2_tj(const double* Xi, const double* Xj, int64_t n, int64_t l, int64_t ldx, const double* yc,
-                         double ybar, const double* colvar, double var_thr, int commutative, double* beta,
-                         cudaStream_t stream) {
+                         double ybar, const double* colvar, double var_thr, int commutative, int64_t row0,
+                         int64_t row1, double* beta, cudaStream_t stream) {
   const size_t smem = 2 * sizeof(T2Stage);
   static bool configured = false;
   if (!configured) {
@@ -365,13 +366,14 @@ static void launch_t2_tj(const double* Xi, const double* Xj, int64_t n, int64_t 
     configured = true;
   }
   const unsigned nb = static_cast<unsigned>((l + kTile - 1) / kTile);
-  transform2_scan_kernel<F, TJ><<<dim3(nb, nb), 1024 / TJ, smem, stream>>>(Xi, Xj, n, l, ldx, yc, ybar, colvar, var_thr,
-                                                                          commutative, beta);
+  const unsigned nby = static_cast<unsigned>((row1 + kTile - 1) / kTile - row0 / kTile);
+  transform2_scan_kernel<F, TJ><<<dim3(nb, nby), 1024 / TJ, smem, stream>>>(Xi, Xj, n, l, ldx, yc, ybar, colvar, var_thr,
+                                                                           commutative, row0, row1, beta);
 }
 template <int F>
 static void launch_t2(const double* Xi, const double* Xj, int64_t n, int64_t l, int64_t ldx, const double* yc,
-                      double ybar, const double* colvar, double var_thr, int commutative, double* beta,
-                      cudaStream_t stream) {
+                      double ybar, const double* colvar, double var_thr, int commutative, int64_t row0, int64_t row1,
+                      double* beta, cudaStream_t stream) {
   // measured (n = 10,000, l = 8,192): the 4 x 4 tile (256 threads) is as fast or faster for the short bodies
   // (mult 189 ms, addnorm 215 vs 218 ms), the 4 x 2 tile (512 threads, 16 warps / SM) for exp (975 vs 1093 ms)
   static const int tj = [] {
@@ -380,15 +382,15 @@ static void launch_t2(const double* Xi, const double* Xj, int64_t n, int64_t l, 
     return F >= GBM_F2_RAISE ? 2 : 4;
   }();
   if (tj == 4)
-    launch_t2_tj<F, 4>(Xi, Xj, n, l, ldx, yc, ybar, colvar, var_thr, commutative, beta, stream);
+    launch_t2_tj<F, 4>(Xi, Xj, n, l, ldx, yc, ybar, colvar, var_thr, commutative, row0, row1, beta, stream);
   else
-    launch_t2_tj<F, 2>(Xi, Xj, n, l, ldx, yc, ybar, colvar, var_thr, commutative, beta, stream);
+    launch_t2_tj<F, 2>(Xi, Xj, n, l, ldx, yc, ybar, colvar, var_thr, commutative, row0, row1, beta, stream);
 }
 
 void launch_transform2_scan(int f, const double* A, int64_t n, int64_t l, int64_t lda, const double* yc, double ybar,
                             const double* colvar, double eps, int use_abs, double var_thr, int commutative,
-                            double* beta, cudaStream_t stream) {
-  if (l <= 0) return;
+                            int64_t row0, int64_t row1, double* beta, cudaStream_t stream) {
+  if (l <= 0 || row1 <= row0) return;
   if ((l + kTile - 1) / kTile > 65535) GBM_THROW(GBM_ERR_ARGUMENT, "transform2: too many loci for one pairwise screen");
   if (f < GBM_F2_MULT || f > GBM_F2_RAISE) GBM_THROW(GBM_ERR_ARGUMENT, "unknown two-argument transformation");
   // X' (and log X' for raise) once, so that the pair kernel only accumulates
@@ -410,13 +412,13 @@ void launch_transform2_scan(int f, const double* A, int64_t n, int64_t l, int64_
     GBM_CUDA(cudaStreamSynchronize(stream));
   }
   switch (f) {
-    case GBM_F2_MULT: launch_t2<GBM_F2_MULT>(Xp.p, Xp.p, n, l, ldx, yc, ybar, colvar, var_thr, commutative, beta, stream); break;
-    case GBM_F2_ADDNORM: launch_t2<GBM_F2_ADDNORM>(Xp.p, Xp.p, n, l, ldx, yc, ybar, colvar, var_thr, commutative, beta, stream); break;
+    case GBM_F2_MULT: launch_t2<GBM_F2_MULT>(Xp.p, Xp.p, n, l, ldx, yc, ybar, colvar, var_thr, commutative, row0, row1, beta, stream); break;
+    case GBM_F2_ADDNORM: launch_t2<GBM_F2_ADDNORM>(Xp.p, Xp.p, n, l, ldx, yc, ybar, colvar, var_thr, commutative, row0, row1, beta, stream); break;
     default:
       if (h_nonpos)  // zero / negative / non-finite bases: pow() itself decides (NaN where Julia throws DomainError)
-        launch_t2<GBM_F2_RAISE>(Xp.p, Xp.p, n, l, ldx, yc, ybar, colvar, var_thr, commutative, beta, stream);
+        launch_t2<GBM_F2_RAISE>(Xp.p, Xp.p, n, l, ldx, yc, ybar, colvar, var_thr, commutative, row0, row1, beta, stream);
       else
-        launch_t2<kRaiseFast>(Lp.p, Xp.p, n, l, ldx, yc, ybar, colvar, var_thr, commutative, beta, stream);
+        launch_t2<kRaiseFast>(Lp.p, Xp.p, n, l, ldx, yc, ybar, colvar, var_thr, commutative, row0, row1, beta, stream);
   }
   GBM_CUDA(cudaGetLastError());
 }

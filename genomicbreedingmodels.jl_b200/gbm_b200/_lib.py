@@ -92,6 +92,8 @@ SIGNATURES = {
     "gbm_transform1_screen": (c_int, [c_void_p, _P, c_int, c_double, c_int, c_double, c_int64, _P, _P, POINTER(c_int64)]),
     "gbm_transform2_screen": (c_int, [c_void_p, _P, c_int, c_double, c_int, c_double, c_int, c_int64, _P, _P, _P,
                                       POINTER(c_int64)]),
+    "gbm_transform2_screen_rows": (c_int, [c_void_p, _P, c_int, c_double, c_int, c_double, c_int, c_int64, c_int64, c_int64,
+                                           _P, _P, _P, POINTER(c_int64)]),
     "gbm_transform1_apply": (c_int, [c_void_p, c_int, c_double, c_int, _P, c_int64, _P, c_int64]),
     "gbm_transform2_apply": (c_int, [c_void_p, c_int, c_double, c_int, _P, c_int64, _P, c_int64]),
     "gbm_neglog10_sf": (c_int, [_P, c_int64, c_int, c_double, _P]),

@@ -108,6 +108,55 @@ def transform2_screen(dm: DeviceMatrix, y, f, n_new: int, eps: float = _EPS, use
     return beta, counters[:cnt.value].copy(), vals[:cnt.value].copy()
 
 
+def transform2_screen_rows(dm: DeviceMatrix, y, f, row0: int, row1: int, n_new: int, eps: float = _EPS,
+                           use_abs: bool = False, var_threshold: float = 0.01, commutative: bool = False):
+    """Rows [row0, row1) (0-based) of the pair matrix: (counters, values) of the slab's top effects in selection
+    order (descending |beta|, ties by ascending global position) -- one rank's share of a sharded screen."""
+    code = _code(f, 2)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    counters = np.empty(max(int(n_new), 1), dtype=np.int64)
+    vals = np.empty(max(int(n_new), 1))
+    cnt = c_int64()
+    check(_lib.lib().gbm_transform2_screen_rows(dm._h, ptr(y), code, float(eps), int(use_abs), float(var_threshold),
+                                                int(commutative), int(row0), int(row1), int(n_new), None,
+                                                ptr(counters), ptr(vals), byref(cnt)))
+    return counters[:cnt.value].copy(), vals[:cnt.value].copy()
+
+
+def merge_screen_candidates(parts, n_new: int, eps: float = _EPS):
+    """Merges per-shard candidate lists [(counters, values), ...] into the selection of the unsharded screen:
+    sortperm(abs.(beta), rev = true)[1:n_new] is stable, so the global order is (descending |beta|, ascending
+    position); keep abs(beta) > eps and return ascending positions (sort!(idx), transformation.jl:430)."""
+    counters = np.concatenate([np.asarray(c, dtype=np.int64) for c, _ in parts]) if parts else np.zeros(0, np.int64)
+    values = np.concatenate([np.asarray(v, dtype=np.float64) for _, v in parts]) if parts else np.zeros(0)
+    order = np.lexsort((counters, -np.abs(values)))[: int(n_new)]
+    order = order[np.abs(values[order]) > eps]
+    asc = np.sort(counters[order])
+    lookup = dict(zip(counters.tolist(), values.tolist()))
+    return asc, np.array([lookup[c] for c in asc.tolist()])
+
+
+def transform2_screen_sharded(dm: DeviceMatrix, y, f, n_new: int, eps: float = _EPS, use_abs: bool = False,
+                              var_threshold: float = 0.01, commutative: bool = False, group=None):
+    """transform2's pairwise screen over the ranks of a torch.distributed group: every rank holds the n x l
+    matrix and screens a contiguous block of rows of the l x l pair matrix (no data-path collective); the
+    candidate lists (<= n_new per rank) are all-gathered and merged.  Same result as transform2_screen."""
+    import torch.distributed as dist
+
+    from .sharded import shard_bounds
+
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    r0, r1 = shard_bounds(dm.p, world, rank)
+    mine = (np.zeros(0, np.int64), np.zeros(0)) if r1 <= r0 else transform2_screen_rows(
+        dm, y, f, r0, r1, n_new, eps, use_abs, var_threshold, commutative)
+    parts = [mine]
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, mine, group=group)
+    return merge_screen_candidates(parts, n_new, eps)
+
+
 def transform1_apply(dm: DeviceMatrix, f, idx, eps: float = _EPS, use_abs: bool = False) -> np.ndarray:
     idx = np.ascontiguousarray(idx, dtype=np.int64)
     T = np.empty((dm.n, idx.size), order="F")

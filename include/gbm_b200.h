@@ -246,6 +246,14 @@ int gbm_transform1_screen(const gbm_matrix* m, const double* y, int f, double ep
 int gbm_transform2_screen(const gbm_matrix* m, const double* y, int f, double eps, int use_abs, double var_threshold,
                           int commutative, int64_t n_new, double* beta, int64_t* counters, double* beta_sel,
                           int64_t* count);
+/* Rows [row0, row1) (0-based i) of the same pair matrix: the unit of a multi-GPU screen (every rank holds the
+ * n x p matrix and takes a block of rows; no data-path collective).  beta_slab: (row1 - row0) * p values or NULL.
+ * counters / beta_sel: the slab's top min(n_new, slab size) effects with abs(beta) > eps in SELECTION order
+ * (descending abs(beta), ties by ascending position), counters being global one-based positions -- merging the
+ * ranks' lists in that order and cutting at n_new reproduces gbm_transform2_screen (gbm_b200/sharded.py). */
+int gbm_transform2_screen_rows(const gbm_matrix* m, const double* y, int f, double eps, int use_abs,
+                               double var_threshold, int commutative, int64_t row0, int64_t row1, int64_t n_new,
+                               double* beta_slab, int64_t* counters, double* beta_sel, int64_t* count);
 /* T = f.(X[:, idx]) resp. f.(X[:, i], X[:, j]) for the selected features, then abs(T) < eps -> 0 and
  * abs(T - 1) < eps -> 1 (:223-227, :440-461).  T: n x count, pitch ldt, host or device. */
 int gbm_transform1_apply(const gbm_matrix* m, int f, double eps, int use_abs, const int64_t* idx, int64_t count,

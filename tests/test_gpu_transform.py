@@ -197,3 +197,27 @@ def test_packed_matrix_gives_the_same_effects(gbm):
     assert np.array_equal(a2, b2) and np.array_equal(ca, cb)
     dm.free()
     pk.free()
+
+
+@pytest.mark.parametrize("commutative", [False, True])
+def test_row_sharded_screen_equals_the_unsharded_one(gbm, commutative):
+    """gbm_transform2_screen_rows is one rank's share of a multi-GPU screen (a block of rows of the l x l pair
+    matrix, no data-path collective): merging the per-block candidate lists must reproduce the unsharded
+    selection bit for bit, for tile-aligned and ragged row blocks."""
+    tr, _, _ = _pairs(gbm)
+    n, l, n_new = 500, 333, 200
+    A = synth.block(17, n, 0, l, synth.KIND_TETRAPLOID)
+    y = synth.phenotype(17, n, l, synth.KIND_TETRAPLOID, n_causal=5)
+    dm = gbm.DeviceMatrix.upload(A)
+    beta, cnt, vals = tr.transform2_screen(dm, y, tr.addnorm, n_new, commutative=commutative, want_beta=True)
+    for bounds in ([0, 128, 256, l], [0, 100, 101, 250, l], [0, l]):
+        parts = [tr.transform2_screen_rows(dm, y, tr.addnorm, r0, r1, n_new, commutative=commutative)
+                 for r0, r1 in zip(bounds[:-1], bounds[1:])]
+        for (c, v), r0, r1 in zip(parts, bounds[:-1], bounds[1:]):
+            assert np.all((c - 1) // l >= r0) and np.all((c - 1) // l < r1)
+            assert np.array_equal(v, beta[c - 1])
+            assert np.all(np.abs(v[:-1]) >= np.abs(v[1:]))  # selection order
+        mc, mv = tr.merge_screen_candidates(parts, n_new)
+        assert np.array_equal(mc, cnt) and np.array_equal(mv, vals)
+    assert np.array_equal(tr.transform2_screen_sharded(dm, y, tr.addnorm, n_new, commutative=commutative)[0], cnt)
+    dm.free()
