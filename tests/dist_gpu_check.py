@@ -65,6 +65,21 @@ def main():
               f"= {tf:.1f} TFLOP/s aggregate incl. all-reduce -> {'OK' if ok else 'FAIL'}", flush=True)
         if not ok:
             sys.exit(1)
+    # pairwise transformation screen, rows of the pair matrix sharded over the ranks (every rank holds the matrix)
+    from gbm_b200 import transform as tr
+
+    tl, tn_new = 700, 300
+    tm = gbm_b200.DeviceMatrix.generate(seed, 800, tl, synth.KIND_TETRAPLOID)
+    ty = synth.phenotype(seed, 800, tl, synth.KIND_TETRAPLOID)
+    sc, sv = tr.transform2_screen_sharded(tm, ty, tr.mult, tn_new)
+    if rank == 0:
+        _, uc, uv = tr.transform2_screen(tm, ty, tr.mult, tn_new)
+        same = np.array_equal(sc, uc) and np.array_equal(sv, uv)
+        print(f"dist_gpu_check world={world}: sharded transform2 screen (l={tl}, {tl * tl} regressions) "
+              f"selection identical to the unsharded one: {same} -> {'OK' if same else 'FAIL'}", flush=True)
+        if not same:
+            sys.exit(1)
+    tm.free()
     dist.barrier()
     dist.destroy_process_group()
 
