@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 
 namespace gbm {
@@ -25,7 +26,11 @@ struct Error {
                                 ":" + std::to_string(__LINE__) + ")"};                              \
   } while (0)
 
+// One State per driven GPU.  The process-wide default one belongs to gbm_init; a gbm_group (group.cu) owns
+// one per local GPU and runs each on its own host thread.  state() resolves to the State bound to the calling
+// thread (bind_state), the default one otherwise; entry points are serialised per State.
 struct State {
+  std::mutex api_mutex;
   bool ready = false;
   int device = -1;
   int sm_count = 0;
@@ -59,6 +64,9 @@ struct State {
   int64_t packed_blocks = 0, host_packed_blocks = 0, h2d_bytes = 0;
 };
 State& state();
+void bind_state(State* s);  // nullptr: back to the process-wide default State
+void init_state(State& st, int device);
+void shutdown_state(State& st);
 void require_ready();
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed)

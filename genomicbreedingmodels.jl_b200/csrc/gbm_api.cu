@@ -34,14 +34,20 @@ struct gbm_matrix {
 namespace gbm {
 
 static thread_local std::string g_error;
-static std::mutex g_mutex;  // entry points are serialised (SURVEY.md 8b "Threading")
 void set_error(const std::string& msg) { g_error = msg; }
+// entry points are serialised per State (SURVEY.md 8b "Threading"): State::api_mutex
+static thread_local State* t_state = nullptr;
 State& state() {
   static State s;
-  return s;
+  return t_state ? *t_state : s;
 }
+void bind_state(State* s) { t_state = s; }
 void require_ready() {
-  if (!state().ready) throw Error{GBM_ERR_NOT_INITIALISED, "gbm_init has not been called (no CUDA device selected)"};
+  State& st = state();
+  if (!st.ready) throw Error{GBM_ERR_NOT_INITIALISED, "gbm_init has not been called (no CUDA device selected)"};
+  // the current device is per host thread: a caller that comes in on another thread (Julia tasks migrate)
+  // must still land on this State's GPU
+  GBM_CUDA(cudaSetDevice(st.device));
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -552,33 +558,7 @@ static bool upload_codes(const double* A, int64_t n, int64_t p, int64_t lda, uin
   return all;
 }
 
-}  // namespace gbm
-
-using namespace gbm;
-
-#define GBM_API_BEGIN                            \
-  std::lock_guard<std::mutex> lock__(g_mutex);   \
-  try {
-#define GBM_API_END                              \
-  }                                              \
-  catch (const gbm::Error& e) {                  \
-    set_error(e.msg);                            \
-    return e.code;                               \
-  }                                              \
-  catch (const std::exception& e) {              \
-    set_error(std::string("internal: ") + e.what()); \
-    return GBM_ERR_RUNTIME;                      \
-  }                                              \
-  return GBM_OK;
-
-extern "C" {
-
-int gbm_abi_version(void) { return GBM_ABI_VERSION; }
-const char* gbm_last_error(void) { return g_error.c_str(); }
-
-int gbm_init(int device) {
-  GBM_API_BEGIN
-  State& st = state();
+void init_state(State& st, int device) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0)
@@ -589,7 +569,7 @@ int gbm_init(int device) {
   GBM_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10)
     GBM_THROW(GBM_ERR_CUDA, std::string("libgbm_b200 is built for sm_100a (B200) only; found ") + prop.name);
-  if (st.ready && st.device == device) return GBM_OK;
+  if (st.ready && st.device == device) return;
   if (st.ready) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_init: already initialised on another device; call gbm_shutdown first");
   st.device = device;
   st.sm_count = prop.multiProcessorCount;
@@ -603,13 +583,11 @@ int gbm_init(int device) {
     GBM_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
   }
   st.ready = true;
-  GBM_API_END
 }
 
-int gbm_shutdown(void) {
-  GBM_API_BEGIN
-  State& st = state();
-  if (!st.ready) return GBM_OK;
+void shutdown_state(State& st) {
+  if (!st.ready) return;
+  cudaSetDevice(st.device);
   cudaStreamSynchronize(st.stream);
   if (st.cusolver) {
     cusolverDnDestroy(reinterpret_cast<cusolverDnHandle_t>(st.cusolver));
@@ -621,6 +599,54 @@ int gbm_shutdown(void) {
   if (st.raw_stream) cudaStreamDestroy(st.raw_stream);
   st.own_stream = st.copy_stream = st.raw_stream = st.stream = nullptr;
   st.ready = false;
+}
+
+}  // namespace gbm
+
+using namespace gbm;
+
+// Error exit of an entry point: nothing of the call may still be reading the caller's host buffers or writing
+// its outputs after the return ("host pointers are never retained"), so wait for every stream of this State.
+static void drain_streams() {
+  State& st = state();
+  if (!st.ready) return;
+  if (st.stream) cudaStreamSynchronize(st.stream);
+  if (st.copy_stream) cudaStreamSynchronize(st.copy_stream);
+  if (st.raw_stream) cudaStreamSynchronize(st.raw_stream);
+  cudaGetLastError();
+}
+
+#define GBM_API_BEGIN                            \
+  std::lock_guard<std::mutex> lock__(gbm::state().api_mutex); \
+  try {
+#define GBM_API_END                              \
+  }                                              \
+  catch (const gbm::Error& e) {                  \
+    drain_streams();                             \
+    set_error(e.msg);                            \
+    return e.code;                               \
+  }                                              \
+  catch (const std::exception& e) {              \
+    drain_streams();                             \
+    set_error(std::string("internal: ") + e.what()); \
+    return GBM_ERR_RUNTIME;                      \
+  }                                              \
+  return GBM_OK;
+
+extern "C" {
+
+int gbm_abi_version(void) { return GBM_ABI_VERSION; }
+const char* gbm_last_error(void) { return g_error.c_str(); }
+
+int gbm_init(int device) {
+  GBM_API_BEGIN
+  init_state(state(), device);
+  GBM_API_END
+}
+
+int gbm_shutdown(void) {
+  GBM_API_BEGIN
+  shutdown_state(state());
   GBM_API_END
 }
 
@@ -1251,7 +1277,7 @@ int gbm_kstd_pc1(const double* K, int64_t n, double* Kstd, double* pc1, double* 
   DevBuf<double> rec(static_cast<size_t>(n) * stride, st.stream), dmean(n, st.stream), dsd(n, st.stream);
   launch_scan_sums(dKs.p, n, n, ld, nullptr, 0, 0, true, rec.p, st.sm_count, st.stream);
   launch_colstats_finalize(rec.p, stride, n, n, dmean.p, dsd.p, nullptr, nullptr, st.stream);
-  launch_k_standardise(dKs.p, n, ld, dmean.p, dsd.p, st.stream);
+  launch_k_standardise(dKs.p, n, n, ld, dmean.p, dsd.p, st.stream);
   st.launches += 3;
   if (Kstd)
     GBM_CUDA(cudaMemcpy2DAsync(Kstd, n * sizeof(double), dKs.p, ld * sizeof(double), n * sizeof(double), n,
@@ -1287,7 +1313,8 @@ int gbm_kstd_pc1(const double* K, int64_t n, double* Kstd, double* pc1, double* 
         st.launches += iters;
       }
     };
-    if (!force_cusolver && !force_lanczos && (n >= 12000 || force_gram)) run_lanczos(dZ.p, ld, true);
+    // odd n: B = Z Z' has an odd pitch (128-bit loads of its columns would be misaligned), Z is padded: gram operator
+    if (!force_cusolver && !force_lanczos && (n >= 12000 || force_gram || (n >= 1024 && (n & 1)))) run_lanczos(dZ.p, ld, true);
     if (have_pc1) {
       all.stop();
       GBM_CUDA(cudaStreamSynchronize(st.stream));

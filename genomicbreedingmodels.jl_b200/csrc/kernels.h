@@ -79,8 +79,11 @@ void launch_sum_q1mq(const double* mu, int64_t p, double* out, cudaStream_t stre
 
 // pc1.cu -------------------------------------------------------------------------------
 // In place: K <- (K - colmean) / colsd ; then Z = Kstd - rowmean (written to Z). n x n, pitch ld.
-void launch_k_standardise(double* K, int64_t n, int64_t ld, const double* colmean, const double* colsd,
+void launch_k_standardise(double* K, int64_t n, int64_t ncols, int64_t ld, const double* colmean, const double* colsd,
                           cudaStream_t stream);
+// Z[i, j] -= rowsum[i] * inv_cols over an n x ncols column block
+void launch_row_shift(double* Z, int64_t n, int64_t ncols, int64_t ld, const double* rowsum, double inv_cols,
+                      cudaStream_t stream);
 void launch_row_centre(const double* Ks, double* Z, int64_t n, int64_t ld, cudaStream_t stream);
 // gather rows/cols (1-based indices, nullable) from a device source into a padded device matrix
 void launch_gather(const double* src, int64_t lds, const int64_t* rows, int64_t n, const int64_t* cols, int64_t p,
@@ -124,6 +127,19 @@ double lmm_null_lam0(int Q0, const double* S, const double* Cr, int64_t ldcr, co
 // products per step (B B' is never formed); x is then the top left singular vector of B.
 bool lanczos_top_eigenpair(const double* B, int64_t n, int64_t ldb, bool gram, double tol, int max_iter, double* x_dev,
                            double* theta, int* iters, int sm_count, cudaStream_t stream);
+// The same when the columns of Z (n x n) are sharded over the ranks of a group: Zg is this rank's n x nc column
+// block (pitch ld).  Z Z' = sum over ranks of Zg Zg', so a step is u = Zg' v, w = Zg u (two passes over the block)
+// and ONE all-reduce of the n-vector w; everything else runs replicated (NCCL hands every rank the same bits, so
+// the replicas stay identical).  allreduce_sum(buf, count) must sum `count` doubles at `buf` (device) over the
+// ranks, ordered on `stream`.  rowsum_out (nullable, n): Zg 1, the block's row sums, before any all-reduce.
+struct ShardedAllReduce {
+  virtual void sum(double* buf, int64_t count) = 0;
+  virtual ~ShardedAllReduce() {}
+};
+void block_row_sums(const double* Zg, int64_t n, int64_t nc, int64_t ld, double* rowsum, cudaStream_t stream);
+bool lanczos_top_singular_sharded(const double* Zg, int64_t n, int64_t nc, int64_t ld, ShardedAllReduce* ar, double tol,
+                                  int max_iter, double* x_dev, double* theta, int* iters, int sm_count,
+                                  cudaStream_t stream);
 
 // transform.cu -------------------------------------------------------------------------
 // Per-locus OLS screen of f(x): beta[j] (0 when var(x) < var_thr) and colvar[j] = var(x) (nullable).

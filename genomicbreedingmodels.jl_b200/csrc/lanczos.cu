@@ -34,14 +34,15 @@ __device__ __forceinline__ double block_sum_256(double v, double* sh) {
   return t;  // valid in thread 0
 }
 
-// y[j] = B[:, j] . v   (B symmetric, column-major, pitch ld): one warp per column
-__global__ void __launch_bounds__(256) symv_kernel(const double* __restrict__ B, int64_t n, int64_t ld,
+// y[j] = B[:, j] . v for j < ncols  (B: n rows, column-major, pitch ld; for a symmetric B this is B v): one warp
+// per column
+__global__ void __launch_bounds__(256) symv_kernel(const double* __restrict__ B, int64_t n, int64_t ncols, int64_t ld,
                                                    const double* __restrict__ v, double* __restrict__ y) {
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * 8;
   const int64_t n2 = n >> 1;
   const double2* __restrict__ v2 = reinterpret_cast<const double2*>(v);
-  for (int64_t j = (static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x) >> 5; j < n; j += nwarps) {
+  for (int64_t j = (static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x) >> 5; j < ncols; j += nwarps) {
     const double2* __restrict__ c2 = reinterpret_cast<const double2*>(B + j * ld);
     double s0 = 0.0, s1 = 0.0;
 #pragma unroll 4
@@ -61,21 +62,22 @@ __global__ void __launch_bounds__(256) symv_kernel(const double* __restrict__ B,
 // partial[c][i] = sum over the c-th chunk of columns of Z[i, j] u[j]   (Z column-major, pitch ld): thread = row,
 // so every load is coalesced; the chunks are summed in a fixed order by gemv_n_reduce_kernel (deterministic)
 constexpr int kGemvChunks = 64;
-__global__ void __launch_bounds__(256) gemv_n_partial_kernel(const double* __restrict__ Z, int64_t n, int64_t ld,
-                                                             const double* __restrict__ u, double* __restrict__ partial) {
+__global__ void __launch_bounds__(256) gemv_n_partial_kernel(const double* __restrict__ Z, int64_t n, int64_t ncols,
+                                                             int64_t ld, const double* __restrict__ u,
+                                                             double* __restrict__ partial) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-  const int64_t cw = (n + kGemvChunks - 1) / kGemvChunks;
-  const int64_t j0 = static_cast<int64_t>(blockIdx.y) * cw, j1 = min(n, j0 + cw);
+  const int64_t cw = (ncols + kGemvChunks - 1) / kGemvChunks;
+  const int64_t j0 = min(ncols, static_cast<int64_t>(blockIdx.y) * cw), j1 = min(ncols, j0 + cw);
   if (i >= n) return;
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   int64_t j = j0;
   for (; j + 4 <= j1; j += 4) {
-    a0 = fma(Z[(j + 0) * ld + i], u[j + 0], a0);
-    a1 = fma(Z[(j + 1) * ld + i], u[j + 1], a1);
-    a2 = fma(Z[(j + 2) * ld + i], u[j + 2], a2);
-    a3 = fma(Z[(j + 3) * ld + i], u[j + 3], a3);
+    a0 = fma(Z[(j + 0) * ld + i], u ? u[j + 0] : 1.0, a0);
+    a1 = fma(Z[(j + 1) * ld + i], u ? u[j + 1] : 1.0, a1);
+    a2 = fma(Z[(j + 2) * ld + i], u ? u[j + 2] : 1.0, a2);
+    a3 = fma(Z[(j + 3) * ld + i], u ? u[j + 3] : 1.0, a3);
   }
-  for (; j < j1; ++j) a0 = fma(Z[j * ld + i], u[j], a0);
+  for (; j < j1; ++j) a0 = fma(Z[j * ld + i], u ? u[j] : 1.0, a0);
   partial[static_cast<int64_t>(blockIdx.y) * n + i] = (a0 + a1) + (a2 + a3);
 }
 __global__ void __launch_bounds__(256) gemv_n_reduce_kernel(const double* __restrict__ partial, int64_t n,
@@ -237,18 +239,17 @@ void tridiag_top(const std::vector<double>& a, const std::vector<double>& b, int
   }
 }
 
-}  // namespace
-
-bool lanczos_top_eigenpair(const double* B, int64_t n, int64_t ldb, bool gram, double tol, int max_iter, double* x_dev,
-                           double* theta_out, int* iters_out, int sm_count, cudaStream_t stream) {
-  if ((ldb & 1) != 0 || (reinterpret_cast<uintptr_t>(B) & 15u) != 0) return false;
+// Lanczos with full reorthogonalisation on the operator `apply(v, out)` (out = Op v, both device n-vectors, launched
+// on `stream`); Op symmetric positive semi-definite.
+template <typename Apply>
+static bool lanczos_core(int64_t n, Apply&& apply, double tol, int max_iter, double* x_dev, double* theta_out,
+                         int* iters_out, cudaStream_t stream) {
   const int m_max = static_cast<int>(std::min<int64_t>(max_iter, n - 1));
   if (m_max < 2) return false;
   const int64_t ldv = (n + 1) / 2 * 2;
   double *V = nullptr, *w = nullptr, *c = nullptr, *alpha = nullptr, *beta = nullptr, *sdev = nullptr;
-  double *u = nullptr, *partial = nullptr;  // gram operator: u = B' v, w = B u through chunk partials
   auto release = [&] {
-    for (double* p : {V, w, c, alpha, beta, sdev, u, partial})
+    for (double* p : {V, w, c, alpha, beta, sdev})
       if (p) cudaFreeAsync(p, stream);
   };
   try {
@@ -259,23 +260,7 @@ bool lanczos_top_eigenpair(const double* B, int64_t n, int64_t ldb, bool gram, d
     GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&beta), sizeof(double) * (m_max + 1), stream));
     GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&sdev), sizeof(double) * (m_max + 1), stream));
     GBM_CUDA(cudaMemsetAsync(w, 0, sizeof(double) * ldv, stream));
-    if (gram) {
-      GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&u), sizeof(double) * ldv, stream));
-      GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&partial), sizeof(double) * n * kGemvChunks, stream));
-    }
     const unsigned row_blocks = static_cast<unsigned>((n + 255) / 256);
-    const unsigned symv_grid = static_cast<unsigned>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(sm_count) * 8));
-    // out = Op v:  Op = B (symmetric), or Op = B B' for the gram operator (B = Z: the eigenvector of Z Z' without
-    // ever forming it: two passes over Z per step instead of one pass over Z Z' plus an n^3 SYRK up front)
-    auto apply = [&](const double* v, double* out) {
-      if (!gram) {
-        symv_kernel<<<symv_grid, 256, 0, stream>>>(B, n, ldb, v, out);
-      } else {
-        symv_kernel<<<symv_grid, 256, 0, stream>>>(B, n, ldb, v, u);  // u[j] = B[:, j] . v
-        gemv_n_partial_kernel<<<dim3(row_blocks, kGemvChunks), 256, 0, stream>>>(B, n, ldb, u, partial);
-        gemv_n_reduce_kernel<<<row_blocks, 256, 0, stream>>>(partial, n, out);
-      }
-    };
     start_vector_kernel<<<row_blocks, 256, 0, stream>>>(w, n);
     norm_next_kernel<<<1, 256, 0, stream>>>(w, n, V, beta, m_max);  // V[:, 0] = unit start vector (beta slot unused)
 
@@ -313,7 +298,7 @@ bool lanczos_top_eigenpair(const double* B, int64_t n, int64_t ldb, bool gram, d
       GBM_CUDA(cudaMemcpyAsync(sdev, s.data(), sizeof(double) * m, cudaMemcpyHostToDevice, stream));
       combine_kernel<<<row_blocks, 256, 0, stream>>>(V, n, ldv, m, sdev, w);
       norm_next_kernel<<<1, 256, 0, stream>>>(w, n, x_dev, beta, 0);  // unit norm
-      // explicit residual ||B x - theta x|| as the final word
+      // explicit residual ||Op x - theta x|| as the final word
       apply(x_dev, w);
       GBM_CUDA(cudaGetLastError());
       std::vector<double> hx(n), hy(n);
@@ -337,6 +322,69 @@ bool lanczos_top_eigenpair(const double* B, int64_t n, int64_t ldb, bool gram, d
     release();
     throw;
   }
+}
+
+// stream-ordered scratch vector
+struct Scratch {
+  double* p = nullptr;
+  cudaStream_t s;
+  Scratch(size_t count, cudaStream_t stream) : s(stream) {
+    if (count) GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), sizeof(double) * count, stream));
+  }
+  ~Scratch() {
+    if (p) cudaFreeAsync(p, s);
+  }
+  Scratch(const Scratch&) = delete;
+  Scratch& operator=(const Scratch&) = delete;
+};
+
+}  // namespace
+
+bool lanczos_top_eigenpair(const double* B, int64_t n, int64_t ldb, bool gram, double tol, int max_iter, double* x_dev,
+                           double* theta_out, int* iters_out, int sm_count, cudaStream_t stream) {
+  if ((ldb & 1) != 0 || (reinterpret_cast<uintptr_t>(B) & 15u) != 0) return false;
+  const int64_t ldv = (n + 1) / 2 * 2;
+  // gram operator: u = B' v, w = B u through chunk partials
+  Scratch u(gram ? ldv : 0, stream), partial(gram ? static_cast<size_t>(n) * kGemvChunks : 0, stream);
+  const unsigned row_blocks = static_cast<unsigned>((n + 255) / 256);
+  const unsigned symv_grid = static_cast<unsigned>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(sm_count) * 8));
+  // out = Op v:  Op = B (symmetric), or Op = B B' for the gram operator (B = Z: the eigenvector of Z Z' without
+  // ever forming it: two passes over Z per step instead of one pass over Z Z' plus an n^3 SYRK up front)
+  auto apply = [&](const double* v, double* out) {
+    if (!gram) {
+      symv_kernel<<<symv_grid, 256, 0, stream>>>(B, n, n, ldb, v, out);
+    } else {
+      symv_kernel<<<symv_grid, 256, 0, stream>>>(B, n, n, ldb, v, u.p);  // u[j] = B[:, j] . v
+      gemv_n_partial_kernel<<<dim3(row_blocks, kGemvChunks), 256, 0, stream>>>(B, n, n, ldb, u.p, partial.p);
+      gemv_n_reduce_kernel<<<row_blocks, 256, 0, stream>>>(partial.p, n, out);
+    }
+  };
+  return lanczos_core(n, apply, tol, max_iter, x_dev, theta_out, iters_out, stream);
+}
+
+void block_row_sums(const double* Zg, int64_t n, int64_t nc, int64_t ld, double* rowsum, cudaStream_t stream) {
+  Scratch partial(static_cast<size_t>(n) * kGemvChunks, stream);
+  const unsigned row_blocks = static_cast<unsigned>((n + 255) / 256);
+  gemv_n_partial_kernel<<<dim3(row_blocks, kGemvChunks), 256, 0, stream>>>(Zg, n, nc, ld, nullptr, partial.p);
+  gemv_n_reduce_kernel<<<row_blocks, 256, 0, stream>>>(partial.p, n, rowsum);
+  GBM_CUDA(cudaGetLastError());
+}
+
+bool lanczos_top_singular_sharded(const double* Zg, int64_t n, int64_t nc, int64_t ld, ShardedAllReduce* ar, double tol,
+                                  int max_iter, double* x_dev, double* theta_out, int* iters_out, int sm_count,
+                                  cudaStream_t stream) {
+  if ((ld & 1) != 0 || (reinterpret_cast<uintptr_t>(Zg) & 15u) != 0) return false;
+  Scratch u(static_cast<size_t>(std::max<int64_t>(nc, 1)), stream), partial(static_cast<size_t>(n) * kGemvChunks, stream);
+  const unsigned row_blocks = static_cast<unsigned>((n + 255) / 256);
+  const unsigned symv_grid =
+      static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((nc + 7) / 8, static_cast<int64_t>(sm_count) * 8)));
+  auto apply = [&](const double* v, double* out) {
+    if (nc > 0) symv_kernel<<<symv_grid, 256, 0, stream>>>(Zg, n, nc, ld, v, u.p);  // u = Zg' v
+    gemv_n_partial_kernel<<<dim3(row_blocks, kGemvChunks), 256, 0, stream>>>(Zg, n, nc, ld, u.p, partial.p);
+    gemv_n_reduce_kernel<<<row_blocks, 256, 0, stream>>>(partial.p, n, out);         // this rank's Zg u
+    ar->sum(out, n);                                                                   // sum over the ranks
+  };
+  return lanczos_core(n, apply, tol, max_iter, x_dev, theta_out, iters_out, stream);
 }
 
 }  // namespace gbm

@@ -21,13 +21,13 @@ __global__ void __launch_bounds__(256)
     col[i] = (col[i] - mu) / sd;  // a true division, as the reference's ./
 }
 
-void launch_k_standardise(double* K, int64_t n, int64_t ld, const double* colmean, const double* colsd,
+void launch_k_standardise(double* K, int64_t n, int64_t ncols, int64_t ld, const double* colmean, const double* colsd,
                           cudaStream_t stream) {
-  if (n <= 0) return;
+  if (n <= 0 || ncols <= 0) return;
   unsigned gx = static_cast<unsigned>((n + 255) / 256);
   if (gx > 8) gx = 8;
-  for (int64_t j0 = 0; j0 < n; j0 += 65535) {
-    const unsigned gy = static_cast<unsigned>(n - j0 < 65535 ? n - j0 : 65535);
+  for (int64_t j0 = 0; j0 < ncols; j0 += 65535) {
+    const unsigned gy = static_cast<unsigned>(ncols - j0 < 65535 ? ncols - j0 : 65535);
     k_standardise_kernel<<<dim3(gx, gy), 256, 0, stream>>>(K + j0 * ld, n, ld, colmean + j0, colsd + j0);
   }
   GBM_CUDA(cudaGetLastError());
@@ -56,6 +56,29 @@ __global__ void __launch_bounds__(128)
 void launch_row_centre(const double* Ks, double* Z, int64_t n, int64_t ld, cudaStream_t stream) {
   if (n <= 0) return;
   row_centre_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, stream>>>(Ks, Z, n, ld);
+  GBM_CUDA(cudaGetLastError());
+}
+
+// Z[i, j] -= rowmean[i] on an n x ncols column block (the row-centring step when the columns of Kstd are
+// sharded over GPUs: the row sums are all-reduced first)
+__global__ void __launch_bounds__(256)
+    row_shift_kernel(double* __restrict__ Z, int64_t n, int64_t ld, const double* __restrict__ rowsum, double inv_cols) {
+  const int64_t j = blockIdx.y;
+  double* col = Z + j * ld;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    col[i] -= rowsum[i] * inv_cols;
+}
+
+void launch_row_shift(double* Z, int64_t n, int64_t ncols, int64_t ld, const double* rowsum, double inv_cols,
+                      cudaStream_t stream) {
+  if (n <= 0 || ncols <= 0) return;
+  unsigned gx = static_cast<unsigned>((n + 255) / 256);
+  if (gx > 8) gx = 8;
+  for (int64_t j0 = 0; j0 < ncols; j0 += 65535) {
+    const unsigned gy = static_cast<unsigned>(ncols - j0 < 65535 ? ncols - j0 : 65535);
+    row_shift_kernel<<<dim3(gx, gy), 256, 0, stream>>>(Z + j0 * ld, n, ld, rowsum, inv_cols);
+  }
   GBM_CUDA(cudaGetLastError());
 }
 

@@ -17,7 +17,7 @@ _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(_PKG_DIR, "libgbm_b200.so")
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 
-ABI_VERSION = 2  # GBM_ABI_VERSION of include/gbm_b200.h
+ABI_VERSION = 3  # GBM_ABI_VERSION of include/gbm_b200.h
 GBM_OK = 0
 GBM_ERR_ARGUMENT = 1
 GBM_ERR_RUNTIME = 2
@@ -42,6 +42,17 @@ class ErrorException(RuntimeError):
 
 class CudaError(RuntimeError):
     """CUDA / cuSOLVER failure, or no usable B200 (GBM_ERR_CUDA / NOT_INITIALISED)."""
+
+
+class GwasTiming(ctypes.Structure):
+    """gbm_gwas_timing of include/gbm_b200.h"""
+    _fields_ = [("colstats_ms", c_double), ("grm_ms", c_double), ("allreduce_ms", c_double), ("kstd_pc1_ms", c_double),
+                ("eig_ms", c_double), ("scan_ms", c_double), ("gather_ms", c_double), ("total_ms", c_double),
+                ("grm_tflops", c_double), ("scan_kernel_ms", c_double), ("launches", c_int64),
+                ("ploidy", ctypes.c_int32), ("lanczos_steps", ctypes.c_int32)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 class Timing(ctypes.Structure):
@@ -96,6 +107,24 @@ SIGNATURES = {
                                            _P, _P, _P, POINTER(c_int64)]),
     "gbm_transform1_apply": (c_int, [c_void_p, c_int, c_double, c_int, _P, c_int64, _P, c_int64]),
     "gbm_transform2_apply": (c_int, [c_void_p, c_int, c_double, c_int, _P, c_int64, _P, c_int64]),
+    "gbm_group_create_local": (c_int, [c_int, POINTER(c_int), POINTER(c_void_p)]),
+    "gbm_group_unique_id": (c_int, [_P]),
+    "gbm_group_create_rank": (c_int, [_P, c_int, c_int, POINTER(c_void_p)]),
+    "gbm_group_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "gbm_group_free": (c_int, [c_void_p]),
+    "gbm_sharded_upload": (c_int, [c_void_p, _P, c_int64, c_int64, c_int64, c_int, POINTER(c_void_p), POINTER(c_int)]),
+    "gbm_sharded_generate": (c_int, [c_void_p, c_uint64, c_int64, c_int64, c_int, c_int, POINTER(c_void_p), POINTER(c_int)]),
+    "gbm_sharded_adopt": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p)]),
+    "gbm_sharded_info": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64),
+                                 POINTER(c_int)]),
+    "gbm_sharded_free": (c_int, [c_void_p]),
+    "gbm_sharded_colstats": (c_int, [c_void_p, _P, _P, _P, _P, _P, POINTER(c_int64), POINTER(c_double)]),
+    "gbm_sharded_grm": (c_int, [c_void_p, c_int, c_int, c_int, _P, POINTER(c_double)]),
+    "gbm_sharded_kstd_pc1": (c_int, [c_void_p, _P, _P, POINTER(c_double)]),
+    "gbm_sharded_scan": (c_int, [c_void_p, _P, c_int64, c_int64, _P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P,
+                                 _P]),
+    "gbm_sharded_gwas": (c_int, [c_void_p, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, POINTER(c_int64), _P,
+                                 POINTER(GwasTiming)]),
     "gbm_neglog10_sf": (c_int, [_P, c_int64, c_int, c_double, _P]),
     "gbm_measure_copy_bandwidth": (c_int, [c_int64, c_int, POINTER(c_double)]),
 }

@@ -19,8 +19,11 @@
  *    pinned) or a DEVICE pointer of the selected GPU; the library tells them apart
  *    (unified virtual addressing).  Host pointers are never retained after return.
  *  - device memory is library-owned behind the opaque gbm_matrix handle.
- *  - one process drives one GPU (gbm_init(device)); multi-GPU runs use one process per GPU
- *    and shard markers by column block (gbm_grm_accumulate + an all-reduce by the host).
+ *  - gbm_init(device) selects one GPU for the single-GPU entry points.  Multi-GPU runs go through a
+ *    gbm_group (section "multi-GPU" below): markers sharded by column block over the GPUs of one box,
+ *    either all driven by this process (gbm_group_create_local: one host thread per GPU inside the
+ *    library, what a Julia session uses) or one process per GPU (gbm_group_create_rank: torchrun / MPI).
+ *    NCCL lives inside the library; the caller never issues a collective.
  *  - there is no CPU fallback: without a CUDA device every compute call fails.
  */
 #ifndef GBM_B200_H
@@ -32,7 +35,7 @@
 extern "C" {
 #endif
 
-#define GBM_ABI_VERSION 2
+#define GBM_ABI_VERSION 3
 
 #define GBM_OK 0
 #define GBM_ERR_ARGUMENT 1 /* Julia ArgumentError */
@@ -260,6 +263,83 @@ int gbm_transform1_apply(const gbm_matrix* m, int f, double eps, int use_abs, co
                          double* T, int64_t ldt);
 int gbm_transform2_apply(const gbm_matrix* m, int f, double eps, int use_abs, const int64_t* counters, int64_t count,
                          double* T, int64_t ldt);
+
+/* ---- multi-GPU: marker shards over the GPUs of one box --------------------------------
+ * The reference's only parallel axis is the marker loop (`Threads.@threads for j = 1:l`,
+ * /root/reference/src/gwas.jl:239, :363); its B200 equivalent is one contiguous column block
+ * [p r / W, p (r + 1) / W) per GPU r of W.  gwasprep's pieces then need exactly these exchanges, all done inside
+ * the library over NCCL / NVLink:
+ *   - GRM (gwas.jl:120, :124): every GPU contracts its own markers, ONE all-reduce sums the n x n partials;
+ *   - K standardisation + PC1 (gwas.jl:130, :234, :357): the columns of K are sharded, one all-reduce of the
+ *     row sums, then one all-reduce of an n-vector per Lanczos step;
+ *   - fixed-locus filter (gwas.jl:113): local; idx_cols is the shard-order concatenation, offsets from the
+ *     prefix of the per-shard counts;
+ *   - marker loop (gwas.jl:239-249, :363-389): no exchange, results gathered in locus order.
+ * Two ways to form a group, same entry points afterwards:
+ *   gbm_group_create_local : this process drives n_gpus GPUs (devices[] or 0 .. n_gpus-1), one library-owned
+ *                            host thread and State per GPU, ncclCommInitAll.  No gbm_init needed.
+ *   gbm_group_create_rank  : one process per GPU; the GPU is the one of gbm_init.  Rank 0 makes the 128-byte id
+ *                            with gbm_group_unique_id and hands it to the others (torch.distributed, MPI, a file);
+ *                            every rank then calls gbm_group_create_rank (collective).
+ * Every gbm_sharded_* call is collective over the group: all processes call it with the same arguments.  Host
+ * outputs are full-length (all p markers, locus order) and are filled on EVERY process. */
+typedef struct gbm_group gbm_group;
+typedef struct gbm_sharded gbm_sharded; /* an n x p genotype matrix, column blocks resident on the group's GPUs */
+#define GBM_GROUP_ID_BYTES 128
+int gbm_group_create_local(int n_gpus, const int* devices, gbm_group** out);
+int gbm_group_unique_id(void* id);
+int gbm_group_create_rank(const void* id, int world, int rank, gbm_group** out);
+int gbm_group_info(const gbm_group* g, int* world, int* n_local, int* first_rank);
+int gbm_group_free(gbm_group* g);
+
+/* A: the WHOLE n x p host matrix (every process passes the same matrix; each uploads the blocks of its own GPUs).
+ * compact != 0: host cores pack to 1-byte dosage codes on the way when every element of every block is a code
+ * (*packed = 1), otherwise Float64 slabs everywhere (*packed = 0).  This is extractxyetc's
+ * `G = allele_frequencies[...]` copy (/root/reference/src/prediction.jl:129) landing sharded in HBM. */
+int gbm_sharded_upload(gbm_group* g, const double* A, int64_t n, int64_t p, int64_t lda, int compact,
+                       gbm_sharded** out, int* packed);
+/* synthetic columns 0 .. p-1 of the counter-based generator, each block made on its GPU; pack != 0 converts
+ * to dosage codes when every block packs */
+int gbm_sharded_generate(gbm_group* g, uint64_t seed, int64_t n, int64_t p, int kind, int pack, gbm_sharded** out,
+                         int* packed);
+/* wrap blocks that are already resident: local[i] is the block of this process' i-th GPU (same n everywhere, any
+ * column counts; blocks are ordered by rank).  The handles stay owned by the caller and must outlive *out. */
+int gbm_sharded_adopt(gbm_group* g, gbm_matrix* const* local, gbm_sharded** out);
+/* first_col / ncols: n_local entries, the column ranges of this process' blocks */
+int gbm_sharded_info(const gbm_sharded* m, int64_t* n, int64_t* p, int64_t* first_col, int64_t* ncols, int* packed);
+int gbm_sharded_free(gbm_sharded* m);
+
+/* gbm_colstats over the shards; mean / sd / min_nonzero / keep have length p (all markers), idx_cols has room for
+ * p entries: 1-based, ascending, global (gwas.jl:112-113, :119) */
+int gbm_sharded_colstats(gbm_sharded* m, double* mean, double* sd, double* min_nonzero, uint8_t* keep,
+                         int64_t* idx_cols, int64_t* n_keep, double* min_nonzero_kept);
+/* gbm_grm over the shards: per-GPU partials, one all-reduce, scale + mirror.  K (host, n x n) nullable: the GRM then
+ * only stays resident on the GPUs for gbm_sharded_kstd_pc1.  tflops: n(n+1)p / (slowest GPU's contraction + the
+ * all-reduce), i.e. the aggregate rate of the group. */
+int gbm_sharded_grm(gbm_sharded* m, int grm_type, int ploidy, int flags, double* K, double* tflops);
+/* gbm_kstd_pc1 on the GRM left resident by gbm_sharded_grm (K = NULL) or on K (host, n x n, every process the same):
+ * columns of K sharded, Lanczos with one n-vector all-reduce per step.  pc1: host, n. */
+int gbm_sharded_kstd_pc1(gbm_sharded* m, const double* K, double* pc1, double* eig_ms);
+/* gbm_scan over the shards: outputs p x T column-major (ld p) / length p, host, on every process */
+int gbm_sharded_scan(gbm_sharded* m, const double* Y, int64_t T, int64_t ldy, const double* C, int64_t k, int64_t ldc,
+                     int model, int flags, double* beta, double* se, double* stat, double* neglog10p, double* mean,
+                     double* sd, uint8_t* keep);
+
+/* The whole of gwasols (gwas.jl:206-259) / gwaslmm (:329-399) after extractxyetc, in one collective call:
+ * filter + ploidy probe, GRM (+ all-reduce), K standardisation, PC1, marker scan with [1, PC1], gather.
+ * y: n, used as given (the caller standardises, gwas.jl:128).  grm_type GBM_GRM_PLOIDY_AWARE infers the ploidy as
+ * gwas.jl:119 does.  Outputs (host, nullable): stat / beta / se / neglog10p / mean / sd / keep of length p in locus
+ * order (NaN for filtered or degenerate markers), idx_cols (room for p), pc1 (n). */
+typedef struct gbm_gwas_timing {
+  double colstats_ms, grm_ms, allreduce_ms, kstd_pc1_ms, eig_ms, scan_ms, gather_ms, total_ms; /* host wall clock */
+  double grm_tflops;      /* n(n+1)p / (grm_ms + allreduce_ms): aggregate of the group */
+  double scan_kernel_ms;  /* slowest GPU's streaming kernel (CUDA events) */
+  int64_t launches;       /* kernels launched by this process */
+  int32_t ploidy, lanczos_steps;
+} gbm_gwas_timing;
+int gbm_sharded_gwas(gbm_sharded* m, const double* y, int model, int grm_type, int flags, double* stat, double* beta,
+                     double* se, double* neglog10p, double* mean, double* sd, uint8_t* keep, int64_t* idx_cols,
+                     int64_t* n_keep, double* pc1, gbm_gwas_timing* timing);
 
 /* -log10 upper-tail probabilities on the device (log-space; finite where 1 - cdf saturates) */
 int gbm_neglog10_sf(const double* stat, int64_t len, int dist /*0: TDist(df), 1: Normal*/, double df, double* out);

@@ -11,6 +11,8 @@ for p in (ROOT, os.path.join(ROOT, "genomicbreedingmodels.jl_b200")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run by the driver with -m gpu)")
+    config.addinivalue_line("markers", "multigpu: needs at least 2 B200s on the box (gpurun --gpus N); only generated "
+                                       "when they are visible, always carries the gpu marker too")
 
 
 @pytest.fixture(scope="session")

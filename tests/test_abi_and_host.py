@@ -33,7 +33,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     lib = gbm_b200.load()
     from gbm_b200 import _lib as L
 
-    assert lib.gbm_abi_version() == L.ABI_VERSION == 2
+    assert lib.gbm_abi_version() == L.ABI_VERSION == 3
 
 
 def test_library_is_sm100a_with_tma_and_dmma():
