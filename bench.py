@@ -58,7 +58,10 @@ def parse_args():
     ap.add_argument("--no-multitrait", action="store_true", help="skip the 20-trait batch on the resident shard")
     ap.add_argument("--no-transform", action="store_true", help="skip the pairwise transformation screen (SURVEY 8f-4)")
     ap.add_argument("--transform-l", type=int, default=8192, help="loci in the pairwise screen (l^2 regressions)")
-    ap.add_argument("--pipeline", action="store_true", help="also time the whole gwaslmm pipeline (GRM + PC1) once")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="skip the whole sharded gwaslmm (filter + GRM + all-reduce + PC1 + scan + gather) through gbm_sharded_gwas")
+    ap.add_argument("--pipeline-detail", action="store_true",
+                    help="N=1 only: also the phase-by-phase single-GPU pipeline incl. ingestion from pageable host memory")
     ap.add_argument("--lmm-markers", type=int, default=0,
                     help="also run the GRM-covariance LMM engine (eigen-rotation GEMM + per-marker delta search) "
                          "on this many markers")
@@ -477,7 +480,15 @@ def main():
         del host
 
     plan.free()
-    dm.free()
+    # ---- the whole sharded gwaslmm (north_star's target run), every rank takes part: ONE collective call into the
+    #      library (gbm_sharded_gwas), NCCL inside it ----
+    if not args.no_pipeline:
+        res = run_pipeline_group(gbm_b200, _lib, dm, n, p, ys, world, rank)
+        if rank == 0:
+            line["pipeline"] = res
+        dm = None
+    if dm is not None:
+        dm.free()
 
     if rank == 0 and not args.no_grm:
         gn, gp = args.grm_n, args.grm_p
@@ -528,12 +539,8 @@ def main():
     if rank == 0 and not args.no_transform:
         line["transform2"] = run_transform2(gbm_b200, n, args.transform_l)
 
-    if args.pipeline and world > 1:  # every rank takes part
-        res = run_pipeline_sharded(gbm_b200, _lib, n, p, j0, p_loc, ys, world)
-        if rank == 0:
-            line["pipeline_sharded"] = res
-    elif rank == 0 and args.pipeline:
-        line["pipeline"] = run_pipeline(gbm_b200, _lib, n, p_loc, j0, ys)
+    if rank == 0 and world == 1 and args.pipeline_detail:
+        line["pipeline_detail"] = run_pipeline(gbm_b200, _lib, n, p_loc, j0, ys)
 
     if rank == 0 and args.lmm_markers > 0:
         line["lmm_rotation_engine"] = run_lmm(gbm_b200, _lib, n, args.lmm_markers)
@@ -659,82 +666,68 @@ def run_pipeline(gbm_b200, _lib, n, p_loc, j0, ys):
     return out
 
 
-def run_pipeline_sharded(gbm_b200, _lib, n, p, j0, p_loc, ys, world):
-    """Whole gwaslmm on all ranks (north_star's target run): each rank holds its column block; colstats and
-    filter local, GRM partials summed with ONE NCCL all-reduce, K standardisation + PC1 on every rank
-    (deterministic, no broadcast), scan local, statistics gathered in locus order on every rank.  Uses the
-    packed (1-byte) copy when the block packs.  Times are max over ranks (barrier on both sides)."""
+def run_pipeline_group(gbm_b200, _lib, dm, n, p, ys, world, rank):
+    """Whole gwaslmm (/root/reference/src/gwas.jl:329-399 after extractxyetc) on all ranks through the library's
+    group API: gbm_group_create_rank + gbm_sharded_adopt + gbm_sharded_gwas.  Each rank holds its column block;
+    filter local, GRM partials summed with ONE NCCL all-reduce, K standardisation + PC1 with the columns of K
+    sharded (one n-vector all-reduce per Lanczos step), scan local, results gathered in locus order on every
+    rank.  Both storages: Float64 slabs (FP64 DMMA GRM) and 1-byte dosage codes (u8 scan, tcgen05 INT8 GRM).
+    Times are the library's host wall clock per phase, max over ranks; the second (warm) call is reported.
+    Consumes dm."""
     import torch
     import torch.distributed as dist
 
-    from gbm_b200 import sharded
+    from gbm_b200 import multigpu
 
-    def sync():
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-
-    wm = gbm_b200.DeviceMatrix.generate(SEED, 256, 512, KIND_DIPLOID)  # one-off library initialisation
-    wK, _ = wm.grm(_lib.GRM_SIMPLE, 2, 0)
-    gbm_b200.kstd_pc1(wK, want_kstd=False)
-    wm.free()
-    dm = gbm_b200.DeviceMatrix.generate(SEED, n, p_loc, KIND_DIPLOID, col0=j0)
-    out = {"world": world, "n": n, "p": p}
+    grp = multigpu.Group.from_torch_distributed() if world > 1 else multigpu.Group.from_rank(multigpu.Group.unique_id(), 1, 0)
+    out = {"world": world, "n": n, "p": p, "api": "gbm_sharded_gwas (one collective call; NCCL inside libgbm_b200.so)"}
+    keys = ("colstats_ms", "grm_ms", "allreduce_ms", "kstd_pc1_ms", "eig_ms", "scan_ms", "gather_ms", "total_ms",
+            "scan_kernel_ms")
+    m = dm
     for storage in ("float64", "packed"):
-        m = dm
         if storage == "packed":
-            sync()
             t0 = time.perf_counter()
             m = dm.pack()
-            sync()
-            if m is None:
-                break
-            out_pack_s = time.perf_counter() - t0
+            pack_s = time.perf_counter() - t0
             dm.free()
-        sg = sharded.ShardedGWAS(m, p, j0)
-        ph = {}
+            ok = torch.tensor([0.0 if m is None else 1.0], device="cuda")
+            if world > 1:
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() < 0.5:
+                break
+        sm = multigpu.ShardedMatrix.adopt(grp, [m])
         for attempt in ("cold", "warm"):
-            sync()
-            t_all = time.perf_counter()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
             t0 = time.perf_counter()
-            st = m.colstats()
-            sync()
-            ph["colstats_s"] = time.perf_counter() - t0
-            t0 = time.perf_counter()
-            dK = sg.grm("simple")
-            sync()
-            ph["grm_incl_allreduce_s"] = time.perf_counter() - t0
-            t0 = time.perf_counter()
-            pc, eig_ms = gbm_b200.kstd_pc1_device(dK.data_ptr(), n)
-            sync()
-            ph["kstd_pc1_s"] = time.perf_counter() - t0
-            ph["eig_s"] = eig_ms * 1e-3
-            del dK
-            t0 = time.perf_counter()
-            res = m.scan(ys, pc[:, None], model=_lib.MODEL_LMM)
-            sync()
-            ph["scan_s"] = time.perf_counter() - t0
-            t0 = time.perf_counter()
-            idx = sharded.global_idx_cols(st["idx_cols"], j0)
-            z = sharded.gather_marker_results(res["stat"][:, 0], p)
-            nlp = sharded.gather_marker_results(res["neglog10p"][:, 0], p)
-            sync()
-            ph["gather_s"] = time.perf_counter() - t0
-            ph["total_s"] = time.perf_counter() - t_all
-        tt = torch.tensor([ph[k] for k in sorted(ph)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ph = {k: float(v) for k, v in zip(sorted(ph), tt.cpu())}
-        ph["markers_per_s_whole_gwaslmm"] = p / ph["total_s"]
+            res = sm.gwas(ys, model=_lib.MODEL_LMM, grm_type=_lib.GRM_SIMPLE)
+            wall = time.perf_counter() - t0
+            if attempt == "cold":
+                cold_total = res["timing"]["total_ms"]
+        tm = res["timing"]
+        tt = torch.tensor([tm[k] for k in keys] + [wall * 1e3, cold_total], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        vals = [float(v) for v in tt.cpu()]
+        ph = dict(zip(keys, vals[: len(keys)]))
+        ph["wall_ms_python_call"] = vals[len(keys)]
+        ph["first_call_total_ms"] = vals[len(keys) + 1]
+        ph["grm_tflops_aggregate_incl_allreduce"] = n * (n + 1.0) * p / ((ph["grm_ms"] + ph["allreduce_ms"]) * 1e-3) / 1e12
+        ph["markers_per_s_whole_gwaslmm"] = p / (ph["total_ms"] * 1e-3)
+        ph["lanczos_steps"] = tm["lanczos_steps"]
+        ph["launches_this_rank"] = tm["launches"]
+        idx = res["idx_cols"]
         ph["markers_kept"] = int(idx.size)
-        ph["max_neglog10p"] = float(np.nanmax(nlp[idx - 1]))
-        ph["sum_abs_z"] = float(np.nansum(np.abs(z[idx - 1])))  # a checksum to compare across GPU counts
+        ph["max_neglog10p"] = float(np.nanmax(res["neglog10p"][idx - 1]))
+        ph["sum_abs_z"] = float(np.nansum(np.abs(res["stat"][idx - 1])))  # a checksum to compare across GPU counts
         if storage == "packed":
-            ph["pack_s"] = out_pack_s
+            ph["pack_s"] = pack_s
         out[storage] = ph
+        sm.free()
     if m is not None:
         m.free()
-    else:
-        dm.free()
+    grp.free()
     return out
 
 

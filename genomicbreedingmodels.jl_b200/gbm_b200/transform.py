@@ -147,14 +147,29 @@ def transform2_screen_sharded(dm: DeviceMatrix, y, f, n_new: int, eps: float = _
 
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
-    r0, r1 = shard_bounds(dm.p, world, rank)
-    mine = (np.zeros(0, np.int64), np.zeros(0)) if r1 <= r0 else transform2_screen_rows(
-        dm, y, f, r0, r1, n_new, eps, use_abs, var_threshold, commutative)
-    parts = [mine]
+    _code(f, 2)
+    l = dm.p
+    if n_new > l * l:  # sortperm(...)[1:n_new] on a shorter vector (transformation.jl:425); same on every rank
+        raise _lib.ArgumentError(f"BoundsError: attempt to access {l * l}-element Vector{{Int64}} at index [1:{n_new}]")
+    r0, r1 = shard_bounds(l, world, rank)
+    # A failure on one rank only (NaN effects in its slab, out of memory) must not leave the others waiting in the
+    # collective: every rank reports (error, payload), and the first error is re-raised on ALL ranks -- the same
+    # ArgumentError the unsharded screen raises for a NaN effect anywhere.
+    err, mine = None, (np.zeros(0, np.int64), np.zeros(0))
+    try:
+        if r1 > r0:
+            mine = transform2_screen_rows(dm, y, f, r0, r1, n_new, eps, use_abs, var_threshold, commutative)
+    except Exception as e:  # noqa: BLE001 -- re-raised below on every rank
+        err = (type(e).__name__, str(e))
+    parts = [(err, mine)]
     if world > 1:
         parts = [None] * world
-        dist.all_gather_object(parts, mine, group=group)
-    return merge_screen_candidates(parts, n_new, eps)
+        dist.all_gather_object(parts, (err, mine), group=group)
+    for e, _ in parts:
+        if e is not None:
+            cls = {"ArgumentError": _lib.ArgumentError, "ErrorException": _lib.ErrorException}.get(e[0], _lib.CudaError)
+            raise cls(e[1])
+    return merge_screen_candidates([m for _, m in parts], n_new, eps)
 
 
 def transform1_apply(dm: DeviceMatrix, f, idx, eps: float = _EPS, use_abs: bool = False) -> np.ndarray:

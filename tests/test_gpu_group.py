@@ -213,3 +213,31 @@ def test_c_program_drives_the_group_through_the_abi_alone(gbm, n_gpus):
     assert ploidy == 4 and packed == 1
     assert np.array_equal(idx, prep.idx_cols)
     assert np.max(np.abs(z - want) / np.maximum(np.abs(want), 1e-3 * np.abs(want).max())) < 1e-9
+
+
+@pytest.mark.multigpu
+@pytest.mark.skipif(visible_gpus() < 2, reason="needs at least 2 GPUs on the box")
+def test_one_process_per_gpu_under_torchrun(gbm):
+    """tests/dist_gpu_check.py on every visible GPU: the RANK group (gbm_group_create_rank) against the oracle."""
+    import sys
+
+    import signal
+
+    n = visible_gpus()
+    port = 29600 + os.getpid() % 300
+    # own session: if a rank dies the others wait in NCCL for ever -- the whole process group is killed at the timeout
+    proc = subprocess.Popen([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                             "--master-addr", "127.0.0.1", "--master-port", str(port),
+                             os.path.join(ROOT, "tests", "dist_gpu_check.py")], stdout=subprocess.PIPE,
+                            stderr=subprocess.STDOUT, text=True, start_new_session=True)
+    try:
+        log, _ = proc.communicate(timeout=300)
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)
+        log, _ = proc.communicate()
+        log += "\n[killed at the 300 s timeout]"
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"dist_gpu_check_{n}gpu.log"), "w") as f:
+        f.write(log)
+    assert proc.returncode == 0, log[-3000:]
+    assert log.count("-> OK") == 2 and "FAIL" not in log, log[-3000:]
