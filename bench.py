@@ -60,6 +60,11 @@ def parse_args():
     ap.add_argument("--transform-l", type=int, default=8192, help="loci in the pairwise screen (l^2 regressions)")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="skip the whole sharded gwaslmm (filter + GRM + all-reduce + PC1 + scan + gather) through gbm_sharded_gwas")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs[3] / configs[4] sections")
+    ap.add_argument("--stream-markers", type=int, default=12_500,
+                    help="configs[4]: markers per rank and step in the host-resident sample (n = 20,000: 2 GB per rank)")
+    ap.add_argument("--no-whole-api", action="store_true",
+                    help="skip gwasols / gwaslmm(genomes, phenomes) -> Fit through the host mirror against the CPU whole function")
     ap.add_argument("--pipeline-detail", action="store_true",
                     help="N=1 only: also the phase-by-phase single-GPU pipeline incl. ingestion from pageable host memory")
     ap.add_argument("--lmm-markers", type=int, default=0,
@@ -192,6 +197,39 @@ def cpu_sample_rate(n: int, p: int, markers: int, reps: int = 1):
     return markers * reps / total, total, cbind.num_threads()
 
 
+def find_julia():
+    """A Julia runtime on this box: PATH first, then anything the driver may have installed under
+    baseline/_ref/.  None in the build image."""
+    import shutil
+
+    exe = shutil.which("julia")
+    if exe:
+        return exe
+    for root, _, files in os.walk(os.path.join(ROOT, "baseline", "_ref")):
+        if "julia" in files and os.access(os.path.join(root, "julia"), os.X_OK):
+            return os.path.join(root, "julia")
+    return None
+
+
+def julia_reference(model: str):
+    """The reference's own gwasols / gwaslmm on its own CPU-runnable case (BASELINE configs[0]: n=300, l=10,000)
+    through baseline/reference_gwas.jl, when Julia AND the package are there.  Returns a dict or a reason string."""
+    exe = find_julia()
+    if exe is None:
+        return "no `julia` on PATH or under baseline/_ref/"
+    try:
+        out = subprocess.run([exe, "--threads=auto,1", os.path.join(ROOT, "baseline", "reference_gwas.jl"), "300", "10000",
+                              model, "3"], capture_output=True, text=True, timeout=900)
+    except Exception as e:  # noqa: BLE001
+        return f"julia found at {exe} but the run failed: {e}"
+    for ln in out.stdout.splitlines():
+        if ln.startswith("reference_gwas "):
+            f = ln.split()
+            return {"julia": exe, "n": int(f[1]), "l": int(f[2]), "model": f[3], "seconds_per_call": float(f[4]),
+                    "threads": int(f[5]), "blas_threads": int(f[6]), "markers_per_s": int(f[2]) / float(f[4])}
+    return f"julia found at {exe} but GenomicBreedingModels did not run: {(out.stderr or out.stdout)[-300:]}"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -224,6 +262,11 @@ def run_reference(args):
         "gpu_launches": 0,
         "note": "reference is pure Julia; no Julia runtime in the image: oracle port timed (DESIGN.md)",
     }
+    jr = julia_reference(args.model)
+    line["julia_reference"] = jr  # the reference itself on BASELINE configs[0] when a runtime exists, else why not
+    if isinstance(jr, dict):
+        line["note"] = ("a Julia runtime was found: julia_reference holds the UNMODIFIED reference's own time on its "
+                        "CPU-runnable case (configs[0]); value stays the port on the configs[2] sample for comparability")
     print(json.dumps(line))
     return 0
 
@@ -392,103 +435,35 @@ def main():
             "note": "one pass over the genotypes; FP64 tensor pipe (DMMA m8n8k4) for the 22 dots per marker"}
 
     if not args.no_e2e:
-        pe = min(args.e2e_markers, p_loc)
-        host = torch.empty((pe, n), dtype=torch.float64, pin_memory=True)  # (p, n) C-order == n x p column-major
-        sub = gbm_b200.DeviceMatrix.generate(SEED, n, pe, KIND_DIPLOID, col0=j0)
-        info = sub.info()
-        assert info["lda"] == n
-        # device -> pinned host (untimed set-up)
-        import ctypes
-
-        cudart = ctypes.CDLL("libcudart.so.12")
-        rc = cudart.cudaMemcpy(ctypes.c_void_p(host.data_ptr()), ctypes.c_void_p(info["device_ptr"]),
-                               ctypes.c_size_t(8 * n * pe), ctypes.c_int(2))
-        assert rc == 0, rc
-        sub.free()
-        hout = {k: np.empty(pe) for k in ("beta", "se", "stat", "nlp", "mean", "sd")}
-        hkeep = np.empty(pe, dtype=np.uint8)
-
-        def e2e_step():
-            # plain Float64 copies (GBM_SCAN_HOST_NO_PACK): every byte of the host matrix crosses PCIe
-            _lib.check(lib.gbm_scan_host(_lib.ptr(host), n, pe, n, _lib.ptr(Y), 1, n, _lib.ptr(C), 1, n, model,
-                                         _lib.SCAN_HOST_NO_PACK, _lib.ptr(hout["beta"]), _lib.ptr(hout["se"]),
-                                         _lib.ptr(hout["stat"]), _lib.ptr(hout["nlp"]), _lib.ptr(hout["mean"]),
-                                         _lib.ptr(hout["sd"]), _lib.ptr(hkeep)))
-
-        e2e_step()
-        # the link itself: plain pinned H2D copy of the same buffer (reference point for e2e)
-        dev = torch.empty((pe, n), dtype=torch.float64, device="cuda")
-        dev.copy_(host, non_blocking=True)
-        torch.cuda.synchronize()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        dev.copy_(host, non_blocking=True)
-        ev1.record()
-        torch.cuda.synchronize()
-        h2d_peak = 8.0 * n * pe / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
-        del dev
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            e2e_step()
-        barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        if not args.no_packed:
-            def e2e_packed_step():
-                # the API's default: host cores pack each block to 1-byte codes before H2D
-                _lib.check(lib.gbm_scan_host(_lib.ptr(host), n, pe, n, _lib.ptr(Y), 1, n, _lib.ptr(C), 1, n, model,
-                                             0, _lib.ptr(hout["beta"]), _lib.ptr(hout["se"]),
-                                             _lib.ptr(hout["stat"]), _lib.ptr(hout["nlp"]), _lib.ptr(hout["mean"]),
-                                             _lib.ptr(hout["sd"]), _lib.ptr(hkeep)))
-
-            e2e_packed_step()
-            barrier()
-            t0 = time.perf_counter()
-            for _ in range(args.e2e_steps):
-                e2e_packed_step()
-            barrier()
-            dtp = time.perf_counter() - t0
-            tt = torch.tensor([dtp], dtype=torch.float64, device="cuda")
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dtp = float(tt.item())
-            ltm = _lib.last_timing()
-            e2e_packed = {"value": pe * world * args.e2e_steps / dtp, "unit": "markers/s",
-                          "h2d_bytes_per_step": ltm["h2d_bytes"] + 16 * n, "d2h_bytes_per_step": pe * (6 * 8 + 1),
-                          "host_threads": len(os.sched_getaffinity(0)),
-                          "blocks_as_codes": ltm["packed_blocks"], "blocks_packed_by_host": ltm["host_packed_blocks"],
-                          "note": "same Float64 host buffer through the default gbm_scan_host: column blocks are "
-                                  "handed out dynamically to the host cores (pack to 1-byte codes, exactness-checked, "
-                                  "then H2D) and to the copy engine (Float64 H2D, packed on the device); h2d bytes "
-                                  "are those of the last timed step"}
-        else:
-            e2e_packed = None
-        line["e2e_float64_copies"] = {"value": pe * world * args.e2e_steps / dt, "unit": "markers/s",
-                       "h2d_bytes_per_step": 8 * n * pe + 16 * n, "d2h_bytes_per_step": pe * (6 * 8 + 1),
-                       "sample": f"{pe} host-resident (pinned) markers per GPU per step through gbm_scan_host",
-                       "h2d_gbps": 8.0 * n * pe * args.e2e_steps / dt / 1e9, "h2d_link_gbps_plain_copy": h2d_peak,
-                       "bound": "PCIe host->device link: 8n bytes per marker must cross it",
-                       "note": "gbm_scan_host with GBM_SCAN_HOST_NO_PACK"}
-        if e2e_packed is not None:
-            line["e2e"] = dict(e2e_packed, sample=line["e2e_float64_copies"]["sample"])
-        else:
-            line["e2e"] = line["e2e_float64_copies"]
-        del host
+        line.update(run_e2e(args, gbm_b200, _lib, lib, n, p_loc, j0, world, model, Y, C, barrier))
 
     plan.free()
     # ---- the whole sharded gwaslmm (north_star's target run), every rank takes part: ONE collective call into the
     #      library (gbm_sharded_gwas), NCCL inside it ----
+    grp = None
+    if not (args.no_pipeline and args.no_configs):
+        from gbm_b200 import multigpu
+
+        grp = (multigpu.Group.from_torch_distributed() if world > 1
+               else multigpu.Group.from_rank(multigpu.Group.unique_id(), 1, 0))
     if not args.no_pipeline:
-        res = run_pipeline_group(gbm_b200, _lib, dm, n, p, ys, world, rank)
+        res = run_pipeline_group(gbm_b200, _lib, grp, dm, n, p, ys, world, rank)
         if rank == 0:
             line["pipeline"] = res
         dm = None
     if dm is not None:
         dm.free()
+    if not args.no_configs:
+        # BASELINE configs[3]: grmploidyaware + gwaslmm on tetraploid frequencies, n = 2,000 x p = 500,000
+        res = run_config3_tetraploid(gbm_b200, _lib, grp, world, rank, measured_peaks()[0])
+        if rank == 0:
+            line["config3_tetraploid"] = res
+        # BASELINE configs[4]: 20 traits x n = 20,000 x p = 2,000,000 streamed from host memory
+        res = run_config4_stream(args, gbm_b200, _lib, lib, world, rank, j0, barrier)
+        if rank == 0:
+            line["config4_multitrait_stream"] = res
+    if grp is not None:
+        grp.free()
 
     if rank == 0 and not args.no_grm:
         gn, gp = args.grm_n, args.grm_p
@@ -538,6 +513,9 @@ def main():
 
     if rank == 0 and not args.no_transform:
         line["transform2"] = run_transform2(gbm_b200, n, args.transform_l)
+
+    if rank == 0 and world == 1 and not args.no_whole_api:
+        line["whole_api"] = run_whole_api(gbm_b200, with_cpu=not args.no_cpu)
 
     if rank == 0 and world == 1 and args.pipeline_detail:
         line["pipeline_detail"] = run_pipeline(gbm_b200, _lib, n, p_loc, j0, ys)
@@ -666,7 +644,90 @@ def run_pipeline(gbm_b200, _lib, n, p_loc, j0, ys):
     return out
 
 
-def run_pipeline_group(gbm_b200, _lib, dm, n, p, ys, world, rank):
+def run_e2e(args, gbm_b200, _lib, lib, n, p_loc, j0, world, model, Y, C, barrier):
+    """The metric end to end through the C-ABI call a host makes with HOST buffers: gbm_scan_host(A, ...) -> results,
+    host -> device copies inside the timed region.  The headline `e2e` is timed from PAGEABLE memory -- what a Julia
+    `Array` (genomes.allele_frequencies) is -- through the API's default path (blocks that are all dosage codes
+    are packed to 1 byte per genotype by the host cores before crossing PCIe; the data here is diploid dosages).
+    Also reported: the same from pinned memory, and plain Float64 copies (GBM_SCAN_HOST_NO_PACK: what continuous
+    allele frequencies get) from pageable and from pinned memory, next to the link's plain-copy rate."""
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    pe = min(args.e2e_markers, p_loc)
+    pinned = torch.empty((pe, n), dtype=torch.float64, pin_memory=True)  # (p, n) C-order == n x p column-major
+    sub = gbm_b200.DeviceMatrix.generate(SEED, n, pe, KIND_DIPLOID, col0=j0)
+    info = sub.info()
+    assert info["lda"] == n
+    cudart = ctypes.CDLL("libcudart.so.12")
+    rc = cudart.cudaMemcpy(ctypes.c_void_p(pinned.data_ptr()), ctypes.c_void_p(info["device_ptr"]),
+                           ctypes.c_size_t(8 * n * pe), ctypes.c_int(2))  # device -> host, untimed set-up
+    assert rc == 0, rc
+    sub.free()
+    pageable = np.empty((pe, n))  # plain malloc'ed memory, like a Julia Array
+    pageable[:] = pinned.numpy()
+    hout = {k: np.zeros(pe) for k in ("beta", "se", "stat", "nlp", "mean", "sd")}
+    hkeep = np.zeros(pe, dtype=np.uint8)
+
+    def step(buf, flags):
+        _lib.check(lib.gbm_scan_host(_lib.ptr(buf), n, pe, n, _lib.ptr(Y), 1, n, _lib.ptr(C), 1, n, model, flags,
+                                     _lib.ptr(hout["beta"]), _lib.ptr(hout["se"]), _lib.ptr(hout["stat"]),
+                                     _lib.ptr(hout["nlp"]), _lib.ptr(hout["mean"]), _lib.ptr(hout["sd"]), _lib.ptr(hkeep)))
+
+    def timed(buf, flags):
+        step(buf, flags)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            step(buf, flags)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        ltm = _lib.last_timing()
+        return {"value": pe * world * args.e2e_steps / dt, "unit": "markers/s",
+                "h2d_bytes_per_step": ltm["h2d_bytes"] + 16 * n, "d2h_bytes_per_step": pe * (6 * 8 + 1),
+                "host_read_gbps": 8.0 * n * pe * world * args.e2e_steps / dt / 1e9,
+                "blocks_as_codes": ltm["packed_blocks"], "blocks_packed_by_host": ltm["host_packed_blocks"]}
+
+    # the link itself: plain pinned H2D copy of the same buffer (reference point)
+    dev = torch.empty((pe, n), dtype=torch.float64, device="cuda")
+    dev.copy_(pinned, non_blocking=True)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    dev.copy_(pinned, non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    h2d_peak = 8.0 * n * pe / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+    del dev
+    sample = f"{pe} host-resident markers per GPU per step through gbm_scan_host (n={n})"
+    out = {}
+    e = timed(pageable, 0)
+    e.update(sample=sample, host_memory="pageable (malloc), as a Julia Array", host_threads=len(os.sched_getaffinity(0)),
+             note="API default: column blocks handed out dynamically to the host cores (pack to 1-byte codes, exactness-"
+                  "checked, then H2D) and/or the copy engine (Float64 H2D, packed on the device)")
+    out["e2e"] = e
+    if not args.no_packed:
+        e = timed(pinned, 0)
+        e.update(sample=sample, host_memory="pinned")
+        out["e2e_pinned"] = e
+    for name, buf in (("e2e_float64_copies", pageable), ("e2e_float64_copies_pinned", pinned)):
+        e = timed(buf, _lib.SCAN_HOST_NO_PACK)
+        e.update(sample=sample, host_memory="pageable" if buf is pageable else "pinned",
+                 h2d_gbps_per_gpu=e["host_read_gbps"] / world, h2d_link_gbps_plain_copy=h2d_peak,
+                 frac_of_link=e["host_read_gbps"] / world / h2d_peak,
+                 bound="PCIe host->device link: 8n bytes per marker must cross it",
+                 note="gbm_scan_host with GBM_SCAN_HOST_NO_PACK: what continuous (non-dosage) allele frequencies get")
+        out[name] = e
+    return out
+
+
+def run_pipeline_group(gbm_b200, _lib, grp, dm, n, p, ys, world, rank):
     """Whole gwaslmm (/root/reference/src/gwas.jl:329-399 after extractxyetc) on all ranks through the library's
     group API: gbm_group_create_rank + gbm_sharded_adopt + gbm_sharded_gwas.  Each rank holds its column block;
     filter local, GRM partials summed with ONE NCCL all-reduce, K standardisation + PC1 with the columns of K
@@ -679,7 +740,6 @@ def run_pipeline_group(gbm_b200, _lib, dm, n, p, ys, world, rank):
 
     from gbm_b200 import multigpu
 
-    grp = multigpu.Group.from_torch_distributed() if world > 1 else multigpu.Group.from_rank(multigpu.Group.unique_id(), 1, 0)
     out = {"world": world, "n": n, "p": p, "api": "gbm_sharded_gwas (one collective call; NCCL inside libgbm_b200.so)"}
     keys = ("colstats_ms", "grm_ms", "allreduce_ms", "kstd_pc1_ms", "eig_ms", "scan_ms", "gather_ms", "total_ms",
             "scan_kernel_ms")
@@ -696,12 +756,15 @@ def run_pipeline_group(gbm_b200, _lib, dm, n, p, ys, world, rank):
             if ok.item() < 0.5:
                 break
         sm = multigpu.ShardedMatrix.adopt(grp, [m])
+        res = None
         for attempt in ("cold", "warm"):
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
             t0 = time.perf_counter()
-            res = sm.gwas(ys, model=_lib.MODEL_LMM, grm_type=_lib.GRM_SIMPLE)
+            # Fit needs b_hat = the statistic (gwas.jl:245, :385); -log10 p is what `verbose` plots (:252, :392).
+            # The output arrays of the first call are reused by the second (like a preallocated Fit.b_hat).
+            res = sm.gwas(ys, model=_lib.MODEL_LMM, grm_type=_lib.GRM_SIMPLE, want=("stat", "neglog10p"), out=res)
             wall = time.perf_counter() - t0
             if attempt == "cold":
                 cold_total = res["timing"]["total_ms"]
@@ -727,7 +790,226 @@ def run_pipeline_group(gbm_b200, _lib, dm, n, p, ys, world, rank):
         sm.free()
     if m is not None:
         m.free()
-    grp.free()
+    return out
+
+
+def run_config3_tetraploid(gbm_b200, _lib, grp, world, rank, hbm_peak):
+    """BASELINE configs[3]: grmploidyaware + gwaslmm, tetraploid allele frequencies, n = 2,000 x p = 500,000 -- the
+    ploidy-aware branch of gwasprep (/root/reference/src/gwas.jl:117-121: ploidy = Int(round(1 / minimum(G[G .!= 0]))),
+    then grmploidyaware) -- sharded over the ranks through gbm_sharded_generate + gbm_sharded_gwas.  Float64 storage
+    (FP64 DMMA GRM, Float64 scan) and dosage codes (INT8 GRM, u8 scan).  Parity at this full size:
+    tests/test_gpu_fullsize.py::test_config3_tetraploid_full_size."""
+    import torch
+    import torch.distributed as dist
+
+    from gbm_b200 import multigpu
+    from oracle import synth
+
+    n, p, kind = 2_000, 500_000, 1  # KIND_TETRAPLOID
+    y = synth.phenotype(SEED, n, p, kind)
+    ys = (y - y.mean()) / y.std(ddof=1)
+    out = {"workload": f"grmploidyaware + gwaslmm, tetraploid, n={n} p={p} (BASELINE configs[3]), {world} GPU(s)",
+           "reference": "gwas.jl:117-121 (ploidy-aware branch), :344-389"}
+    keys = ("colstats_ms", "grm_ms", "allreduce_ms", "kstd_pc1_ms", "eig_ms", "scan_ms", "gather_ms", "total_ms", "scan_kernel_ms")
+    for storage in ("float64", "packed"):
+        sm = multigpu.ShardedMatrix.generate(grp, SEED, n, p, kind, pack=(storage == "packed"))
+        if storage == "packed" and not sm.packed:
+            sm.free()
+            break
+        res = None
+        for _ in range(2):  # cold, warm
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            res = sm.gwas(ys, model=_lib.MODEL_LMM, grm_type=_lib.GRM_PLOIDY_AWARE, want=("stat", "neglog10p"), out=res)
+        tm = res["timing"]
+        tt = torch.tensor([tm[k] for k in keys], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ph = dict(zip(keys, (float(v) for v in tt.cpu())))
+        p_loc = max(sm.ncols)
+        bytes_per = 8.0 if storage == "float64" else 1.0
+        scan_gbps = bytes_per * n * p_loc / (ph["scan_kernel_ms"] * 1e-3) / 1e9
+        grm_tf = n * (n + 1.0) * p / ((ph["grm_ms"] + ph["allreduce_ms"]) * 1e-3) / 1e12
+        idx = res["idx_cols"]
+        ph.update(ploidy_inferred=tm["ploidy"], markers_kept=int(idx.size), lanczos_steps=tm["lanczos_steps"],
+                  markers_per_s_whole_gwaslmm=p / (ph["total_ms"] * 1e-3),
+                  grm_tflops_aggregate_incl_allreduce=grm_tf,
+                  max_neglog10p=float(np.nanmax(res["neglog10p"][idx - 1])),
+                  sum_abs_z=float(np.nansum(np.abs(res["stat"][idx - 1]))),
+                  roofline_scan={"bound": "hbm", "kernel": "scan_sums_kernel<16,2>" if storage == "float64" else "scan_sums_u8_kernel<16,2>",
+                                 "achieved": scan_gbps, "peak": hbm_peak, "unit": "GB/s", "frac": scan_gbps / hbm_peak,
+                                 "algorithmic_bytes_per_launch": bytes_per * n * p_loc,
+                                 "note": "slowest rank's streaming kernel; its columns are only 2,000 entries (16 KB) long"})
+        if storage == "float64":
+            ph["roofline_grm"] = {"bound": "tensor", "kernel": "grm_dmma_kernel", "achieved": grm_tf / world, "peak": 40.0,
+                                  "unit": "TFLOP/s", "frac": grm_tf / world / 40.0,
+                                  "peak_source": "B200 FP64 datasheet (MEASURED_PEAKS.json has no FP64 figure; cuBLAS DGEMM "
+                                                 "measured in this run is in grm.cublas_dgemm_8192_tflops)",
+                                  "note": "per GPU, n(n+1)p SYRK flops / (contraction + centring passes + all-reduce wall time)"}
+        out[storage] = ph
+        sm.free()
+    return out
+
+
+def run_config4_stream(args, gbm_b200, _lib, lib, world, rank, j0, barrier):
+    """BASELINE configs[4]: gwasols multi-trait batch, 20 traits x n = 20,000 x p = 2,000,000 SNPs streamed from host
+    memory (the marker loop /root/reference/src/gwas.jl:239-249 once per trait in the reference; here ONE pass over the
+    genotypes for all 20 traits, scan_sums_mt_kernel on the FP64 tensor pipe per column block).  The whole matrix is
+    320 GB of Float64; each rank streams a bounded host-resident sample of its share per step through gbm_scan_host
+    (PAGEABLE memory) and the full job's time is the extrapolation 2,000,000 / rate.  Float64 copies are PCIe-bound:
+    reported as a fraction of the link's plain pinned-copy rate measured in the same run."""
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    n, T, p_total = 20_000, 20, 2_000_000
+    pe = args.stream_markers
+    rng = np.random.default_rng(11)
+    Y = np.asfortranarray(rng.normal(size=(n, T)))
+    C = rng.normal(size=(n, 1))
+    C -= C.mean()
+    sub = gbm_b200.DeviceMatrix.generate(SEED, n, pe, KIND_DIPLOID, col0=rank * pe)
+    info = sub.info()
+    pinned = torch.empty((pe, n), dtype=torch.float64, pin_memory=True)
+    cudart = ctypes.CDLL("libcudart.so.12")
+    assert cudart.cudaMemcpy(ctypes.c_void_p(pinned.data_ptr()), ctypes.c_void_p(info["device_ptr"]),
+                             ctypes.c_size_t(8 * n * pe), ctypes.c_int(2)) == 0
+    # the same block resident: device-only rate of the 20-trait kernel at this n
+    plan = gbm_b200.ScanPlan(sub, Y, C, model=_lib.MODEL_OLS)
+    dstat = torch.empty(pe * T, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        plan.run(stat=dstat)
+    tm = plan.run(stat=dstat)
+    plan.free()
+    sub.free()
+    del dstat
+    host = np.empty((pe, n))
+    host[:] = pinned.numpy()
+    stat = np.zeros((T, pe))  # p x T column-major
+    nlp = np.zeros((T, pe))
+
+    def step(buf, flags):
+        _lib.check(lib.gbm_scan_host(_lib.ptr(buf), n, pe, n, _lib.ptr(Y), T, n, _lib.ptr(C), 1, n, _lib.MODEL_OLS, flags,
+                                     None, None, _lib.ptr(stat), _lib.ptr(nlp), None, None, None))
+
+    def timed(buf, flags, steps=2):
+        step(buf, flags)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step(buf, flags)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        ltm = _lib.last_timing()
+        rate = pe * world * steps / dt
+        return {"markers_per_s": rate, "marker_trait_tests_per_s": rate * T, "estimated_full_job_s": p_total / rate,
+                "host_read_gbps_per_gpu": 8.0 * n * pe * steps / dt / 1e9, "h2d_bytes_per_step": ltm["h2d_bytes"],
+                "blocks_as_codes": ltm["packed_blocks"]}
+
+    dev = torch.empty((pe, n), dtype=torch.float64, device="cuda")
+    dev.copy_(pinned, non_blocking=True)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    dev.copy_(pinned, non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    link = 8.0 * n * pe / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+    del dev
+    out = {"workload": f"gwasols batch: {T} traits x n={n} x p={p_total} streamed from host memory over {world} GPU(s) "
+                       f"(BASELINE configs[4]); sample: {pe} markers per rank per step ({8e-9 * n * pe:.1f} GB of Float64)",
+           "resident_block": {"kernel_ms": tm["kernel_ms"], "sums_kernel_ms": tm["main_ms"],
+                              "markers_per_s_per_gpu": pe / (tm["kernel_ms"] * 1e-3),
+                              "hbm_GBps": 8.0 * n * pe / (tm["main_ms"] * 1e-3) / 1e9,
+                              "dmma_tflops": 2.0 * n * pe * 8 * 3 / (tm["main_ms"] * 1e-3) / 1e12},
+           "h2d_link_gbps_plain_pinned_copy": link}
+    e = timed(host, _lib.SCAN_HOST_NO_PACK)
+    e.update(host_memory="pageable", frac_of_link=e["host_read_gbps_per_gpu"] / link,
+             roofline={"bound": "pcie", "achieved": e["host_read_gbps_per_gpu"], "peak": link, "unit": "GB/s per GPU",
+                       "frac": e["host_read_gbps_per_gpu"] / link, "algorithmic_bytes_per_marker": 8 * n})
+    out["float64_copies"] = e
+    e = timed(pinned, _lib.SCAN_HOST_NO_PACK)
+    e.update(host_memory="pinned", frac_of_link=e["host_read_gbps_per_gpu"] / link)
+    out["float64_copies_pinned"] = e
+    e = timed(host, 0)
+    e.update(host_memory="pageable", note="API default: diploid dosages are packed to 1-byte codes by the host cores / on the device")
+    out["default_packing"] = e
+    return out
+
+
+def cpu_whole_function(A, y):
+    """The reference's whole gwasols on the host cores, restated with the fastest stock pieces: column std + filter
+    (gwas.jl:112-115), GRM through BLAS (the call at :124), K standardisation (:130), PCA by LAPACK SVD (:234), then
+    the per-marker loop (:239-249) by the oracle's C/OpenMP twin.  Returns per-phase seconds."""
+    from threadpoolctl import threadpool_limits
+
+    from oracle import cbind, gwas_oracle as go
+
+    cores = cbind.use_all_cores()
+    t = {}
+    with threadpool_limits(limits=cores):
+        t0 = time.perf_counter()
+        mu, v = cbind.colstats(A)
+        t["colstats_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        Z = A - mu[None, :]
+        K = (Z @ Z.T) / A.shape[1]
+        del Z
+        t["grm_blas_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        pc = go.pca_pc1(go.standardise_K(K))
+        t["kstd_svd_s"] = time.perf_counter() - t0
+    ys = (y - y.mean()) / y.std(ddof=1)
+    t0 = time.perf_counter()
+    so, sl, keep = cbind.gwasols_raw(A, ys, pc)
+    t["marker_loop_s"] = time.perf_counter() - t0
+    t["total_s"] = sum(t.values())
+    t["cores"] = cores
+    return t, sl[keep]
+
+
+def run_whole_api(gbm_b200, with_cpu=True):
+    """The call a user of the reference makes: gwaslmm(genomes = ..., phenomes = ...) -> Fit (gwas.jl:329-337) through
+    the host mirror (same keyword API over the C ABI; Genomes holds a pageable host matrix), wall clock per call incl.
+    ingestion, filter, GRM, PC1, scan and Fit assembly -- on BASELINE configs[0] (n=300, l=10,000, continuous
+    frequencies) and configs[1]'s shape (n=5,000 x p=100,000 diploid).  CPU arm: cpu_whole_function on the same
+    matrices."""
+    from oracle import synth
+
+    out = {}
+    for name, n, p, kind in (("config0_n300_l10000", 300, 10_000, 2), ("config1_shape_n5000_p100000", 5_000, 100_000, 0)):
+        A = synth_block_chunked(n, p) if kind == 0 else synth.block(SEED, n, 0, p, kind)
+        y = synth.phenotype(SEED, n, p, kind)
+        g = gbm_b200.Genomes.from_matrix(A)
+        ph = gbm_b200.Phenomes.from_matrix(y, entries=g.entries)
+        d = {"n": n, "p": p}
+        for fn_name in ("gwasols", "gwaslmm"):
+            fn = getattr(gbm_b200, fn_name)
+            fit = fn(genomes=g, phenomes=ph)  # first call: library / cuSOLVER initialisation
+            ts = []
+            for _ in range(5 if n <= 1000 else 3):
+                t0 = time.perf_counter()
+                fit = fn(genomes=g, phenomes=ph)
+                ts.append(time.perf_counter() - t0)
+            d[fn_name] = {"seconds_per_call_median": float(np.median(ts)), "seconds_per_call_max": float(max(ts)),
+                          "markers_per_s": p / float(np.median(ts)), "storage": fit.extras["storage"],
+                          "l_kept": int(fit.b_hat.size)}
+        if with_cpu:
+            t, z_cpu = cpu_whole_function(A, y)
+            d["cpu_whole_function"] = dict(t, markers_per_s=p / t["total_s"], kind="port",
+                                           note="BLAS GRM + LAPACK SVD + C/OpenMP marker loop on all host cores")
+            d["speedup_gwaslmm_vs_cpu_whole_function"] = t["total_s"] / d["gwaslmm"]["seconds_per_call_median"]
+            zg = fit.b_hat
+            if zg.size == z_cpu.size:
+                d["max_abs_diff_z_vs_cpu"] = float(np.max(np.abs(np.abs(zg) - np.abs(z_cpu))))
+        out[name] = d
+        del A, g, ph
     return out
 
 

@@ -291,7 +291,9 @@ static bool lanczos_core(int64_t n, Apply&& apply, double tol, int max_iter, dou
           converged = true;
           break;
         }
-        next_check = m + std::max(10, m / 8);
+        // a check is one stream synchronisation + an O(m) host solve: cheap next to the steps an overshoot costs
+        // (every step past convergence is a pass over the matrix and, when sharded, an all-reduce)
+        next_check = m + (m < 100 ? 10 : 6);
       }
     }
     if (converged) {

@@ -243,8 +243,58 @@ def gwasprep(*, genomes: Genomes, phenomes: Phenomes, idx_entries=None, idx_loci
     return np.asfortranarray(G), pr.y, K, fit
 
 
+def _gwas_multigpu(group, model_name: str, model: int, genomes, phenomes, idx_trait, GRM_type, y, verbose) -> Fit:
+    """gwasols / gwaslmm on a group of GPUs (GBM_NUM_GPUS > 1): markers sharded by column block, ONE collective
+    call into the library (gbm_sharded_upload + gbm_sharded_gwas); same Fit as the single-GPU path."""
+    from .multigpu import ShardedMatrix
+
+    A = np.asarray(genomes.allele_frequencies, dtype=np.float64)
+    sm = ShardedMatrix.upload(group, A, compact=True)
+    try:
+        ys = (y - y.mean()) / np.std(y, ddof=1)  # gwas.jl:128
+        res = sm.gwas(ys, model=model,
+                      grm_type=_lib.GRM_PLOIDY_AWARE if GRM_type == "ploidy-aware" else _lib.GRM_SIMPLE)
+        packed = sm.packed
+    finally:
+        sm.free()
+    idx_cols = res["idx_cols"].copy()
+    sel = idx_cols - 1
+    if np.isnan(res["stat"][sel]).all() and np.isnan(A).any():
+        raise ErrorException("cannot convert a value of type Missing to Float64")
+    fit = Fit.new(A.shape[0], int(idx_cols.size))  # gwas.jl:133-140
+    fit.model = model_name
+    fit.trait = phenomes.traits[idx_trait - 1]
+    fit.b_hat_labels = [genomes.loci_alleles[j] for j in sel]
+    fit.entries = list(genomes.entries)
+    fit.populations = list(genomes.populations)
+    fit.metrics = {"": 0.0}
+    b = res["stat"][sel]
+    if model == _lib.MODEL_LMM:
+        b = np.where(np.isnan(b), 0.0, b)  # failed fits leave 0.0 (:367-382)
+    fit.b_hat = np.ascontiguousarray(b)
+    tm = res["timing"]
+    fit.extras = {"beta": res["beta"][sel], "se": res["se"][sel], "neglog10p": res["neglog10p"][sel],
+                  "pvalue": np.power(10.0, -res["neglog10p"][sel]), "idx_cols": idx_cols, "pc1": res["pc1"].copy(),
+                  "ploidy": tm["ploidy"] if GRM_type == "ploidy-aware" else None, "eig_ms": tm["eig_ms"], "timing": tm,
+                  "storage": "u8 dosage codes" if packed else "float64", "n_gpus": group.world}
+    if not fit.checkdims():
+        raise ErrorException(f"Error performing GWAS via {model_name[5:]} using the {GRM_type} GRM.")
+    return fit
+
+
 def _gwas(model_name: str, model: int, genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type,
           verbose) -> Fit:
+    from .multigpu import default_group
+
+    group = default_group()  # GBM_NUM_GPUS > 1
+    if group is not None:
+        rows1, cols1, y = _validate_and_select(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait)
+        if GRM_type not in GRM_TYPES:
+            raise ArgumentError("Unrecognised `GRM_type`. Please select from:\n\t‣ " + "\n\t‣ ".join(GRM_TYPES))
+        if np.var(y, ddof=1) < _EPS:
+            raise ArgumentError("No variance in the trait: " + phenomes.traits[idx_trait - 1] + ".")
+        if rows1 is None and cols1 is None and np.shape(genomes.allele_frequencies)[1] >= group.world:
+            return _gwas_multigpu(group, model_name, model, genomes, phenomes, idx_trait, GRM_type, y, verbose)
     pr = _prepare(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type, True, need_kstd=False,
                   need_pc1=True)  # gwas.jl:221-230 / :344-353, PCA :234 / :357
     try:

@@ -179,23 +179,26 @@ class ShardedMatrix:
         return out
 
     def gwas(self, y, model: int = _lib.MODEL_LMM, grm_type: int = _lib.GRM_SIMPLE, flags: int = 0,
-             want=("stat", "beta", "se", "neglog10p")):
+             want=("stat", "beta", "se", "neglog10p"), out=None):
         """Whole gwasols / gwaslmm after extractxyetc in ONE collective call (``gbm_sharded_gwas``): filter + ploidy
-        probe, GRM + all-reduce, K standardisation, PC1, marker scan, gather.  ``y`` is used as given."""
+        probe, GRM + all-reduce, K standardisation, PC1, marker scan, gather.  ``y`` is used as given.
+        ``out``: a dict from a previous call whose arrays are reused (no fresh allocations: a fresh NumPy array is
+        page-faulted in while the results are copied into it)."""
         y = np.ascontiguousarray(y, dtype=np.float64)
         if y.shape != (self.n,):
             raise _lib.ArgumentError("phenotype length does not match the number of entries")
         p = self.p
-        out = {k: np.empty(p) for k in want}
-        keep = np.empty(p, dtype=np.uint8)
-        idx = np.empty(p, dtype=np.int64)
-        pc = np.empty(self.n)
+        if out is None:
+            out = {k: np.zeros(p) for k in want}
+            out["_keep"] = np.zeros(p, dtype=np.uint8)
+            out["_idx"] = np.zeros(p, dtype=np.int64)
+            out["pc1"] = np.zeros(self.n)
         nk = c_int64()
         tm = _lib.GwasTiming()
         check(_lib.load().gbm_sharded_gwas(self._h, ptr(y), model, grm_type, flags, ptr(out.get("stat")), ptr(out.get("beta")),
-                                           ptr(out.get("se")), ptr(out.get("neglog10p")), None, None, ptr(keep), ptr(idx),
-                                           byref(nk), ptr(pc), byref(tm)))
-        out.update(keep=keep.astype(bool), idx_cols=idx[: nk.value].copy(), pc1=pc, timing=tm.asdict())
+                                           ptr(out.get("se")), ptr(out.get("neglog10p")), None, None, ptr(out["_keep"]),
+                                           ptr(out["_idx"]), byref(nk), ptr(out["pc1"]), byref(tm)))
+        out.update(keep=out["_keep"].view(bool), idx_cols=out["_idx"][: nk.value], timing=tm.asdict())
         return out
 
 

@@ -222,7 +222,74 @@ function gwasprep(;
     (G, pr.y, pr.K, fit)
 end
 
+# ---- multi-GPU: GBM_NUM_GPUS > 1 shards the markers over that many GPUs of this box -------------------
+# The reference's parallel axis is `Threads.@threads for j = 1:l` (src/gwas.jl:239, :363); here this ONE Julia
+# process drives a group of GPUs through the library (gbm_group_create_local: a host thread per GPU inside
+# libgbm_b200.so, NCCL for the GRM all-reduce and the PC1 all-reduces, results gathered in locus order).
+# Same calls, same Fit; applies when no entries / loci are subset (the reference's own working domain for
+# gwasols / gwaslmm, since its GRM is always computed on the full `genomes`, src/gwas.jl:120, :124).
+const GROUP = Ref{Ptr{Cvoid}}(C_NULL)
+numgpus() = parse(Int, get(ENV, "GBM_NUM_GPUS", "1"))
+function group()
+    if GROUP[] == C_NULL
+        g = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:gbm_group_create_local, LIBGBM), Cint, (Cint, Ptr{Cint}, Ref{Ptr{Cvoid}}), numgpus(), C_NULL, g))
+        GROUP[] = g[]
+        atexit(() -> ccall((:gbm_group_free, LIBGBM), Cint, (Ptr{Cvoid},), GROUP[]))
+    end
+    GROUP[]
+end
+
+struct GwasTiming   # gbm_gwas_timing of include/gbm_b200.h
+    colstats_ms::Float64; grm_ms::Float64; allreduce_ms::Float64; kstd_pc1_ms::Float64; eig_ms::Float64
+    scan_ms::Float64; gather_ms::Float64; total_ms::Float64; grm_tflops::Float64; scan_kernel_ms::Float64
+    launches::Int64; ploidy::Int32; lanczos_steps::Int32
+end
+
+function gwas_multigpu(model_name::String, model::Cint, genomes, phenomes, idx_trait, GRM_type, y)::Fit
+    A = Matrix{Float64}(genomes.allele_frequencies)       # throws on `missing`, as src/prediction.jl:129 does
+    n, p = size(A)
+    sm = Ref{Ptr{Cvoid}}(C_NULL); packed = Ref{Cint}(0)
+    check(ccall((:gbm_sharded_upload, LIBGBM), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Cint, Ref{Ptr{Cvoid}}, Ref{Cint}), group(), A, n, p, n, 1, sm, packed))
+    ys = (y .- mean(y)) ./ std(y)                         # src/gwas.jl:128
+    stat = Vector{Float64}(undef, p); idx = Vector{Int64}(undef, p); nk = Ref{Int64}(0)
+    tm = Ref{GwasTiming}()
+    rc = ccall((:gbm_sharded_gwas, LIBGBM), Cint,
+               (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                Ptr{Float64}, Ptr{UInt8}, Ptr{Int64}, Ref{Int64}, Ptr{Float64}, Ref{GwasTiming}),
+               sm[], ys, model, GRM_type == "ploidy-aware" ? GBM_GRM_PLOIDY_AWARE : GBM_GRM_SIMPLE, 0, stat, C_NULL, C_NULL,
+               C_NULL, C_NULL, C_NULL, C_NULL, idx, nk, C_NULL, tm)
+    ccall((:gbm_sharded_free, LIBGBM), Cint, (Ptr{Cvoid},), sm[])
+    check(rc)
+    idx_cols = idx[1:nk[]]
+    fit = Fit(n = n, l = length(idx_cols))                # src/gwas.jl:133-140
+    fit.model = model_name
+    fit.trait = phenomes.traits[idx_trait]
+    fit.b_hat_labels = genomes.loci_alleles[idx_cols]
+    fit.entries = genomes.entries
+    fit.populations = genomes.populations
+    fit.metrics = Dict("" => 0.0)
+    b = stat[idx_cols]
+    model == GBM_MODEL_LMM && (b[isnan.(b)] .= 0.0)       # failed fits leave 0.0 (src/gwas.jl:367-382)
+    fit.b_hat = b
+    if !checkdims(fit)
+        throw(ErrorException("Error performing GWAS using the " * GRM_type * " GRM."))
+    end
+    fit
+end
+
 function gwas(model_name::String, model::Cint, genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type)::Fit
+    if numgpus() > 1
+        rows, cols, y = selectrows(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait)
+        if sum(["simple", "ploidy-aware"] .== GRM_type) == 0
+            throw(ArgumentError("Unrecognised `GRM_type`. Please select from:\n\t‣ simple\n\t‣ ploidy-aware"))
+        end
+        var(y) < eps(Float64) && throw(ArgumentError("No variance in the trait: " * phenomes.traits[idx_trait] * "."))
+        if isnothing(rows) && isnothing(cols) && size(genomes.allele_frequencies, 2) >= numgpus()
+            return gwas_multigpu(model_name, model, genomes, phenomes, idx_trait, GRM_type, y)
+        end
+    end
     pr = prepare(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type, true; need_kstd = false, need_pc1 = true)
     if length(pr.entries) != length(pr.pc1)
         free!(pr.dm)

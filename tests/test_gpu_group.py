@@ -241,3 +241,25 @@ def test_one_process_per_gpu_under_torchrun(gbm):
         f.write(log)
     assert proc.returncode == 0, log[-3000:]
     assert log.count("-> OK") == 2 and "FAIL" not in log, log[-3000:]
+
+
+@pytest.mark.parametrize("n_gpus", group_sizes())
+def test_host_mirror_uses_the_group_when_gbm_num_gpus_is_set(gbm, n_gpus, monkeypatch):
+    """gwasols / gwaslmm of the host mirror (same keyword API as /root/reference/src/gwas.jl:206-214, :329-337) with
+    GBM_NUM_GPUS: the Fit equals the single-GPU one."""
+    from gbm_b200 import multigpu
+
+    n, p = 320, 1500
+    A = synth.block(3, n, 0, p, synth.KIND_TETRAPLOID)
+    y = synth.phenotype(3, n, p, synth.KIND_TETRAPLOID)
+    g = gbm.Genomes.from_matrix(A)
+    ph = gbm.Phenomes.from_matrix(y, entries=g.entries)
+    monkeypatch.delenv("GBM_NUM_GPUS", raising=False)
+    one = gbm.gwaslmm(genomes=g, phenomes=ph, GRM_type="ploidy-aware")
+    monkeypatch.setenv("GBM_NUM_GPUS", str(max(n_gpus, 2) if visible_gpus() >= 2 else 1))
+    if visible_gpus() < 2:  # a single visible GPU: exercise the group path with a group of one
+        monkeypatch.setattr(multigpu, "default_group", lambda: multigpu.Group.local(1))
+    many = gbm.gwaslmm(genomes=g, phenomes=ph, GRM_type="ploidy-aware")
+    assert many.model == one.model == "GWAS_LMM" and many.b_hat_labels == one.b_hat_labels
+    assert "n_gpus" in many.extras and many.extras["ploidy"] == 4
+    np.testing.assert_allclose(many.b_hat, one.b_hat, rtol=1e-9, atol=1e-9 * np.abs(one.b_hat).max())

@@ -550,6 +550,13 @@ def test_full_size_config3_sampled_parity(gbm):
     rt = torch.as_tensor(rows, device="cuda:0")
     got = K.index_select(0, rt).index_select(1, rt).cpu().numpy()
     assert np.max(np.abs(got - want)) < 1e-11 * np.abs(want).max()
+    # centred GRM (the default, north_star's "centred X X'"): same rows, the device's column means (checked above on
+    # the sampled columns)
+    dm.grm(0, 2, 0, out=dK)
+    Zc = R - res["mean"][None, :]
+    want_c = (Zc @ Zc.T) / p
+    got_c = K.index_select(0, rt).index_select(1, rt).cpu().numpy()
+    assert np.max(np.abs(got_c - want_c)) < RTOL * np.abs(want_c).max()
     dm.free()
 
 
