@@ -284,6 +284,7 @@ struct SideVectors {
   std::vector<double> W;      // n x k_eff, orthonormal, orthogonal to 1
   std::vector<double> R;      // n x T residualised traits  (I - 11'/n - WW') y
   std::vector<double> yMy;    // T
+  std::vector<double> wy;     // T x k_eff: w_a' (y_t - mean), the covariates' own coefficients (degenerate markers)
 };
 
 static SideVectors prepare_side_vectors(const double* Y, int64_t n, int64_t T, int64_t ldy, const double* C,
@@ -328,6 +329,7 @@ static SideVectors prepare_side_vectors(const double* Y, int64_t n, int64_t T, i
   }
   sv.R.resize(static_cast<size_t>(n) * T);
   sv.yMy.resize(T);
+  sv.wy.assign(static_cast<size_t>(T) * std::max(sv.k_eff, 1), 0.0);
   for (int64_t t = 0; t < T; ++t) {
     double* r = sv.R.data() + t * n;
     memcpy(r, hY.data() + t * n, sizeof(double) * n);
@@ -336,6 +338,7 @@ static SideVectors prepare_side_vectors(const double* Y, int64_t n, int64_t T, i
       for (int a = 0; a < sv.k_eff; ++a) {
         const double* w = sv.W.data() + static_cast<size_t>(a) * n;
         const double h = dot(w, r);
+        sv.wy[static_cast<size_t>(t) * sv.k_eff + a] += h;
         for (int64_t i = 0; i < n; ++i) r[i] -= h * w[i];
       }
     }
@@ -351,9 +354,10 @@ struct Pass {
   int64_t t0;
   int tcount, M, stride;
   bool mt;
-  DevBuf<double> dQ, dyMy;
-  Pass(int64_t t0_, int tcount_, int M_, int stride_, bool mt_, size_t qcount, cudaStream_t s)
-      : t0(t0_), tcount(tcount_), M(M_), stride(stride_), mt(mt_), dQ(qcount, s), dyMy(tcount_ > 0 ? tcount_ : 1, s) {}
+  DevBuf<double> dQ, dyMy, dWy;
+  Pass(int64_t t0_, int tcount_, int M_, int stride_, bool mt_, size_t qcount, int k, cudaStream_t s)
+      : t0(t0_), tcount(tcount_), M(M_), stride(stride_), mt(mt_), dQ(qcount, s), dyMy(tcount_ > 0 ? tcount_ : 1, s),
+        dWy(static_cast<size_t>(tcount_ > 0 ? tcount_ : 1) * (k > 0 ? k : 1), s) {}
 };
 
 static std::vector<std::unique_ptr<Pass>> build_passes(const SideVectors& sv, int64_t n, int64_t T) {
@@ -371,7 +375,7 @@ static std::vector<std::unique_ptr<Pass>> build_passes(const SideVectors& sv, in
     const int stride = mt ? 2 + M : scan_record_stride(M, false);
     const int ncols = mt ? M + 1 : stride - 2;  // columns of the device Q (padded for the FMA kernels)
     const int first = mt ? 1 : 0;               // [1 | W | R] for the tensor-pipe kernel
-    std::unique_ptr<Pass> ps(new Pass(t0, tcount, M, stride, mt, static_cast<size_t>(ldq) * ncols, st.stream));
+    std::unique_ptr<Pass> ps(new Pass(t0, tcount, M, stride, mt, static_cast<size_t>(ldq) * ncols, k, st.stream));
     GBM_CUDA(cudaMemsetAsync(ps->dQ.p, 0, sizeof(double) * ldq * ncols, st.stream));
     std::vector<double> ones;
     if (mt) {
@@ -386,6 +390,9 @@ static std::vector<std::unique_ptr<Pass>> build_passes(const SideVectors& sv, in
                                tcount, cudaMemcpyHostToDevice, st.stream));
     GBM_CUDA(cudaMemcpyAsync(ps->dyMy.p, sv.yMy.data() + t0, sizeof(double) * tcount, cudaMemcpyHostToDevice,
                              st.stream));
+    if (k > 0)
+      GBM_CUDA(cudaMemcpyAsync(ps->dWy.p, sv.wy.data() + static_cast<size_t>(t0) * k, sizeof(double) * tcount * k,
+                               cudaMemcpyHostToDevice, st.stream));
     // the host vectors are pageable: make sure the copies have drained before they go away
     GBM_CUDA(cudaStreamSynchronize(st.stream));
     passes.push_back(std::move(ps));
@@ -426,6 +433,7 @@ static void scan_block(const gbm_matrix& mat, int64_t p_blk, const std::vector<s
     fp.flags = flags;
     fp.rec = rec.p;
     fp.yMy = ps->dyMy.p;
+    fp.wy = ps->dWy.p;
     auto off = [&](double* base) { return base ? base + ps->t0 * ld_out + col0 : nullptr; };
     fp.beta = off(dev_out.beta);
     fp.se = off(dev_out.se);
@@ -1867,6 +1875,7 @@ struct gbm_lmm_plan {
   double* dYr = nullptr;  // U'y
   double* dCr = nullptr;  // U'[1, C], n x Q0 (ld n)
   double lam0 = 0.0;
+  double s_min = 0.0;     // smallest eigenvalue (negative for an indefinite K)
 };
 
 extern "C" {
@@ -1956,6 +1965,7 @@ int gbm_lmm_plan_create(const double* K, int64_t n, const double* y, const doubl
   GBM_CUDA(cudaMemcpy(hS.data(), pl->dS, sizeof(double) * n, cudaMemcpyDeviceToHost));
   GBM_CUDA(cudaMemcpy(hY.data(), pl->dYr, sizeof(double) * n, cudaMemcpyDeviceToHost));
   GBM_CUDA(cudaMemcpy(hC.data(), pl->dCr, sizeof(double) * n * Q0, cudaMemcpyDeviceToHost));
+  pl->s_min = hS[0];
   pl->lam0 = lmm_null_lam0(Q0, hS.data(), hC.data(), n, hY.data(), n);
   if (null_log_delta) *null_log_delta = pl->lam0;
   guard.p = nullptr;
@@ -1972,6 +1982,7 @@ int gbm_lmm_plan_run(gbm_lmm_plan* pl, const gbm_matrix* m, int flags, double* b
   State& st = state();
   reset_timing();
   const int64_t n = pl->n, p = m->p;
+  const bool ref_obj = (flags & GBM_LMM_REFERENCE_OBJECTIVE) != 0;
   // fixed-locus filter + column sd (beta / se are reported for the standardised column)
   const int stride = scan_record_stride(0, true);
   DevBuf<double> rec(static_cast<size_t>(p) * stride, st.stream), dsd(p, st.stream);
@@ -2006,8 +2017,10 @@ int gbm_lmm_plan_run(gbm_lmm_plan* pl, const gbm_matrix* m, int flags, double* b
     ss.emplace_back(new Span(st.stream));
     ss.back()->start();
     auto off = [&](int i) { return out.slot[i].dev ? static_cast<double*>(out.slot[i].dev) + j0 : nullptr; };
-    launch_lmm_delta(pl->Q0, dAr.p, n, pb, ldr, pl->dS, pl->dYr, pl->dCr, n, pl->lam0, dsd.p + j0, dkeep.p + j0,
-                     off(0), off(1), off(2), off(3), off(4), flags, st.sm_count, st.stream);
+    // reference objective: the search starts at s2e / s2u = 1, the reference's theta_init = [0.5, 0.5] (gwas.jl:578)
+    launch_lmm_delta(pl->Q0, dAr.p, n, pb, ldr, pl->dS, pl->dYr, pl->dCr, n, ref_obj ? 0.0 : pl->lam0, dsd.p + j0,
+                     dkeep.p + j0, off(0), off(1), off(2), off(3), off(4), flags & GBM_PVALUE_TWO_SIDED, st.sm_count,
+                     st.stream, ref_obj ? 1 : 0, pl->s_min);
     ss.back()->stop();
     st.launches += 2;
   }

@@ -37,6 +37,7 @@ struct FinalizeParams {
   int model, flags;
   const double* rec;   // [p][rec_stride]
   const double* yMy;   // [T] device
+  const double* wy;    // [T][k] device: w_a' (y_t - mean) for the orthonormal covariates (degenerate markers)
   double* beta;        // p x T (nullable)
   double* se;
   double* stat;
@@ -115,7 +116,7 @@ void launch_gemm_tn(const double* A, int64_t lda, const double* B, int64_t ldb, 
 void launch_lmm_delta(int Q0, const double* Ar, int64_t n, int64_t pb, int64_t ld, const double* S, const double* Yr,
                       const double* Cr, int64_t ldcr, double lam0, const double* col_sd, const uint8_t* keep,
                       double* beta, double* se, double* stat, double* nlp, double* log_delta, int flags,
-                      int sm_count, cudaStream_t stream);
+                      int sm_count, cudaStream_t stream, int objective = 0, double s_min = 0.0);
 // null-model log(delta) on the host from rotated vectors
 double lmm_null_lam0(int Q0, const double* S, const double* Cr, int64_t ldcr, const double* Yr, int64_t n);
 

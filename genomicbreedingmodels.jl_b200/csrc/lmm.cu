@@ -13,6 +13,15 @@
 // in FP64 registers, a butterfly all-reduce, then the q x q algebra redundantly per lane.
 // The root of f is bracketed by marching from the null-model estimate lam0 in steps of 0.5
 // and polished by safeguarded Newton (bisection fallback) to |dlam| < 1e-13.
+//
+// objective = 1 ("reference objective"): the reference's own function and box instead of the standard REML --
+// minimise 0.5 log det V + y'Py + log det(X'V^-1X) (gwas.jl:478) over theta = [s2e, s2u] in [eps, 1]^2 (:588),
+// statistic b[end] / sqrt(inv(X'V^-1X)[end]) without a sigma^2 factor (:596-599).  On rotated data, with
+// c = s2u, delta = s2e / s2u: the objective is (n/2 - q) log c + 1/2 sum log(s_i + delta) + R(delta) / c +
+// log det A(delta); for a fixed delta it is unimodal in c with minimiser c* = R / (n/2 - q), and the box is
+// c <= min(1, 1/delta), so the constrained minimiser is c* clamped and the search stays ONE-dimensional in
+// lam = log(delta): F'(lam) below has three regimes (interior / s2u = 1 / s2e = 1), continuous except at lam = 0.
+// oracle/lmm_oracle.py: refobj_terms / refobj_fit restate it; its dense 2-D brute force agrees to 1e-12.
 #include <math.h>
 
 #include "common.cuh"
@@ -21,8 +30,8 @@
 
 namespace gbm {
 
-constexpr double kLamMin = -11.512925464970229;  // log(1e-5)
-constexpr double kLamMax = 11.512925464970229;   // log(1e+5)
+constexpr double kLamMinDefault = -11.512925464970229;  // log(1e-5)
+constexpr double kLamMaxDefault = 11.512925464970229;   // log(1e+5)
 constexpr double kMarch = 0.5;
 
 // q x q symmetric positive-definite inverse by Gauss-Jordan (q <= 4, registers only)
@@ -63,11 +72,12 @@ struct RemlEval {
   double beta_last;    // GLS coefficient of the last fixed effect
   double var_last;     // [ (X'WX)^-1 ]_last,last
   double R;            // residual quadratic form
+  double c;            // reference objective: the fitted s2u (clamped c*); 0 for REML
 };
 
 template <int MM>
 __host__ __device__ inline RemlEval<MM> reml_eval(const double* g1, const double* g2, const double* g3, double sw,
-                                                  double sw2, double delta, double n) {
+                                                  double sw2, double delta, double n, int objective = 0) {
   constexpr int Q = MM - 1;
   // unpack packed upper triangles (index of (a,b), a <= b: a*MM - a(a-1)/2 + (b-a))
   double G1[MM][MM], H1[MM][MM], H2[MM][MM];
@@ -146,8 +156,29 @@ __host__ __device__ inline RemlEval<MM> reml_eval(const double* g1, const double
   const double L1 = delta * sw, L2 = delta * sw - delta * delta * sw2;
   const double rr = R1 / R;
   RemlEval<MM> e;
-  e.f = -0.5 * ((n - Q) * rr + L1 + D1);
-  e.fp = -0.5 * ((n - Q) * (R2 / R - rr * rr) + L2 + D2);
+  if (objective == 0) {
+    e.f = -0.5 * ((n - Q) * rr + L1 + D1);
+    e.fp = -0.5 * ((n - Q) * (R2 / R - rr * rr) + L2 + D2);
+    e.c = 0.0;
+  } else {
+    const double nq = 0.5 * n - Q, cstar = R / nq, chi = delta <= 1.0 ? 1.0 : 1.0 / delta;
+    double F1, F2;
+    if (cstar < chi) {          // interior: both variance components inside the box
+      F1 = nq * rr + 0.5 * L1 + D1;
+      F2 = nq * (R2 / R - rr * rr) + 0.5 * L2 + D2;
+      e.c = cstar;
+    } else if (delta <= 1.0) {  // s2u = 1
+      F1 = 0.5 * L1 + R1 + D1;
+      F2 = 0.5 * L2 + R2 + D2;
+      e.c = 1.0;
+    } else {                    // s2e = 1, s2u = 1 / delta
+      F1 = -nq + 0.5 * L1 + delta * (R1 + R) + D1;
+      F2 = 0.5 * L2 + delta * (R2 + 2.0 * R1 + R) + D2;
+      e.c = chi;
+    }
+    e.f = -F1;  // the search below looks for a maximum of -F
+    e.fp = -F2;
+  }
   e.beta_last = -v[Q - 1];
   e.var_last = Ai[Q - 1][Q - 1];
   e.R = R;
@@ -162,6 +193,8 @@ struct LmmParams {
   const double* Cr;       // rotated fixed covariates incl. intercept, n x Q0, leading dimension ldcr
   int64_t ldcr;
   double lam0;
+  double lam_min, lam_max;  // search interval in lam = log(delta)
+  int objective;            // 0: standard REML, 1: the reference's objective and box (see the header comment)
   const double* col_sd;   // raw-column sd (beta / se are reported for the standardised column)
   const uint8_t* keep;    // fixed-locus filter
   double* beta;
@@ -220,7 +253,7 @@ __device__ __forceinline__ RemlEval<Q0 + 2> warp_eval(const LmmParams& prm, cons
     sw += __shfl_xor_sync(0xffffffffu, sw, o);
     sw2 += __shfl_xor_sync(0xffffffffu, sw2, o);
   }
-  return reml_eval<MM>(g1, g2, g3, sw, sw2, delta, static_cast<double>(prm.n));
+  return reml_eval<MM>(g1, g2, g3, sw, sw2, delta, static_cast<double>(prm.n), prm.objective);
 }
 
 template <int Q0>
@@ -242,6 +275,7 @@ __global__ void __launch_bounds__(256) lmm_delta_kernel(const LmmParams prm) {
     }
     const double* x = prm.Ar + j * prm.ld;
     // bracket the stationary point by marching from lam0 in the ascent direction
+    const double kLamMin = prm.lam_min, kLamMax = prm.lam_max;
     double a = fmin(fmax(prm.lam0, kLamMin), kLamMax);
     auto ea = warp_eval<Q0>(prm, x, a, lane);
     double lam = a;
@@ -292,7 +326,9 @@ __global__ void __launch_bounds__(256) lmm_delta_kernel(const LmmParams prm) {
     }
     if (lane == 0) {
       const double n = static_cast<double>(prm.n);
-      const double sg2 = ex.R / (n - Q);
+      // REML: sigma2_g profiled out, R / (n - q); reference objective: the fitted s2u itself (no sigma^2 factor in
+      // b[end] / sqrt(inv(X'V^-1X)[end]), gwas.jl:596-599)
+      const double sg2 = prm.objective == 0 ? ex.R / (n - Q) : ex.c;
       const double se_raw = sqrt(sg2 * ex.var_last);
       const double z = ex.beta_last / se_raw;
       const double sd = prm.col_sd ? prm.col_sd[j] : 1.0;
@@ -312,9 +348,13 @@ __global__ void __launch_bounds__(256) lmm_delta_kernel(const LmmParams prm) {
 void launch_lmm_delta(int Q0, const double* Ar, int64_t n, int64_t pb, int64_t ld, const double* S, const double* Yr,
                       const double* Cr, int64_t ldcr, double lam0, const double* col_sd, const uint8_t* keep,
                       double* beta, double* se, double* stat, double* nlp, double* log_delta, int flags,
-                      int sm_count, cudaStream_t stream) {
+                      int sm_count, cudaStream_t stream, int objective, double s_min) {
   if (pb <= 0) return;
-  LmmParams prm{n, pb, ld, Ar, S, Yr, Cr, ldcr, lam0, col_sd, keep, beta, se, stat, nlp, log_delta, flags};
+  // s_i + delta must stay positive: an indefinite K (the symmetrised standardised GRM) raises the lower end
+  double lam_min = kLamMinDefault;
+  if (s_min < 0.0) lam_min = fmax(lam_min, log(-s_min * (1.0 + 1e-6) + 1e-300) + 1e-3);
+  LmmParams prm{n, pb, ld, Ar, S, Yr, Cr, ldcr, lam0, lam_min, kLamMaxDefault, objective, col_sd, keep, beta, se, stat, nlp,
+                log_delta, flags};
   const int64_t warps_needed = pb;
   int64_t blocks = (warps_needed + 7) / 8;
   const int64_t max_blocks = static_cast<int64_t>(sm_count) * 6;
@@ -381,6 +421,9 @@ static double null_f(const double* S, const double* Cr, int64_t ldcr, const doub
 template <int Q0>
 static double null_lam0_t(const double* S, const double* Cr, int64_t ldcr, const double* Yr, int64_t n) {
   const int grid = 101;
+  double kLamMin = kLamMinDefault;
+  const double kLamMax = kLamMaxDefault;
+  if (S[0] < 0.0) kLamMin = fmax(kLamMin, log(-S[0] * (1.0 + 1e-6) + 1e-300) + 1e-3);
   double best = -INFINITY;
   int gbest = 0;
   for (int g = 0; g < grid; ++g) {

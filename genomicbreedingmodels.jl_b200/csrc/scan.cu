@@ -308,7 +308,11 @@ __global__ void __launch_bounds__(256) scan_finalize_kernel(const FinalizeParams
   double uu = 0.0;
   for (int i = 0; i < prm.k; ++i) uu = fma(rec[2 + i], rec[2 + i], uu);
   const double xMx = ss - uu;  // x'Mx on the raw scale, M = projector off [1, C]
-  const bool ok = keep && (xMx > 1e-12 * ss);
+  // A marker inside span[1, C] makes X'X singular.  The reference's `pinv(X' * X)` (gwas.jl:242) truncates singular
+  // values below rtol * sigma_max with rtol = eps * min(size) = (k + 2) eps; sigma_max ~ n and the small one is
+  // ~ xMx / (sd^2 n), so truncation happens below xMx / SS ~ (k + 2) eps n -- and its minimum-norm solution is finite.
+  const double thr = fmax(static_cast<double>(prm.k + 2) * kEps * static_cast<double>(prm.n), 16.0 * kEps);
+  const bool ok = keep && (xMx > thr * ss);
   const double dfres = static_cast<double>(prm.n - prm.k - 2);
   const int64_t o = static_cast<int64_t>(t) * prm.ld_out + j;
   double beta = NAN, se = NAN, stat = NAN, nlp = NAN;
@@ -329,7 +333,21 @@ __global__ void __launch_bounds__(256) scan_finalize_kernel(const FinalizeParams
       nlp = -log_sf_normal(stat) * 0.4342944819032518;
     }
     if (prm.flags & 1) nlp -= 0.3010299956639812;  // two-sided
+  } else if (keep && prm.model == 0 && prm.k > 0 && uu > 0.0) {
+    // gwasols on a marker collinear with the covariates: the truncated pseudo-inverse's minimum-norm solution.  With
+    // c = C'g (g the standardised column, C orthonormal) and h = C'y:  b_g = c'h / (1 + c'c),
+    // Vinv_gg = c'c / (1 + c'c)^2, statistic c'h / |c|  (for the reference's X = [1, PC1, g]: sign(c) PC1'y).
+    double uh = 0.0;
+    for (int i = 0; i < prm.k; ++i) uh = fma(rec[2 + i], prm.wy[t * prm.k + i], uh);
+    const double cc = uu / (sd * sd), ch = uh / sd;
+    beta = ch / (1.0 + cc);
+    se = sqrt(cc) / (1.0 + cc);
+    stat = uh / sqrt(uu);
+    nlp = -log_sf_t(stat, static_cast<double>(prm.n - 1)) * 0.4342944819032518;
+    if (prm.flags & 1) nlp -= 0.3010299956639812;
   }
+  // gwaslmm on such a marker: MixedModels' rank-deficient fit is not pinned (source absent); NaN here, the host
+  // mirror writes the 0.0 a failed fit leaves (gwas.jl:367-382)
   if (prm.beta) prm.beta[o] = beta;
   if (prm.se) prm.se[o] = se;
   if (prm.stat) prm.stat[o] = stat;

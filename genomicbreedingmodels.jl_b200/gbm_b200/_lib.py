@@ -29,6 +29,7 @@ GRM_NO_CENTRE = 1
 MODEL_OLS, MODEL_LMM = 0, 1
 PVALUE_TWO_SIDED = 1
 SCAN_HOST_NO_PACK = 4
+LMM_REFERENCE_OBJECTIVE = 8
 KIND_DIPLOID, KIND_TETRAPLOID, KIND_CONTINUOUS = 0, 1, 2
 
 

@@ -345,19 +345,26 @@ def gwaslmm(*, genomes: Genomes, phenomes: Phenomes, idx_entries=None, idx_loci_
 
 
 def gwasreml(*, genomes: Genomes, phenomes: Phenomes, idx_entries=None, idx_loci_alleles=None, idx_trait: int = 1,
-             GRM_type: str = "simple", verbose: bool = False) -> Fit:
+             GRM_type: str = "simple", verbose: bool = False, objective: str = "reml") -> Fit:
     """gwasreml (/root/reference/src/gwas.jl:549-613): per-marker LMM with the GRM as the
     covariance of the random genotype effect, variance components re-estimated for every
     marker, fit.b_hat[j] = b[end]/sqrt(inv(X'V^-1 X)[end]) with X = [1, g_j] (:586, :596-599).
 
-    Engine: eigen-rotation (cuSOLVER + FP64 DMMA GEMM) and a per-marker REML delta search on
-    the device.  Differences from the reference's code, by design (oracle/lmm_oracle.py):
-    the symmetric un-standardised GRM is the covariance (the reference passes the
-    column-standardised, non-symmetric K of gwas.jl:130) and the objective is the standard
-    REML log-likelihood (the reference's `0.5 log det V + y'Py + log det X'V^-1X`, :478, is
-    minimised by L-BFGS to g_tol 1e-4).  PARITY UNPINNED."""
-    pr = _prepare(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type, False, need_kstd=False,
-                  need_pc1=False)  # gwas.jl:564-573 (K stays symmetric: standardise=False)
+    Engine: eigen-rotation (cuSOLVER + FP64 DMMA GEMM) and a per-marker search on the device.
+    ``objective`` (an extension; the reference has no such keyword):
+
+    * ``"reml"`` (default): the standard REML log-likelihood on the symmetric un-standardised GRM, z with the
+      profiled sigma^2 -- a proper LMM test statistic.
+    * ``"reference"``: the reference's OWN objective, box and statistic (`0.5 log det V + y'Py + log det X'V^-1X`
+      over [eps, 1]^2, no sigma^2 factor; :478, :588, :596-599) on the symmetric part of the column-standardised K
+      that gwasprep hands to loglikreml (:130, :564-573) -- as close as a rotation-based engine can get; the
+      non-symmetric part of that K and the L-BFGS path are what remains (oracle/lmm_oracle.py).
+    PARITY UNPINNED either way."""
+    if objective not in ("reml", "reference"):
+        raise ArgumentError("objective must be \"reml\" or \"reference\"")
+    ref = objective == "reference"
+    pr = _prepare(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type, ref, need_kstd=ref,
+                  need_pc1=False)  # gwas.jl:564-573 (reml: K stays symmetric, standardise=False)
     try:
         if len(pr.entries) != pr.K.shape[0]:
             raise ArgumentError(
@@ -365,10 +372,11 @@ def gwasreml(*, genomes: Genomes, phenomes: Phenomes, idx_entries=None, idx_loci
                 "y and the GRM have different sizes.")
         fit = _new_fit(pr)
         fit.model = "GWAS_REML"  # :574
-        y = (pr.y - pr.y.mean()) / np.std(pr.y, ddof=1)  # :128 (z is invariant to it)
-        plan = LmmPlan(pr.K, y)
+        y = (pr.y - pr.y.mean()) / np.std(pr.y, ddof=1)  # :128 (the REML z is invariant to it; the reference box is not)
+        K = 0.5 * (pr.K + pr.K.T) if ref else pr.K
+        plan = LmmPlan(K, y)
         try:
-            res = plan.run(pr.scan_dm)
+            res = plan.run(pr.scan_dm, flags=_lib.LMM_REFERENCE_OBJECTIVE if ref else 0)
         finally:
             plan.free()
         sel = pr.idx_cols - 1
@@ -376,7 +384,7 @@ def gwasreml(*, genomes: Genomes, phenomes: Phenomes, idx_entries=None, idx_loci
         fit.extras = {"beta": res["beta"][sel], "se": res["se"][sel], "neglog10p": res["neglog10p"][sel],
                       "log_delta": res["log_delta"][sel], "null_log_delta": plan.null_log_delta,
                       "idx_cols": pr.idx_cols, "eig_ms": plan.eig_ms, "gemm_tflops": res["gemm_tflops"],
-                      "search_ms": res["search_ms"], "ploidy": pr.ploidy}
+                      "search_ms": res["search_ms"], "ploidy": pr.ploidy, "objective": objective}
         if not fit.checkdims():  # :609-611
             raise ErrorException("Error performing GWAS via REML using the " + GRM_type + " GRM.")
         return fit

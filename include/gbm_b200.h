@@ -215,6 +215,13 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
  *         estimate, safeguarded Newton on dLL/dlog(delta)), and emits beta, se (of the
  *         standardised column), z, -log10 P(N(0,1) > |z|) and log(delta).  Outputs length p,
  *         host or device, nullable.  gemm_tflops: 2 n^2 p / DMMA GEMM time. */
+/* gbm_lmm_plan_run flag: minimise the REFERENCE's own objective over its own box instead of the standard REML --
+ * 0.5 log det V + y'Py + log det(X'V^-1X) (gwas.jl:478) over [s2e, s2u] in [eps, 1]^2 from [0.5, 0.5] (:578, :588),
+ * statistic b[end] / sqrt(inv(X'V^-1X)[end]) with no sigma^2 factor (:596-599).  y must be standardised (the box is
+ * absolute).  K must be symmetric to be rotated: pass the symmetric part of the column-standardised GRM to stay as
+ * close as a rotation can to what the reference feeds loglikreml (csrc/lmm.cu has the algebra).  log_delta then
+ * receives log(s2e / s2u), se = sqrt(s2u [ (X'WX)^-1 ]_xx). */
+#define GBM_LMM_REFERENCE_OBJECTIVE 8
 typedef struct gbm_lmm_plan gbm_lmm_plan;
 int gbm_lmm_plan_create(const double* K, int64_t n, const double* y, const double* C, int64_t k, int64_t ldc,
                         gbm_lmm_plan** plan, double* eig_ms, double* null_log_delta);

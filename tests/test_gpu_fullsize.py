@@ -56,7 +56,7 @@ def test_config1_grm_full_size_sampled_rows(gbm, storage):
     got = K[np.ix_(rows, rows)]
     assert np.max(np.abs(got - want)) <= RTOL * np.abs(want).max()
     # entries far from the diagonal are differences of large terms: still 1e-9 of their own size where they are not ~0
-    big = np.abs(want) > 1e-3 * np.abs(want).max()
+    big = np.abs(want) > 1e-4 * np.abs(want).max()
     assert np.max(np.abs(got - want)[big] / np.abs(want)[big]) < RTOL
 
 
@@ -98,4 +98,4 @@ def test_config3_tetraploid_full_size(gbm):
     ok = v > go.EPS
     ref = go.scan_closed_form(A[:, ok], ys, pc)
     z = res["stat"][cols[ok]]
-    assert np.max(np.abs(z - ref["stat_lmm"]) / np.maximum(np.abs(ref["stat_lmm"]), 1e-3 * np.abs(ref["stat_lmm"]).max())) < RTOL
+    assert np.max(np.abs(z - ref["stat_lmm"]) / np.maximum(np.abs(ref["stat_lmm"]), 1e-4 * np.abs(ref["stat_lmm"]).max())) < RTOL
