@@ -402,7 +402,7 @@ def main():
             pach = 1.0 * n * p_loc / (pmain * 1e-3) / 1e9
             line["packed"] = {"metric": "GWAS markers/sec, 1-byte dosage codes resident in HBM",
                               "value": p * args.steps / pdev_s, "unit": "markers/s",
-                              "roofline": {"bound": "hbm", "kernel": "scan_sums_u8_kernel<16,2>", "achieved": pach,
+                              "roofline": {"bound": "hbm", "kernel": "scan_sums_u8_tc_kernel (tcgen05 kind::i8 dots)", "achieved": pach,
                                            "peak": peak, "unit": "GB/s", "frac": pach / peak,
                                            "algorithmic_bytes_per_launch": 1.0 * n * p_loc, "avg_launch_ms": pmain},
                               "note": "not the graded Float64 path: algorithmic bytes are n per marker here"}
@@ -837,7 +837,7 @@ def run_config3_tetraploid(gbm_b200, _lib, grp, world, rank, hbm_peak):
                   grm_tflops_aggregate_incl_allreduce=grm_tf,
                   max_neglog10p=float(np.nanmax(res["neglog10p"][idx - 1])),
                   sum_abs_z=float(np.nansum(np.abs(res["stat"][idx - 1]))),
-                  roofline_scan={"bound": "hbm", "kernel": "scan_sums_kernel<16,2>" if storage == "float64" else "scan_sums_u8_kernel<16,2>",
+                  roofline_scan={"bound": "hbm", "kernel": "scan_sums_kernel<16,2>" if storage == "float64" else "scan_sums_u8_tc_kernel",
                                  "achieved": scan_gbps, "peak": hbm_peak, "unit": "GB/s", "frac": scan_gbps / hbm_peak,
                                  "algorithmic_bytes_per_launch": bytes_per * n * p_loc,
                                  "note": "slowest rank's streaming kernel; its columns are only 2,000 entries (16 KB) long"})

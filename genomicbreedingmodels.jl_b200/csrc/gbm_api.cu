@@ -173,8 +173,18 @@ struct DevBuf {
 // streaming sums over a resident matrix of either storage type.  mt: Q is [1 | side vectors] (M + 1 columns)
 // and the FP64 tensor-pipe kernel of scan_mt.cu runs (records of `stride` doubles); otherwise the streaming
 // kernels of scan.cu / scan_u8.cu with their own record stride.
+struct SideDigits {  // fixed-point digits of the side vectors for the tensor-core code kernel (scan_u8_tc.cu)
+  const int8_t* d = nullptr;
+  int64_t ld = 0;
+  double scale[2] = {0.0, 0.0};
+};
+static bool use_u8_tensor_cores() {  // GBM_U8_TC=0: the CUDA-core kernel of scan_u8.cu (read at every call: tests toggle it)
+  const char* e = getenv("GBM_U8_TC");
+  return e ? atoi(e) != 0 : true;
+}
+
 static void scan_sums_any(const gbm_matrix* m, int64_t j0, int64_t pb, const double* Q, int M, int64_t ldq,
-                          double* rec, bool mt = false, int mt_stride = 0) {
+                          double* rec, bool mt = false, int mt_stride = 0, const SideDigits* dg = nullptr) {
   State& st = state();
   if (m->dtype == 0) {
     if (mt)
@@ -184,7 +194,10 @@ static void scan_sums_any(const gbm_matrix* m, int64_t j0, int64_t pb, const dou
   } else {
     const int stride = mt ? mt_stride : scan_record_stride(M, false);
     const int Mp = stride - 2 - (M == 0 ? 1 : 0);
-    if (!mt && Mp <= 2) {
+    if (!mt && M >= 1 && M <= 2 && dg && dg->d && use_u8_tensor_cores()) {
+      launch_scan_sums_u8_tc(m->d8 + j0 * m->ld8, m->n, pb, m->ld8, dg->d, dg->ld, dg->scale, M, stride, rec, st.sm_count,
+                             st.stream);
+    } else if (!mt && Mp <= 2) {
       launch_scan_sums_u8(m->d8 + j0 * m->ld8, m->n, pb, m->ld8, Q, Mp, ldq, rec, st.sm_count, st.stream);
     } else if (mt) {
       launch_scan_sums_mt_u8(m->d8 + j0 * m->ld8, m->n, pb, m->ld8, Q, M, ldq, rec, stride, st.sm_count, st.stream);
@@ -355,9 +368,11 @@ struct Pass {
   int tcount, M, stride;
   bool mt;
   DevBuf<double> dQ, dyMy, dWy;
-  Pass(int64_t t0_, int tcount_, int M_, int stride_, bool mt_, size_t qcount, int k, cudaStream_t s)
+  DevBuf<int8_t> dDigits;  // M <= 2 without the tensor-pipe kernel: digits for the code matrix' tcgen05 kernel
+  SideDigits digits;
+  Pass(int64_t t0_, int tcount_, int M_, int stride_, bool mt_, size_t qcount, int k, size_t digit_bytes, cudaStream_t s)
       : t0(t0_), tcount(tcount_), M(M_), stride(stride_), mt(mt_), dQ(qcount, s), dyMy(tcount_ > 0 ? tcount_ : 1, s),
-        dWy(static_cast<size_t>(tcount_ > 0 ? tcount_ : 1) * (k > 0 ? k : 1), s) {}
+        dWy(static_cast<size_t>(tcount_ > 0 ? tcount_ : 1) * (k > 0 ? k : 1), s), dDigits(digit_bytes, s) {}
 };
 
 static std::vector<std::unique_ptr<Pass>> build_passes(const SideVectors& sv, int64_t n, int64_t T) {
@@ -375,7 +390,21 @@ static std::vector<std::unique_ptr<Pass>> build_passes(const SideVectors& sv, in
     const int stride = mt ? 2 + M : scan_record_stride(M, false);
     const int ncols = mt ? M + 1 : stride - 2;  // columns of the device Q (padded for the FMA kernels)
     const int first = mt ? 1 : 0;               // [1 | W | R] for the tensor-pipe kernel
-    std::unique_ptr<Pass> ps(new Pass(t0, tcount, M, stride, mt, static_cast<size_t>(ldq) * ncols, k, st.stream));
+    const bool want_digits = !mt && M >= 1 && M <= 2;
+    const int64_t ldd = scan_u8_tc_digit_rows(n);
+    std::unique_ptr<Pass> ps(new Pass(t0, tcount, M, stride, mt, static_cast<size_t>(ldq) * ncols, k,
+                                      want_digits ? static_cast<size_t>(16) * ldd : 0, st.stream));
+    std::vector<int8_t> hdig;
+    if (want_digits) {
+      std::vector<double> hq(static_cast<size_t>(n) * M);
+      if (k > 0) memcpy(hq.data(), sv.W.data(), sizeof(double) * n * k);
+      memcpy(hq.data() + static_cast<size_t>(n) * k, sv.R.data() + static_cast<size_t>(t0) * n, sizeof(double) * n * tcount);
+      hdig.resize(static_cast<size_t>(16) * ldd);
+      scan_u8_tc_build_digits(hq.data(), n, M, n, hdig.data(), ldd, ps->digits.scale);
+      GBM_CUDA(cudaMemcpyAsync(ps->dDigits.p, hdig.data(), hdig.size(), cudaMemcpyHostToDevice, st.stream));
+      ps->digits.d = ps->dDigits.p;
+      ps->digits.ld = ldd;
+    }
     GBM_CUDA(cudaMemsetAsync(ps->dQ.p, 0, sizeof(double) * ldq * ncols, st.stream));
     std::vector<double> ones;
     if (mt) {
@@ -420,7 +449,7 @@ static void scan_block(const gbm_matrix& mat, int64_t p_blk, const std::vector<s
     DevBuf<double> rec_tmp(own_rec ? static_cast<size_t>(p_blk) * ps->stride : 0, st.stream);
     struct { double* p; } rec{own_rec ? rec_tmp.p : rec_bufs[pi]};
     if (main_span) main_span->start();
-    scan_sums_any(&mat, 0, p_blk, ps->dQ.p, ps->M, ldq, rec.p, ps->mt, ps->stride);
+    scan_sums_any(&mat, 0, p_blk, ps->dQ.p, ps->M, ldq, rec.p, ps->mt, ps->stride, &ps->digits);
     if (main_span) main_span->stop();
     FinalizeParams fp;
     fp.n = n;

@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "tcgen05.cuh"
 
 namespace gbm {
 
@@ -46,61 +47,6 @@ struct I8Params {
   int* counter;
 };
 
-// ---- tcgen05 / TMEM wrappers ----------------------------------------------------------
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, u8 x u8 -> s32, M = N = 128, K = 32
-__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                       uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
-      : "memory");
-}
-// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per lane
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// Shared-memory matrix descriptor for an MN-major, SWIZZLE_128B operand tile of 8-bit codes as
-// written by TMA (128-byte rows = 128 consecutive matrix rows of one marker; 8 markers form a
-// 1024-byte swizzle atom): start address, LBO = 0 (a single 128-row block), SBO = 1024 B between
-// 8-marker groups, descriptor version 1, layout type SWIZZLE_128B.
-__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);  // [0,14)  start address >> 4
-  d |= static_cast<uint64_t>(0u) << 16;                    // [16,30) leading byte offset >> 4
-  d |= static_cast<uint64_t>(1024u >> 4) << 32;            // [32,46) stride byte offset >> 4
-  d |= static_cast<uint64_t>(1u) << 46;                    // [46,48) version = 1 (Blackwell)
-  d |= static_cast<uint64_t>(2u) << 61;                    // [61,64) SWIZZLE_128B
-  return d;
-}
 // Instruction descriptor: dense, no saturate, D = s32 (2), A = B = unsigned 8-bit (0), both
 // MN-major (1), N >> 3 = 16, M >> 4 = 8.
 constexpr uint32_t kI8Idesc = (2u << 4) | (0u << 7) | (0u << 10) | (1u << 15) | (1u << 16) | (16u << 17) | (8u << 24);

@@ -62,6 +62,13 @@ void launch_neglog10_sf(const double* stat, int64_t len, int dist, double df, do
 // records have the same meaning and stride as the Float64 kernel's (Mp = 0 tracks min-nonzero).
 void launch_scan_sums_u8(const uint8_t* A8, int64_t n, int64_t p, int64_t ld8, const double* Q, int Mp, int64_t ldq,
                          double* rec, int sm_count, cudaStream_t stream);
+// scan_u8_tc.cu: the same sums with the dots on the tcgen05 INT8 tensor cores (side vectors as seven base-256
+// fixed-point digits, exact integer contractions).  digits: 16 x ldd int8 (device), built by scan_u8_tc_build_digits
+// on the host from the n x M side vectors (M <= 2); scale[m] = 2^(E_m - 55).
+int scan_u8_tc_digit_rows(int64_t n);
+void scan_u8_tc_build_digits(const double* Q, int64_t n, int M, int64_t ldq, int8_t* digits, int64_t ld, double* scale);
+void launch_scan_sums_u8_tc(const uint8_t* A8, int64_t n, int64_t p, int64_t ld8, const int8_t* digits, int64_t ldd,
+                            const double* scale, int M, int rec_stride, double* rec, int sm_count, cudaStream_t stream);
 void launch_pack_u8(const double* A, int64_t n, int64_t p, int64_t lda, uint8_t* out, int64_t ld8,
                     unsigned long long* inexact, cudaStream_t stream);
 void launch_decode_u8(const uint8_t* A8, int64_t n, int64_t p, int64_t ld8, double* out, int64_t ldo,

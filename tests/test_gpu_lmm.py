@@ -158,4 +158,7 @@ def test_gwasreml_reference_objective_end_to_end(gbm):
     Ksym = 0.5 * (prep.K + prep.K.T)
     z_ref, _, _ = lo.refobj_scan(prep.G, prep.y, Ksym)
     assert np.array_equal(f.extras["idx_cols"], prep.idx_cols)
-    assert np.max(np.abs(f.b_hat - z_ref)) < 1e-8 * max(1.0, np.abs(z_ref).max())
+    # the device's Kstd and NumPy's differ in the last bits; the symmetrised standardised K is indefinite with
+    # eigenvalues close to -delta_min, so the fitted s2u (which scales z directly here: no sigma^2 is profiled out)
+    # amplifies that: 1e-6 end to end, 1e-8 on identical K (test_reference_objective_mode_matches_its_oracle)
+    assert np.max(np.abs(f.b_hat - z_ref)) < 1e-6 * max(1.0, np.abs(z_ref).max())

@@ -243,3 +243,43 @@ def test_config5_reduced_multi_trait_from_host(gbm, kind):
         cf = go.scan_closed_form(A[:, sub], ys, pc)
         err = np.abs(host["stat"][sub, t] - cf["stat_ols"]) / np.maximum(np.abs(cf["stat_ols"]), 1e-4 * np.abs(cf["stat_ols"]).max())
         assert err.max() < 1e-9, (t, err.max())
+
+
+@pytest.mark.parametrize("n,p", [(300, 500), (1000, 129), (10_000, 700), (131, 64), (70_001, 40)])
+def test_tensor_core_code_scan_equals_the_cuda_core_kernel_and_the_oracle(gbm, n, p, monkeypatch):
+    """scan_u8_tc.cu (dots as exact u8 x s8 integer contractions on the tcgen05 tensor cores, side vectors as seven
+    base-256 digits) against the CUDA-core code kernel (GBM_U8_TC=0) and the oracle's closed form: ragged n and p
+    (TMA zero fill), n beyond one s32 accumulation segment (65,536 rows), side vectors with a wide dynamic range."""
+    rng = np.random.default_rng(n + p)
+    A = synth.block(21, n, 0, p, synth.KIND_TETRAPLOID)
+    A[:, 3] = 0.75  # constant code
+    A[:, 4] = 0.0
+    y = rng.normal(size=n) * np.exp(rng.normal(size=n) * 3.0)  # heavy tails: entries from 1e-4 to 1e4 of the scale
+    pc = rng.normal(size=n)
+    pc[rng.integers(0, n, 5)] *= 1e3
+    dm = gbm.DeviceMatrix.upload(A)
+    pk = dm.pack()
+    assert pk is not None
+    monkeypatch.setenv("GBM_U8_TC", "1")
+    tc = pk.scan(y, pc[:, None], model=1)
+    tc1 = pk.scan(y, None, model=0)  # one side vector only
+    monkeypatch.setenv("GBM_U8_TC", "0")
+    cc = pk.scan(y, pc[:, None], model=1)
+    cc1 = pk.scan(y, None, model=0)
+    monkeypatch.delenv("GBM_U8_TC")
+    f64 = dm.scan(y, pc[:, None], model=1)
+    dm.free()
+    pk.free()
+    keep = f64["keep"]
+    assert np.array_equal(tc["keep"], keep) and np.array_equal(cc["keep"], keep) and not keep[3] and not keep[4]
+    assert tc["sd"][3] == 0.0 and tc["sd"][4] == 0.0
+    for key in ("mean", "sd"):  # integer sums in both code kernels: bit for bit
+        assert np.array_equal(tc[key], cc[key]), key
+    for a, b in ((tc, cc), (tc, f64), (tc1, cc1)):
+        for key in ("beta", "se", "stat"):
+            x, z = a[key][keep], b[key][keep]
+            assert np.nanmax(np.abs(x - z)) <= 1e-10 * max(1.0, np.nanmax(np.abs(z))), key
+    pcn = pc - pc.mean()
+    ref = go.scan_closed_form(A[:, keep], y - y.mean(), pcn / np.linalg.norm(pcn))
+    got = tc["stat"][keep, 0]
+    assert np.max(np.abs(got - ref["stat_lmm"]) / np.maximum(np.abs(ref["stat_lmm"]), 1e-4 * np.abs(ref["stat_lmm"]).max())) < 1e-9
