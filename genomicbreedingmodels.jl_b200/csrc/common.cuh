@@ -59,6 +59,7 @@ struct State {
   void* up_stage[kHostSlots] = {};
   size_t up_bytes = 0;
   cudaEvent_t up_copied[kHostSlots] = {};
+  int lane_choice = 0, lane_choice_threads = 0;  // gbm_scan_host: measured lane (1 host packer, 2 copy engine)
   double h2d_ms = 0, kernel_ms = 0, main_ms = 0, d2h_ms = 0;
   int64_t launches = 0;
   int64_t packed_blocks = 0, host_packed_blocks = 0, h2d_bytes = 0;

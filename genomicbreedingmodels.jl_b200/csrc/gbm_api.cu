@@ -1633,13 +1633,23 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
   // reads slow the packing cores down by more than they add (1 GPU x 16 threads: 1.29 M markers/s together
   // against 1.71-1.76 M for the host lane alone; 8 GPUs x 4 threads: 2.28 M together, 2.33 M copy lane
   // alone), on a host with more memory bandwidth per core it pays.
+  // Which lane wins depends on the host (cores and memory bandwidth per GPU, how many ranks share them), so the
+  // choice is MEASURED: the first call with enough blocks runs two blocks through the host lane alone, two through
+  // the copy-engine lane alone (every rank of a multi-GPU job does this at the same time, so the contention is the
+  // real one) and keeps the faster for the rest of the call and for later calls of this State.  Until then, and
+  // for short calls: the host lane with >= 12 host threads for this rank, else the copy-engine lane.
+  const bool can_host = want_codes && !device_src && host_threads() >= 2;
   bool host_lane = want_codes && !device_src && host_threads() >= 12;
   bool raw_lane = !host_lane;
+  bool forced = false;
   if (const char* e = getenv("GBM_SCAN_HOST_LANES")) {
-    const bool can_host = want_codes && !device_src && host_threads() >= 2;
-    if (!strcmp(e, "host") && can_host) host_lane = true, raw_lane = false;
-    if (!strcmp(e, "copy")) host_lane = false, raw_lane = true;
-    if (!strcmp(e, "both") && can_host) host_lane = true, raw_lane = pinned;
+    if (!strcmp(e, "host") && can_host) host_lane = true, raw_lane = false, forced = true;
+    if (!strcmp(e, "copy")) host_lane = false, raw_lane = true, forced = true;
+    if (!strcmp(e, "both") && can_host) host_lane = true, raw_lane = pinned, forced = true;
+  }
+  if (!forced && can_host && st.lane_choice_threads == host_threads() && st.lane_choice != 0) {
+    host_lane = st.lane_choice == 1;
+    raw_lane = !host_lane;
   }
   // column blocks of ~128 MB of Float64
   const int64_t ldd = round_up(n, 16);
@@ -1693,6 +1703,7 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
   }
   const bool contiguous = (lda == n && ldd == n);
   const bool stage_pageable = !pinned && host_threads() >= 2;
+  const bool pinned_or_staged = pinned || stage_pageable;  // the copy-engine lane is asynchronous
   if (stage_pageable) {
     static_assert(State::kRawSlots <= State::kHostSlots, "one pinned staging block per copy-engine slot");
     if (st.up_bytes < need) {
@@ -1707,6 +1718,7 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
   }
 
   int64_t next = 0;              // next unassigned block
+  int64_t end_blk = nblk;        // blocks [next, end_blk) are handed out (the lane calibration runs in slices)
   std::deque<int64_t> handback;  // blocks the host lane could not pack
   int64_t code_blocks = 0, host_blocks = 0, h2d_bytes = 0;
   auto take_block = [&](bool for_raw) -> int64_t {
@@ -1715,7 +1727,7 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
       handback.pop_front();
       return bi;
     }
-    return next < nblk ? next++ : -1;
+    return next < end_blk ? next++ : -1;
   };
   struct RawSlot {
     int state = 0;  // 0 free, 1 copy in flight, 2 device pack in flight
@@ -1811,7 +1823,6 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
   };
   const std::function<void()> idle = [&] { raw_service(false); };
 
-  raw_service(false);
   // host lane: up to kHost blocks are queued with the packer ahead of the one being waited for, so the
   // workers never join between blocks
   struct HostSlots {
@@ -1823,6 +1834,10 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
         if (j) pack_wait(j, nullptr), j = nullptr;
     }
   } hs;
+  // hands out and finishes blocks [next, end) with the lanes currently switched on
+  auto run_until = [&](int64_t end) {
+  end_blk = end;
+  raw_service(false);
   while (host_lane) {
     while (hs.count < kHost) {
       const int64_t bi = take_block(false);
@@ -1875,9 +1890,39 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
     raw_service(false);
   }
   // drain: whatever is left goes through the copy-engine lane
-  while (raw_busy > 0 || next < nblk || !handback.empty()) {
+  while (raw_busy > 0 || next < end_blk || !handback.empty()) {
     if (!raw_lane) GBM_THROW(GBM_ERR_RUNTIME, "gbm_scan_host: internal scheduling error");
     raw_service(true);
+  }
+  };
+  const bool calibrate = !forced && can_host && pinned_or_staged && nblk >= 12 &&
+                         !(st.lane_choice_threads == host_threads() && st.lane_choice != 0);
+  if (calibrate) {
+    auto drain_all = [&] {
+      GBM_CUDA(cudaStreamSynchronize(st.stream));
+      GBM_CUDA(cudaStreamSynchronize(st.copy_stream));
+      GBM_CUDA(cudaStreamSynchronize(st.raw_stream));
+    };
+    host_lane = true, raw_lane = false;
+    auto t0 = std::chrono::steady_clock::now();
+    run_until(3);
+    drain_all();
+    const double t_host = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    const bool still_codes = host_lane;  // the host lane switches itself off at the first block that is not all codes
+    host_lane = false, raw_lane = true;
+    t0 = std::chrono::steady_clock::now();
+    run_until(std::min<int64_t>(next + 3, nblk));
+    drain_all();
+    const double t_copy = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (still_codes) {  // dosage data: remember the faster lane; other data always travels as Float64
+      st.lane_choice = t_host <= t_copy ? 1 : 2;
+      st.lane_choice_threads = host_threads();
+      host_lane = st.lane_choice == 1;
+      raw_lane = !host_lane;
+    }
+    run_until(nblk);
+  } else {
+    run_until(nblk);
   }
   all.stop();
   out.copy_back(p, T);

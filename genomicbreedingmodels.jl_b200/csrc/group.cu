@@ -13,6 +13,7 @@
 // own single-GPU entry points, each running on the State bound to the calling thread.
 #include "../../include/gbm_b200.h"
 
+#include <dlfcn.h>
 #include <nccl.h>
 #include <string.h>
 
@@ -30,12 +31,61 @@
 
 using namespace gbm;
 
-#define GBM_NCCL(call)                                                                                          \
-  do {                                                                                                          \
-    ncclResult_t r__ = (call);                                                                                  \
-    if (r__ != ncclSuccess)                                                                                     \
-      throw ::gbm::Error{GBM_ERR_CUDA, std::string(#call) + ": " + ncclGetErrorString(r__) + " (" + __FILE__ + ":" + \
-                                           std::to_string(__LINE__) + ")"};                                     \
+// NCCL is bound at run time, at the first group creation: a process that already holds a libnccl.so.2 (PyTorch
+// ships and loads its own, newer than the system's) must keep using THAT copy -- a second library with the same
+// soname cannot be loaded next to it, and loading the system's first would break a later `import torch`.  Order:
+// an already loaded libnccl.so.2, then $GBM_NCCL_LIB, then the system's libnccl.so.2.
+namespace {
+struct NcclApi {
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  decltype(&ncclCommInitAll) CommInitAll = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclBroadcast) Broadcast = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+};
+
+const NcclApi& nccl() {
+  static std::mutex m;
+  static NcclApi api;
+  static bool ready = false;
+  std::lock_guard<std::mutex> lk(m);
+  if (ready) return api;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!h)
+    if (const char* e = getenv("GBM_NCCL_LIB")) h = dlopen(e, RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) throw Error{GBM_ERR_CUDA, std::string("multi-GPU groups need NCCL: libnccl.so.2 could not be loaded (") + dlerror() + ")"};
+  auto sym = [&](const char* name) {
+    void* p = dlsym(h, name);
+    if (!p) throw Error{GBM_ERR_CUDA, std::string("libnccl.so.2 lacks ") + name};
+    return p;
+  };
+  api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+  api.CommInitAll = reinterpret_cast<decltype(api.CommInitAll)>(sym("ncclCommInitAll"));
+  api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+  api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+  api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+  api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+  api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(sym("ncclBroadcast"));
+  api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+  api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+  ready = true;
+  return api;
+}
+}  // namespace
+
+#define GBM_NCCL(call)                                                                                            \
+  do {                                                                                                            \
+    ncclResult_t r__ = (call);                                                                                    \
+    if (r__ != ncclSuccess)                                                                                       \
+      throw ::gbm::Error{GBM_ERR_CUDA, std::string(#call) + ": " + nccl().GetErrorString(r__) + " (" + __FILE__ + ":" + \
+                                           std::to_string(__LINE__) + ")"};                                       \
   } while (0)
 
 namespace {
@@ -183,7 +233,7 @@ struct gbm_group {
       Dev<int> d(1);
       cudaStream_t s = state().stream;
       GBM_CUDA(cudaMemcpyAsync(d.p, &rc, sizeof(int), cudaMemcpyHostToDevice, s));
-      GBM_NCCL(ncclAllReduce(d.p, d.p, 1, ncclInt, ncclMax, comm[0], s));
+      GBM_NCCL(nccl().AllReduce(d.p, d.p, 1, ncclInt, ncclMax, comm[0], s));
       GBM_CUDA(cudaMemcpyAsync(&worst, d.p, sizeof(int), cudaMemcpyDeviceToHost, s));
       GBM_CUDA(cudaStreamSynchronize(s));
     });
@@ -208,7 +258,7 @@ struct gbm_group {
       Dev<double> d(count);
       cudaStream_t s = state().stream;
       GBM_CUDA(cudaMemcpyAsync(d.p, vals[g].data(), sizeof(double) * count, cudaMemcpyHostToDevice, s));
-      GBM_NCCL(ncclAllReduce(d.p, d.p, count, ncclDouble, op, comm[g], s));
+      GBM_NCCL(nccl().AllReduce(d.p, d.p, count, ncclDouble, op, comm[g], s));
       GBM_CUDA(cudaMemcpyAsync(vals[g].data(), d.p, sizeof(double) * count, cudaMemcpyDeviceToHost, s));
       GBM_CUDA(cudaStreamSynchronize(s));
     });
@@ -225,7 +275,7 @@ struct gbm_group {
       Dev<int64_t> d(world);
       cudaStream_t s = state().stream;
       GBM_CUDA(cudaMemcpyAsync(d.p + rank_of(g), &local[g], sizeof(int64_t), cudaMemcpyHostToDevice, s));
-      GBM_NCCL(ncclAllGather(d.p + rank_of(g), d.p, 1, ncclInt64, comm[g], s));
+      GBM_NCCL(nccl().AllGather(d.p + rank_of(g), d.p, 1, ncclInt64, comm[g], s));
       GBM_CUDA(cudaMemcpyAsync(all.data(), d.p, sizeof(int64_t) * world, cudaMemcpyDeviceToHost, s));
       GBM_CUDA(cudaStreamSynchronize(s));
     });
@@ -252,15 +302,15 @@ void gather_rows(gbm_group& G, int g, const T* src, const std::vector<int64_t>& 
   }
   // one process per GPU: blocks travel over NVLink into a rank-major device buffer, then to the host array
   Dev<T> full(static_cast<size_t>(total) * height);
-  GBM_NCCL(ncclGroupStart());
+  GBM_NCCL(nccl().GroupStart());
   for (int r = 0; r < G.world; ++r) {
     const size_t bytes = static_cast<size_t>(counts[r]) * height * sizeof(T);
     if (!bytes) continue;
     T* slot = full.p + offs[r] * height;
-    GBM_NCCL(ncclBroadcast(r == me ? static_cast<const void*>(src) : static_cast<const void*>(slot), slot, bytes, ncclUint8,
+    GBM_NCCL(nccl().Broadcast(r == me ? static_cast<const void*>(src) : static_cast<const void*>(slot), slot, bytes, ncclUint8,
                            r, G.comm[g], s));
   }
-  GBM_NCCL(ncclGroupEnd());
+  GBM_NCCL(nccl().GroupEnd());
   for (int r = 0; r < G.world; ++r)
     if (counts[r] > 0)
       GBM_CUDA(cudaMemcpy2DAsync(host + offs[r], total * sizeof(T), full.p + offs[r] * height, counts[r] * sizeof(T),
@@ -279,7 +329,7 @@ struct NcclSum : ShardedAllReduce {
   cudaStream_t s;
   NcclSum(ncclComm_t c, cudaStream_t st) : comm(c), s(st) {}
   void sum(double* buf, int64_t count) override {
-    GBM_NCCL(ncclAllReduce(buf, buf, static_cast<size_t>(count), ncclDouble, ncclSum, comm, s));
+    GBM_NCCL(nccl().AllReduce(buf, buf, static_cast<size_t>(count), ncclDouble, ncclSum, comm, s));
   }
 };
 
@@ -370,7 +420,7 @@ GrmTimes sharded_grm(gbm_sharded* m, int grm_type, int ploidy, int flags, int64_
   G.run([&](int g) {
     cudaStream_t s = state().stream;
     if (G.world > 1)
-      GBM_NCCL(ncclAllReduce(m->dK[g], m->dK[g], static_cast<size_t>(n) * n, ncclDouble, ncclSum, G.comm[g], s));
+      GBM_NCCL(nccl().AllReduce(m->dK[g], m->dK[g], static_cast<size_t>(n) * n, ncclDouble, ncclSum, G.comm[g], s));
     ok(gbm_grm_finalize(m->dK[g], n, scale));  // synchronises the stream
     if (launches) launches[g] += 1;
   });
@@ -622,7 +672,7 @@ int gbm_group_create_local(int n_gpus, const int* devices, gbm_group** out) {
     int cur = 0;
     cudaGetDevice(&cur);
     G->comm.assign(n_gpus, nullptr);
-    GBM_NCCL(ncclCommInitAll(G->comm.data(), n_gpus, dev.data()));
+    GBM_NCCL(nccl().CommInitAll(G->comm.data(), n_gpus, dev.data()));
     cudaSetDevice(cur);
   } catch (...) {
     for (auto& w : G->workers) w->stop();
@@ -637,7 +687,7 @@ int gbm_group_unique_id(void* id) {
   if (!id) GBM_THROW(GBM_ERR_ARGUMENT, "gbm_group_unique_id: null output");
   static_assert(sizeof(ncclUniqueId) == GBM_GROUP_ID_BYTES, "ncclUniqueId is 128 bytes");
   ncclUniqueId u;
-  GBM_NCCL(ncclGetUniqueId(&u));
+  GBM_NCCL(nccl().GetUniqueId(&u));
   memcpy(id, &u, sizeof(u));
   GBM_GROUP_END
 }
@@ -656,7 +706,7 @@ int gbm_group_create_rank(const void* id, int world, int rank, gbm_group** out) 
   ncclUniqueId u;
   memcpy(&u, id, sizeof(u));
   G->comm.assign(1, nullptr);
-  GBM_NCCL(ncclCommInitRank(&G->comm[0], world, u, rank));
+  GBM_NCCL(nccl().CommInitRank(&G->comm[0], world, u, rank));
   *out = G.release();
   GBM_GROUP_END
 }
@@ -676,7 +726,7 @@ int gbm_group_free(gbm_group* g) {
   {
     std::lock_guard<std::mutex> lk(g->mutex);
     for (ncclComm_t c : g->comm)
-      if (c) ncclCommDestroy(c);
+      if (c) nccl().CommDestroy(c);
     if (g->threaded) {
       try {
         g->run([&](int) { shutdown_state(state()); });

@@ -28,6 +28,18 @@ from .core import DeviceMatrix, _f64
 GROUP_ID_BYTES = 128
 
 
+def _prefer_torch_nccl():
+    """libgbm_b200.so binds NCCL at its first group creation and prefers a libnccl.so.2 that the process already
+    holds.  PyTorch bundles its own (newer) NCCL; if the system's copy were loaded first, a later `import torch` in
+    the same process would fail to resolve its symbols.  So when PyTorch is installed, load it (and with it its NCCL)
+    before the first group is made.  A Julia process has no such concern: it gets the system's libnccl.so.2."""
+    try:
+        import torch  # noqa: F401
+        import torch.distributed  # noqa: F401
+    except Exception:
+        pass
+
+
 class Group:
     def __init__(self, handle: c_void_p):
         self._h = handle
@@ -38,6 +50,7 @@ class Group:
     @classmethod
     def local(cls, n_gpus: int, devices=None) -> "Group":
         """All ``n_gpus`` GPUs driven by this process (``gbm_group_create_local``)."""
+        _prefer_torch_nccl()
         h = c_void_p()
         dev = None
         if devices is not None:
@@ -47,6 +60,7 @@ class Group:
 
     @staticmethod
     def unique_id() -> bytes:
+        _prefer_torch_nccl()
         buf = ctypes.create_string_buffer(GROUP_ID_BYTES)
         check(_lib.load().gbm_group_unique_id(buf))
         return buf.raw
@@ -56,6 +70,7 @@ class Group:
         """One process per GPU; the GPU is the one of ``gbm_b200.init`` (``gbm_group_create_rank``)."""
         if len(uid) != GROUP_ID_BYTES:
             raise _lib.ArgumentError("the group id must be 128 bytes")
+        _prefer_torch_nccl()
         _lib.lib()  # gbm_init(LOCAL_RANK)
         h = c_void_p()
         check(_lib.load().gbm_group_create_rank(ctypes.c_char_p(uid), int(world), int(rank), byref(h)))

@@ -42,6 +42,13 @@ def test_library_is_sm100a_with_tma_and_dmma():
     sass = subprocess.run(["cuobjdump", "-sass", gbm_b200.build()], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
     assert "UTMALDG" in sass and "DMMA" in sass and "SYNCS" in sass
+    # the tcgen05 kernels (grm_i8.cu, scan_u8_tc.cu): kind::i8 MMA, tcgen05.ld, tcgen05.commit
+    assert "UTCIMMA" in sass and "LDTM" in sass and "UTCBAR" in sass
+    # sm_100a only: no other architecture in the fat binary
+    import re
+
+    elf = subprocess.run(["cuobjdump", "-lelf", gbm_b200.build()], capture_output=True, text=True).stdout
+    assert set(re.findall(r"sm_\d+a?", elf)) == {"sm_100a"}
 
 
 def _has_gpu():
