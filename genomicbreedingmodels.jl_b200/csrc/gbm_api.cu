@@ -1686,7 +1686,8 @@ int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const doub
     GBM_CUDA(cudaMallocHost(reinterpret_cast<void**>(&st.raw_flag_host), sizeof(unsigned long long) * kRaw));
   }
   constexpr int kHost = State::kHostSlots;
-  if (host_lane && st.code_bytes < need8) {
+  // the calibration below may switch the host lane on even when it does not start the call
+  if ((host_lane || (can_host && !forced)) && st.code_bytes < need8) {
     for (int b = 0; b < kHost; ++b) {
       if (st.host_codes[b]) cudaFreeHost(st.host_codes[b]);
       if (st.dev_codes[b]) cudaFree(st.dev_codes[b]);
