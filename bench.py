@@ -150,6 +150,12 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def log(msg: str):
+    """progress on stderr (stdout carries the one JSON line)"""
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def shard_bounds(p: int, world: int, rank: int):
     return (p * rank) // world, (p * (rank + 1)) // world
 
@@ -329,6 +335,7 @@ def main():
         # one pass over the shard: streaming-sums kernel + finalisation kernel, device outputs in place
         return plan.run(outs["beta"], outs["se"], outs["stat"], outs["nlp"], outs["mean"], outs["sd"], keep)
 
+    log(f"scan step: {p_loc} markers on this rank")
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -435,6 +442,7 @@ def main():
             "note": "one pass over the genotypes; FP64 tensor pipe (DMMA m8n8k4) for the 22 dots per marker"}
 
     if not args.no_e2e:
+        log("e2e from host memory")
         line.update(run_e2e(args, gbm_b200, _lib, lib, n, p_loc, j0, world, model, Y, C, barrier))
 
     plan.free()
@@ -447,6 +455,7 @@ def main():
         grp = (multigpu.Group.from_torch_distributed() if world > 1
                else multigpu.Group.from_rank(multigpu.Group.unique_id(), 1, 0))
     if not args.no_pipeline:
+        log("whole sharded gwaslmm")
         res = run_pipeline_group(gbm_b200, _lib, grp, dm, n, p, ys, world, rank)
         if rank == 0:
             line["pipeline"] = res
@@ -455,10 +464,12 @@ def main():
         dm.free()
     if not args.no_configs:
         # BASELINE configs[3]: grmploidyaware + gwaslmm on tetraploid frequencies, n = 2,000 x p = 500,000
+        log("configs[3] tetraploid")
         res = run_config3_tetraploid(gbm_b200, _lib, grp, world, rank, measured_peaks()[0])
         if rank == 0:
             line["config3_tetraploid"] = res
         # BASELINE configs[4]: 20 traits x n = 20,000 x p = 2,000,000 streamed from host memory
+        log("configs[4] multi-trait stream")
         res = run_config4_stream(args, gbm_b200, _lib, lib, world, rank, j0, barrier)
         if rank == 0:
             line["config4_multitrait_stream"] = res
@@ -466,6 +477,7 @@ def main():
         grp.free()
 
     if rank == 0 and not args.no_grm:
+        log("GRM")
         gn, gp = args.grm_n, args.grm_p
         gm = gbm_b200.DeviceMatrix.generate(SEED, gn, gp, KIND_DIPLOID)
         dK = torch.empty(gn * gn, dtype=torch.float64, device="cuda")
