@@ -296,6 +296,18 @@ static void launch_grm_wcorrection(const double* A, int64_t n, int64_t p, int64_
   GBM_CUDA(cudaFreeAsync(w, stream));
 }
 
+// lower-triangle tile list (row block i >= column block j): pass 0 the full tiles, pass 1 the ragged edge row
+__global__ void grm_tiles_kernel(int2* __restrict__ ij, int nb, int ragged) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int q = 0;
+  for (int pass = 0; pass < 2; ++pass)
+    for (int i = 0; i < nb; ++i)
+      for (int j = 0; j <= i; ++j) {
+        const bool edge = ragged && (i == nb - 1);  // j <= i, so an edge column block implies an edge row block
+        if ((pass == 0) != edge) ij[q++] = make_int2(i, j);
+      }
+}
+
 void launch_grm_accumulate(const double* A, int64_t n, int64_t p, int64_t lda, const double* mu, double* dK,
                            int sm_count, cudaStream_t stream, bool centred) {
   if (n <= 0 || p <= 0) return;
@@ -320,26 +332,17 @@ void launch_grm_accumulate(const double* A, int64_t n, int64_t p, int64_t lda, c
   const int steps_per_slice = (steps_total + best_s - 1) / best_s;
   const int num_slices = (steps_total + steps_per_slice - 1) / steps_per_slice;
 
-  // tile table
-  int2* h_ij = nullptr;
-  GBM_CUDA(cudaMallocHost(&h_ij, sizeof(int2) * num_tiles));
-  // full tiles first, ragged edge tiles (last row/column block) last: with the dynamic fetch the
-  // cheap edge tiles fill the tail of the schedule
-  int q = 0;
+  // tile table, built on the device (no pinned host table, no synchronisation per call): full tiles first, ragged
+  // edge tiles (last row/column block) last -- with the dynamic fetch the cheap edge tiles fill the tail of the
+  // schedule
   const bool ragged = (n % kTile) != 0;
-  for (int pass = 0; pass < 2; ++pass)
-    for (int i = 0; i < nb; ++i)
-      for (int j = 0; j <= i; ++j) {
-        const bool edge = ragged && (i == nb - 1);  // j <= i, so an edge column block implies an edge row block
-        if ((pass == 0) != edge) h_ij[q++] = make_int2(i, j);
-      }
   const int num_full_tiles = ragged ? num_tiles - nb : num_tiles;
   int2* d_ij = nullptr;
   int* d_counter = nullptr;
   GBM_CUDA(cudaMallocAsync(&d_ij, sizeof(int2) * num_tiles, stream));
   GBM_CUDA(cudaMallocAsync(&d_counter, sizeof(int), stream));
   GBM_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(int), stream));
-  GBM_CUDA(cudaMemcpyAsync(d_ij, h_ij, sizeof(int2) * num_tiles, cudaMemcpyHostToDevice, stream));
+  grm_tiles_kernel<<<1, 32, 0, stream>>>(d_ij, nb, ragged ? 1 : 0);
 
   alignas(64) CUtensorMap tmA;
   make_tensor_map_2d_f64(&tmA, A, static_cast<uint64_t>(n), static_cast<uint64_t>(p), static_cast<uint64_t>(lda),
@@ -364,8 +367,6 @@ void launch_grm_accumulate(const double* A, int64_t n, int64_t p, int64_t lda, c
   if (centred) launch_grm_wcorrection(A, n, p, lda, mu, dK, stream);
   GBM_CUDA(cudaFreeAsync(d_ij, stream));
   GBM_CUDA(cudaFreeAsync(d_counter, stream));
-  GBM_CUDA(cudaStreamSynchronize(stream));  // h_ij must outlive the async copy
-  GBM_CUDA(cudaFreeHost(h_ij));
 }
 
 // scale the lower triangle and mirror it: 32x32 tiles through shared memory

@@ -13,14 +13,17 @@
 // Kernel (one CTA per SM, 192 threads, warp-specialised):
 //   warp 0  producer lane: dynamic work fetch, TMA loads (SWIZZLE_128B boxes of 128 rows x
 //           128 markers; the matrix is column-major, i.e. MN-major operands, which kind::i8
-//           supports) into a 6-slot ring;
-//   warp 1  MMA lane: per slot four tcgen05.mma (M = N = 128, K = 32) on smem descriptors,
+//           supports) into a 4-slot ring: one box for the tile's 128 rows i, two for its 256 rows i';
+//   warp 1  MMA lane: per slot four tcgen05.mma (M = 128, N = 256, K = 32) on smem descriptors,
 //           tcgen05.commit frees the slot / publishes the accumulator; owns the TMEM allocation
-//           (2 x 128 columns: the next item accumulates while the previous one drains);
+//           (all 512 columns = 2 x 256: the next item accumulates while the previous one drains);
 //   warps 2-5  epilogue: tcgen05.ld 32 lanes x 32 columns, convert to double, RED.ADD.F64 into
 //           the n x n integer-valued matrix (exact, order-independent).
-// A work item is (128x128 lower-triangle tile, slice of <= 32768 markers): 32768 * 240^2 < 2^31,
-// so the s32 accumulators cannot overflow.
+// A work item is (128 x 256 tile touching the lower triangle, slice of <= 32768 markers): 32768 * 240^2 < 2^31,
+// so the s32 accumulators cannot overflow.  N = 256 instead of the first version's 128 x 128 tiles: an MMA reads
+// (128 + 256) x 32 bytes of shared memory for 128 x 256 x 32 MACs, 25 % fewer bytes per MAC -- at N = 128 the
+// tensor pipe waited on the 128 B/clk shared-memory port (40 % active, ncu); the bigger tile also halves the
+// number of times a code slab is pulled through L2.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -29,14 +32,15 @@
 
 namespace gbm {
 
-constexpr int kI8Tile = 128;                         // rows and columns of an output tile
+constexpr int kI8Tile = 128;                         // rows i of an output tile (M of the MMA)
+constexpr int kI8TileN = 256;                        // rows i' of an output tile (N of the MMA)
 constexpr int kI8KB = 128;                           // markers per ring slot
-constexpr int kI8Stages = 6;
-constexpr int kI8OperandBytes = kI8Tile * kI8KB;     // 16384: 128 markers x 128 rows of codes
-constexpr int kI8StageBytes = 2 * kI8OperandBytes;   // row block + column block
+constexpr int kI8Stages = 4;
+constexpr int kI8OperandBytes = kI8Tile * kI8KB;     // 16384: 128 markers x 128 rows of codes (one TMA box)
+constexpr int kI8StageBytes = 3 * kI8OperandBytes;   // row block + two boxes of the column block
 constexpr int kI8SliceStages = 256;                  // 256 * 128 = 32768 markers per accumulation
 constexpr int kI8Threads = 192;
-constexpr int kI8TmemCols = 256;                     // two 128-column accumulators
+constexpr int kI8TmemCols = 512;                     // two 256-column accumulators: all of TMEM
 constexpr int kI8SmemBytes = kI8Stages * kI8StageBytes + 1024 /*alignment slack*/ + 256;
 
 struct I8Params {
@@ -48,8 +52,14 @@ struct I8Params {
 };
 
 // Instruction descriptor: dense, no saturate, D = s32 (2), A = B = unsigned 8-bit (0), both
-// MN-major (1), N >> 3 = 16, M >> 4 = 8.
-constexpr uint32_t kI8Idesc = (2u << 4) | (0u << 7) | (0u << 10) | (1u << 15) | (1u << 16) | (16u << 17) | (8u << 24);
+// MN-major (1), N >> 3 = 32, M >> 4 = 8.
+constexpr uint32_t kI8Idesc = (2u << 4) | (0u << 7) | (0u << 10) | (1u << 15) | (1u << 16) | ((kI8TileN >> 3) << 17) | ((kI8Tile >> 4) << 24);
+
+// MN-major SWIZZLE_128B operand that is TWO 128-wide blocks along MN (the 256 rows i'): the blocks are the two TMA
+// boxes, 16384 bytes apart (leading byte offset)
+__device__ __forceinline__ uint64_t make_desc_mn_sw128_wide(uint32_t smem_addr) {
+  return make_desc_mn_sw128(smem_addr) | (static_cast<uint64_t>(kI8OperandBytes >> 4) << 16);
+}
 
 __global__ void __launch_bounds__(kI8Threads, 1)
     grm_i8_kernel(const __grid_constant__ CUtensorMap tmA, const I8Params prm) {
@@ -107,7 +117,8 @@ __global__ void __launch_bounds__(kI8Threads, 1)
           meta[stage] = make_int4(ij.x, ij.y, (s == s0 ? 1 : 0) | (s == s1 - 1 ? 2 : 0), 0);
           mbar_arrive_expect_tx(&full_bar[stage], kI8StageBytes);
           tma_load_2d(dst, &tmA, ij.x * kI8Tile, s * kI8KB, &full_bar[stage], kEvictNormal);
-          tma_load_2d(dst + kI8OperandBytes, &tmA, ij.y * kI8Tile, s * kI8KB, &full_bar[stage], kEvictNormal);
+          tma_load_2d(dst + kI8OperandBytes, &tmA, ij.y * kI8TileN, s * kI8KB, &full_bar[stage], kEvictNormal);
+          tma_load_2d(dst + 2 * kI8OperandBytes, &tmA, ij.y * kI8TileN + kI8Tile, s * kI8KB, &full_bar[stage], kEvictNormal);
           if (++stage == kI8Stages) {
             stage = 0;
             phase ^= 1u;
@@ -141,12 +152,12 @@ __global__ void __launch_bounds__(kI8Threads, 1)
         }
         const uint32_t a_base = smem_u32(smem + stage * kI8StageBytes);
         const uint32_t b_base = a_base + kI8OperandBytes;
-        const uint32_t d_addr = tmem_base + static_cast<uint32_t>(buf * kI8Tile);
+        const uint32_t d_addr = tmem_base + static_cast<uint32_t>(buf * kI8TileN);
 #pragma unroll
         for (int k4 = 0; k4 < kI8KB / 32; ++k4) {
-          // K = 32 markers = four 8-marker swizzle atoms = 4096 bytes further into the tile
+          // K = 32 markers = four 8-marker swizzle atoms = 4096 bytes further into each box
           const uint64_t da = make_desc_mn_sw128(a_base + k4 * 4096);
-          const uint64_t db = make_desc_mn_sw128(b_base + k4 * 4096);
+          const uint64_t db = make_desc_mn_sw128_wide(b_base + k4 * 4096);
           mma_i8(d_addr, da, db, kI8Idesc, ((md.z & 1) && k4 == 0) ? 0u : 1u);
         }
         tc_commit(&empty_bar[stage]);  // slot is free once these MMAs have read it
@@ -175,13 +186,13 @@ __global__ void __launch_bounds__(kI8Threads, 1)
       const int4 em = emeta[buf];
       if (em.z < 0) break;
       const int64_t row = static_cast<int64_t>(em.x) * kI8Tile + q * 32 + lane;
-      const int64_t col0 = static_cast<int64_t>(em.y) * kI8Tile;
-      const uint32_t taddr = tmem_base + static_cast<uint32_t>(buf * kI8Tile) + (static_cast<uint32_t>(q * 32) << 16);
+      const int64_t col0 = static_cast<int64_t>(em.y) * kI8TileN;
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(buf * kI8TileN) + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < kI8Tile / 32; ++c) {
+      for (int c = 0; c < kI8TileN / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
-        if (c == kI8Tile / 32 - 1) {
+        if (c == kI8TileN / 32 - 1) {
           // everything this warp needs is in registers: hand the accumulator back
           tc_fence_before();
           __syncwarp();
@@ -205,24 +216,31 @@ __global__ void __launch_bounds__(kI8Threads, 1)
   if (warp == 1) tmem_dealloc(tmem_base, kI8TmemCols);
 }
 
+// tile table on the device: row block bi (128 rows) x column block bj (256 rows), every pair that touches the
+// lower triangle (bj <= bi / 2), in row-block order -- no host table, no pinned allocation, no synchronisation
+__global__ void grm_i8_tiles_kernel(int2* __restrict__ ij, int nb) {
+  const int bi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bi >= nb) return;
+  // tiles before row block bi: sum_{b < bi} (b / 2 + 1) = h (h - 1) + (bi odd ? h : 0) + bi, h = bi / 2
+  const int h = bi >> 1;
+  int q = h * (h - 1) + ((bi & 1) ? h : 0) + bi;
+  for (int bj = 0; bj <= h; ++bj) ij[q++] = make_int2(bi, bj);
+}
+
 void launch_grm_i8_accumulate(const uint8_t* A8, int64_t n, int64_t p, int64_t ld8, double* dG, int sm_count,
                               cudaStream_t stream) {
   if (n <= 0 || p <= 0) return;
   const int nb = static_cast<int>((n + kI8Tile - 1) / kI8Tile);
-  const int num_tiles = nb * (nb + 1) / 2;
+  int num_tiles = 0;
+  for (int bi = 0; bi < nb; ++bi) num_tiles += bi / 2 + 1;
   const int steps_total = static_cast<int>((p + kI8KB - 1) / kI8KB);
   const int num_slices = (steps_total + kI8SliceStages - 1) / kI8SliceStages;
-  int2* h_ij = nullptr;
-  GBM_CUDA(cudaMallocHost(&h_ij, sizeof(int2) * num_tiles));
-  int q = 0;
-  for (int i = 0; i < nb; ++i)
-    for (int j = 0; j <= i; ++j) h_ij[q++] = make_int2(i, j);
   int2* d_ij = nullptr;
   int* d_counter = nullptr;
   GBM_CUDA(cudaMallocAsync(&d_ij, sizeof(int2) * num_tiles, stream));
   GBM_CUDA(cudaMallocAsync(&d_counter, sizeof(int), stream));
   GBM_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(int), stream));
-  GBM_CUDA(cudaMemcpyAsync(d_ij, h_ij, sizeof(int2) * num_tiles, cudaMemcpyHostToDevice, stream));
+  grm_i8_tiles_kernel<<<(nb + 127) / 128, 128, 0, stream>>>(d_ij, nb);
 
   alignas(64) CUtensorMap tmA;
   make_tensor_map_2d_u8_sw128(&tmA, A8, static_cast<uint64_t>(n), static_cast<uint64_t>(p),
@@ -243,8 +261,6 @@ void launch_grm_i8_accumulate(const uint8_t* A8, int64_t n, int64_t p, int64_t l
   GBM_CUDA(cudaGetLastError());
   GBM_CUDA(cudaFreeAsync(d_ij, stream));
   GBM_CUDA(cudaFreeAsync(d_counter, stream));
-  GBM_CUDA(cudaStreamSynchronize(stream));
-  GBM_CUDA(cudaFreeHost(h_ij));
 }
 
 // ---- U_i += sum_j S_j c_ij  (exact integers in FP64), one thread per 8 rows x column slab ----

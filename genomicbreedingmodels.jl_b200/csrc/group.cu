@@ -439,7 +439,8 @@ double sharded_kstd_pc1(gbm_sharded* m, double* pc1_host, int* steps, int64_t* l
   static const bool no_shard = [] { const char* e = getenv("GBM_PC1_SHARDED"); return e && atoi(e) == 0; }();
   std::vector<double> eig(G.n_local, 0.0);
   std::vector<int> conv(G.n_local, 0), iters(G.n_local, 0);
-  const bool sharded = G.world > 1 && n >= 1024 && !no_shard;
+  // below n ~ 4,000 a step's two passes over the block cost less than the all-reduce that sharding adds
+  const bool sharded = G.world > 1 && n >= 4096 && !no_shard;
   if (sharded) {
     const int64_t ld = round_up(n, 16);
     G.run([&](int g) {

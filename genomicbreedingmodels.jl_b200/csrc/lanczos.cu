@@ -59,6 +59,36 @@ __global__ void __launch_bounds__(256) symv_kernel(const double* __restrict__ B,
   }
 }
 
+// The same with one CTA per column, for blocks with few columns (a rank's share of a sharded matrix): a single warp
+// walking a whole 80 KB column is a ~40 us chain of dependent HBM latencies however few columns there are; 256
+// threads cut it to a few rounds.  Fixed-order block reduction.
+__global__ void __launch_bounds__(256) symv_cta_kernel(const double* __restrict__ B, int64_t n, int64_t ld,
+                                                       const double* __restrict__ v, double* __restrict__ y) {
+  __shared__ double sh[8];
+  const int64_t j = blockIdx.x;
+  const int64_t n2 = n >> 1;
+  const double2* __restrict__ c2 = reinterpret_cast<const double2*>(B + j * ld);
+  const double2* __restrict__ v2 = reinterpret_cast<const double2*>(v);
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int64_t i = threadIdx.x;
+  for (; i + 256 < n2; i += 512) {
+    const double2 a = c2[i], b = v2[i], c = c2[i + 256], d = v2[i + 256];
+    s0 = fma(a.x, b.x, s0);
+    s1 = fma(a.y, b.y, s1);
+    s2 = fma(c.x, d.x, s2);
+    s3 = fma(c.y, d.y, s3);
+  }
+  for (; i < n2; i += 256) {
+    const double2 a = c2[i], b = v2[i];
+    s0 = fma(a.x, b.x, s0);
+    s1 = fma(a.y, b.y, s1);
+  }
+  double s = (s0 + s1) + (s2 + s3);
+  if ((n & 1) && threadIdx.x == 0) s = fma(B[j * ld + n - 1], v[n - 1], s);
+  const double t = block_sum_256(s, sh);
+  if (threadIdx.x == 0) y[j] = t;
+}
+
 // partial[c][i] = sum over the c-th chunk of columns of Z[i, j] u[j]   (Z column-major, pitch ld): thread = row,
 // so every load is coalesced; the chunks are summed in a fixed order by gemv_n_reduce_kernel (deterministic)
 constexpr int kGemvChunks = 64;
@@ -89,33 +119,54 @@ __global__ void __launch_bounds__(256) gemv_n_reduce_kernel(const double* __rest
   w[i] = s;
 }
 
-// c[k] = V[:, k] . w for k < cols: one CTA per column, fixed-order reduction
+// c[k] = V[:, k] . w for k < cols: one CTA per column, fixed-order reduction (four independent FMA chains per thread:
+// the loop is latency-bound, not bandwidth-bound)
 __global__ void __launch_bounds__(256) dots_kernel(const double* __restrict__ V, int64_t n, int64_t ldv,
                                                    const double* __restrict__ w, double* __restrict__ c) {
   __shared__ double sh[8];
   const double* col = V + static_cast<int64_t>(blockIdx.x) * ldv;
-  double s = 0.0;
-  for (int64_t i = threadIdx.x; i < n; i += 256) s = fma(col[i], w[i], s);
-  const double t = block_sum_256(s, sh);
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int64_t i = threadIdx.x;
+  for (; i + 768 < n; i += 1024) {
+    s0 = fma(col[i], w[i], s0);
+    s1 = fma(col[i + 256], w[i + 256], s1);
+    s2 = fma(col[i + 512], w[i + 512], s2);
+    s3 = fma(col[i + 768], w[i + 768], s3);
+  }
+  for (; i < n; i += 256) s0 = fma(col[i], w[i], s0);
+  const double t = block_sum_256((s0 + s1) + (s2 + s3), sh);
   if (threadIdx.x == 0) c[blockIdx.x] = t;
 }
 
-// w -= V[:, 0..cols) c ; alpha[j] (+)= c[j] (the projection on the current vector is the Lanczos alpha)
+// w -= V[:, 0..cols) c ; alpha[j] (+)= c[j] (the projection on the current vector is the Lanczos alpha).
+// A CTA owns 32 rows; its 8 warps split the columns (warp g takes k = g, g + 8, ...: every load is a coalesced
+// 256-byte row segment), so a thread walks cols / 8 columns instead of all of them -- with n = 10,000 rows there are
+// only 10,000 row-threads, and one thread per row walking 280 columns was a 40 us dependent-latency chain per call.
+// The 8 partial sums are added in a fixed order (deterministic).
 __global__ void __launch_bounds__(256) project_out_kernel(const double* __restrict__ V, int64_t n, int64_t ldv, int cols,
                                                           const double* __restrict__ c, double* __restrict__ w,
                                                           double* __restrict__ alpha, int j, int accumulate) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  __shared__ double part[8][32];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 32 + lane;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   if (i < n) {
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int k = 0;
-    for (; k + 4 <= cols; k += 4) {
+    int k = g;
+    for (; k + 24 < cols; k += 32) {
       a0 = fma(V[(k + 0) * ldv + i], c[k + 0], a0);
-      a1 = fma(V[(k + 1) * ldv + i], c[k + 1], a1);
-      a2 = fma(V[(k + 2) * ldv + i], c[k + 2], a2);
-      a3 = fma(V[(k + 3) * ldv + i], c[k + 3], a3);
+      a1 = fma(V[(k + 8) * ldv + i], c[k + 8], a1);
+      a2 = fma(V[(k + 16) * ldv + i], c[k + 16], a2);
+      a3 = fma(V[(k + 24) * ldv + i], c[k + 24], a3);
     }
-    for (; k < cols; ++k) a0 = fma(V[k * ldv + i], c[k], a0);
-    w[i] -= (a0 + a1) + (a2 + a3);
+    for (; k < cols; k += 8) a0 = fma(V[k * ldv + i], c[k], a0);
+  }
+  part[g][lane] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (g == 0 && i < n) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += part[q][lane];
+    w[i] -= t;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) alpha[j] = accumulate ? alpha[j] + c[j] : c[j];
 }
@@ -274,7 +325,7 @@ static bool lanczos_core(int64_t n, Apply&& apply, double tol, int max_iter, dou
       apply(vj, w);
       for (int pass = 0; pass < 2; ++pass) {  // classical Gram-Schmidt, twice
         dots_kernel<<<j + 1, 256, 0, stream>>>(V, n, ldv, w, c);
-        project_out_kernel<<<row_blocks, 256, 0, stream>>>(V, n, ldv, j + 1, c, w, alpha, j, pass);
+        project_out_kernel<<<static_cast<unsigned>((n + 31) / 32), 256, 0, stream>>>(V, n, ldv, j + 1, c, w, alpha, j, pass);
       }
       norm_next_kernel<<<1, 256, 0, stream>>>(w, n, V + static_cast<int64_t>(j + 1) * ldv, beta, j);
       m = j + 1;
@@ -381,7 +432,12 @@ bool lanczos_top_singular_sharded(const double* Zg, int64_t n, int64_t nc, int64
   const unsigned symv_grid =
       static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((nc + 7) / 8, static_cast<int64_t>(sm_count) * 8)));
   auto apply = [&](const double* v, double* out) {
-    if (nc > 0) symv_kernel<<<symv_grid, 256, 0, stream>>>(Zg, n, nc, ld, v, u.p);  // u = Zg' v
+    if (nc > 0) {  // u = Zg' v
+      if (nc < 8192)
+        symv_cta_kernel<<<static_cast<unsigned>(nc), 256, 0, stream>>>(Zg, n, ld, v, u.p);
+      else
+        symv_kernel<<<symv_grid, 256, 0, stream>>>(Zg, n, nc, ld, v, u.p);
+    }
     gemv_n_partial_kernel<<<dim3(row_blocks, kGemvChunks), 256, 0, stream>>>(Zg, n, nc, ld, u.p, partial.p);
     gemv_n_reduce_kernel<<<row_blocks, 256, 0, stream>>>(partial.p, n, out);         // this rank's Zg u
     ar->sum(out, n);                                                                   // sum over the ranks

@@ -41,7 +41,7 @@ def main():
     z, idx = sg.scan(ys, pc, _lib.MODEL_LMM)
     one = sg.sm.gwas(ys, model=_lib.MODEL_LMM, grm_type=_lib.GRM_PLOIDY_AWARE)  # the whole pipeline in ONE call
     # sharded PC1 at a size where the Lanczos path runs (n >= 1024): against the single-GPU routine on rank 0's GPU
-    n2, p2 = 1536, 4096
+    n2, p2 = 4224, 4096
     c0, c1 = sharded.shard_bounds(p2, world, rank)
     dm2 = gbm_b200.DeviceMatrix.generate(seed, n2, c1 - c0, synth.KIND_DIPLOID, col0=c0)
     sg2 = sharded.ShardedGWAS(dm2, p2, c0)
