@@ -1293,6 +1293,11 @@ int gbm_grm(const gbm_matrix* m, int grm_type, int ploidy, int flags, double* K,
 // ------------------------------------------------------------------------------------
 // K standardisation + PC1
 // ------------------------------------------------------------------------------------
+// Lanczos stops when the Ritz residual estimate is below kPc1Tol * theta; the explicit residual ||Bx - theta x|| is
+// then required to be <= 2e-13 theta.  With the ~3e-3 relative gap of the standardised GRM's top eigenvalue that puts
+// PC1 within ~1e-10 of the exact vector, two orders below the 1e-9 the statistics are held to.
+static constexpr double kPc1Tol = 1e-13;
+
 int gbm_kstd_pc1(const double* K, int64_t n, double* Kstd, double* pc1, double* eig_ms) {
   GBM_API_BEGIN
   require_ready();
@@ -1340,7 +1345,7 @@ int gbm_kstd_pc1(const double* K, int64_t n, double* Kstd, double* pc1, double* 
       eig.start();
       int iters = 0;
       double theta = 0.0;
-      have_pc1 = lanczos_top_eigenpair(mat, n, ldm, gram, 1e-14, 3000, dx.p, &theta, &iters, st.sm_count, st.stream);
+      have_pc1 = lanczos_top_eigenpair(mat, n, ldm, gram, kPc1Tol, 3000, dx.p, &theta, &iters, st.sm_count, st.stream);
       eig.stop();
       if (have_pc1) {
         copy_out(pc1, dx.p, sizeof(double) * n, st.stream);
@@ -1351,7 +1356,11 @@ int gbm_kstd_pc1(const double* K, int64_t n, double* Kstd, double* pc1, double* 
       }
     };
     // odd n: B = Z Z' has an odd pitch (128-bit loads of its columns would be misaligned), Z is padded: gram operator
-    if (!force_cusolver && !force_lanczos && (n >= 12000 || force_gram || (n >= 1024 && (n & 1)))) run_lanczos(dZ.p, ld, true);
+    // n >= 1,024: Lanczos on Z itself (operator Z Z', never formed).  Even n up to 12,288 take the fused one-pass
+    // step (a column in shared memory: its dot with v and its update of w from one read of Z), larger or odd n the
+    // two-pass step; either way the n^3 SYRK for B = Z Z' is not paid.  GBM_PC1_SOLVER=lanczos keeps the older route
+    // through B (one symmetric matrix-vector product per step).
+    if (!force_cusolver && !force_lanczos && (n >= 1024 || force_gram)) run_lanczos(dZ.p, ld, true);
     if (have_pc1) {
       all.stop();
       GBM_CUDA(cudaStreamSynchronize(st.stream));

@@ -469,7 +469,7 @@ double sharded_kstd_pc1(gbm_sharded* m, double* pc1_host, int* steps, int64_t* l
       GBM_CUDA(cudaEventRecord(e0, s));
       double theta = 0.0;
       int it = 0;
-      const bool okc = lanczos_top_singular_sharded(Z.p, n, nc, ld, &ar, 1e-14, 3000, x.p, &theta, &it, st.sm_count, s);
+      const bool okc = lanczos_top_singular_sharded(Z.p, n, nc, ld, &ar, 1e-13, 3000, x.p, &theta, &it, st.sm_count, s);
       GBM_CUDA(cudaEventRecord(e1, s));
       GBM_CUDA(cudaStreamSynchronize(s));
       float ms = 0.f;

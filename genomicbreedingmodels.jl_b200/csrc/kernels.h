@@ -130,7 +130,7 @@ double lmm_null_lam0(int Q0, const double* S, const double* Cr, int64_t ldcr, co
 // lanczos.cu --------------------------------------------------------------------------
 // Largest eigenpair of the symmetric PSD matrix B (n x n, pitch ldb even, 16-byte aligned, device) by Lanczos with
 // full reorthogonalisation; x_dev (device, n) gets the unit eigenvector.  Returns false when the explicit residual
-// ||B x - theta x|| <= max(20 tol, 2e-13) theta was not reached within max_iter steps (the caller then uses cuSOLVER).
+// ||B x - theta x|| <= max(5 tol, 2e-13) theta was not reached within max_iter steps (the caller then uses cuSOLVER).
 // gram = true: the operator is B B' for a general (non-symmetric) n x n matrix B, applied as two matrix-vector
 // products per step (B B' is never formed); x is then the top left singular vector of B.
 bool lanczos_top_eigenpair(const double* B, int64_t n, int64_t ldb, bool gram, double tol, int max_iter, double* x_dev,

@@ -22,6 +22,19 @@ namespace gbm {
 
 namespace {
 
+// the same for any block size up to 1024 threads (sh: 32 doubles)
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) t += sh[w];  // fixed order
+  return t;  // valid in thread 0
+}
+
 __device__ __forceinline__ double block_sum_256(double v, double* sh) {
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
@@ -119,22 +132,136 @@ __global__ void __launch_bounds__(256) gemv_n_reduce_kernel(const double* __rest
   w[i] = s;
 }
 
+// ---- fused gram step: partial[cta][:] = sum over the CTA's columns j of Z[:, j] (Z[:, j] . v) ----------------------
+// One pass over Z per Lanczos step instead of two (u = Z'v, then w = Z u): a CTA takes whole columns; a column is
+// brought into shared memory by one bulk copy (TMA, double-buffered, so the next column streams in while this one
+// is used), the 512 threads take its dot product with v (each thread keeps ITS rows of v in registers for the whole
+// kernel), and the column is added, scaled by that dot, to the thread's rows of the CTA's partial result (registers
+// as well).  The partials of all CTAs are summed in a fixed order by gemv_n_reduce_kernel: deterministic.
+// Needs 2 n doubles of shared memory: n <= 12,288; larger n use the two-pass kernels.
+constexpr int kFusedThreads = 512;
+template <int RPT>  // rows per thread: n <= 512 * RPT
+__global__ void __launch_bounds__(kFusedThreads, 1)
+    gram_fused_kernel(const double* __restrict__ Z, int64_t n, int64_t ncols, int64_t ld, const double* __restrict__ v,
+                      double* __restrict__ partial) {
+  extern __shared__ __align__(128) uint8_t fsm[];
+  const int64_t npad = (n + 1) / 2 * 2;
+  double* buf0 = reinterpret_cast<double*>(fsm);
+  double* buf1 = buf0 + npad;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(buf1 + npad);  // [2]
+  double* red = reinterpret_cast<double*>(bar + 2);           // [16] warp partials
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  double vr[RPT], acc[RPT];
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int64_t i = tid + static_cast<int64_t>(k) * kFusedThreads;
+    vr[k] = i < n ? v[i] : 0.0;
+    acc[k] = 0.0;
+  }
+  const uint32_t bytes = static_cast<uint32_t>(n * sizeof(double));
+  int64_t j = blockIdx.x;
+  if (tid == 0 && j < ncols) {
+    mbar_arrive_expect_tx(&bar[0], bytes);
+    tma_load_1d(buf0, Z + j * ld, bytes, &bar[0]);
+  }
+  uint32_t ph[2] = {0, 0};
+  int b = 0;
+  for (; j < ncols; j += gridDim.x, b ^= 1) {
+    const int64_t jn = j + gridDim.x;
+    if (tid == 0 && jn < ncols) {  // the other buffer was released by the __syncthreads that ended its column
+      mbar_arrive_expect_tx(&bar[b ^ 1], bytes);
+      tma_load_1d(b ? buf0 : buf1, Z + jn * ld, bytes, &bar[b ^ 1]);
+    }
+    mbar_wait(&bar[b], ph[b]);
+    ph[b] ^= 1u;
+    const double* col = b ? buf1 : buf0;
+    double d0 = 0.0, d1 = 0.0;  // the column is read from shared memory twice (dot, then update): registers hold v and acc
+#pragma unroll
+    for (int k = 0; k < RPT; k += 2) {
+      const int64_t i0 = tid + static_cast<int64_t>(k) * kFusedThreads, i1 = i0 + kFusedThreads;
+      d0 = fma(i0 < n ? col[i0] : 0.0, vr[k], d0);
+      d1 = fma(i1 < n ? col[i1] : 0.0, vr[k + 1], d1);
+    }
+    double d = d0 + d1;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) d += __shfl_xor_sync(0xffffffffu, d, m);
+    if (lane == 0) red[warp] = d;
+    __syncthreads();
+    double u = 0.0;
+#pragma unroll
+    for (int w = 0; w < kFusedThreads / 32; ++w) u += red[w];  // fixed order, the same in every thread
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+      const int64_t i = tid + static_cast<int64_t>(k) * kFusedThreads;
+      acc[k] = fma(i < n ? col[i] : 0.0, u, acc[k]);
+    }
+    __syncthreads();  // red and this column's buffer may be reused
+  }
+  double* out = partial + static_cast<int64_t>(blockIdx.x) * n;
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) {
+    const int64_t i = tid + static_cast<int64_t>(k) * kFusedThreads;
+    if (i < n) out[i] = acc[k];
+  }
+}
+
+// w[i] = sum_c partial[c][i] over `chunks` partial vectors, fixed order
+__global__ void __launch_bounds__(256) partial_reduce_kernel(const double* __restrict__ partial, int64_t n, int chunks,
+                                                             double* __restrict__ w) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= n) return;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int c = 0;
+  for (; c + 4 <= chunks; c += 4) {
+    s0 += partial[static_cast<int64_t>(c) * n + i];
+    s1 += partial[static_cast<int64_t>(c + 1) * n + i];
+    s2 += partial[static_cast<int64_t>(c + 2) * n + i];
+    s3 += partial[static_cast<int64_t>(c + 3) * n + i];
+  }
+  for (; c < chunks; ++c) s0 += partial[static_cast<int64_t>(c) * n + i];
+  w[i] = (s0 + s1) + (s2 + s3);
+}
+
+constexpr int64_t kFusedMaxN = 512 * 24;
+static size_t gram_fused_smem(int64_t n) { return static_cast<size_t>((n + 1) / 2 * 2) * 16 + 16 + 16 * 8 + 128; }
+
+// launches the fused step on `grid` CTAs; returns false when n is too large for it
+static bool launch_gram_fused(const double* Z, int64_t n, int64_t ncols, int64_t ld, const double* v, double* partial,
+                              int grid, cudaStream_t stream) {
+  if (n > kFusedMaxN || (ld & 1) || (n & 1)) return false;  // bulk copies need 16-byte multiples
+  const size_t smem = gram_fused_smem(n);
+  auto go = [&](auto kern) {
+    GBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, kFusedThreads, smem, stream>>>(Z, n, ncols, ld, v, partial);
+  };
+  if (n <= 512 * 8) go(gram_fused_kernel<8>);
+  else if (n <= 512 * 16) go(gram_fused_kernel<16>);
+  else go(gram_fused_kernel<24>);
+  return true;
+}
+
 // c[k] = V[:, k] . w for k < cols: one CTA per column, fixed-order reduction (four independent FMA chains per thread:
 // the loop is latency-bound, not bandwidth-bound)
-__global__ void __launch_bounds__(256) dots_kernel(const double* __restrict__ V, int64_t n, int64_t ldv,
-                                                   const double* __restrict__ w, double* __restrict__ c) {
-  __shared__ double sh[8];
+__global__ void __launch_bounds__(1024) dots_kernel(const double* __restrict__ V, int64_t n, int64_t ldv,
+                                                    const double* __restrict__ w, double* __restrict__ c) {
+  __shared__ double sh[32];
   const double* col = V + static_cast<int64_t>(blockIdx.x) * ldv;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   int64_t i = threadIdx.x;
-  for (; i + 768 < n; i += 1024) {
+  for (; i + 3072 < n; i += 4096) {
     s0 = fma(col[i], w[i], s0);
-    s1 = fma(col[i + 256], w[i + 256], s1);
-    s2 = fma(col[i + 512], w[i + 512], s2);
-    s3 = fma(col[i + 768], w[i + 768], s3);
+    s1 = fma(col[i + 1024], w[i + 1024], s1);
+    s2 = fma(col[i + 2048], w[i + 2048], s2);
+    s3 = fma(col[i + 3072], w[i + 3072], s3);
   }
-  for (; i < n; i += 256) s0 = fma(col[i], w[i], s0);
-  const double t = block_sum_256((s0 + s1) + (s2 + s3), sh);
+  for (; i < n; i += 1024) s0 = fma(col[i], w[i], s0);
+  const double t = block_sum((s0 + s1) + (s2 + s3), sh);
   if (threadIdx.x == 0) c[blockIdx.x] = t;
 }
 
@@ -172,20 +299,25 @@ __global__ void __launch_bounds__(256) project_out_kernel(const double* __restri
 }
 
 // beta[j] = ||w||, V[:, j+1] = w / beta[j]   (single CTA)
-__global__ void __launch_bounds__(256) norm_next_kernel(const double* __restrict__ w, int64_t n, double* __restrict__ vnext,
-                                                        double* __restrict__ beta, int j) {
-  __shared__ double sh[8];
+__global__ void __launch_bounds__(1024) norm_next_kernel(const double* __restrict__ w, int64_t n, double* __restrict__ vnext,
+                                                         double* __restrict__ beta, int j) {
+  __shared__ double sh[32];
   __shared__ double inv;
-  double s = 0.0;
-  for (int64_t i = threadIdx.x; i < n; i += 256) s = fma(w[i], w[i], s);
-  const double t = block_sum_256(s, sh);
+  double s0 = 0.0, s1 = 0.0;
+  int64_t i = threadIdx.x;
+  for (; i + 1024 < n; i += 2048) {
+    s0 = fma(w[i], w[i], s0);
+    s1 = fma(w[i + 1024], w[i + 1024], s1);
+  }
+  for (; i < n; i += 1024) s0 = fma(w[i], w[i], s0);
+  const double t = block_sum(s0 + s1, sh);
   if (threadIdx.x == 0) {
     const double b = sqrt(t);
     beta[j] = b;
     inv = b > 0.0 ? 1.0 / b : 0.0;
   }
   __syncthreads();
-  for (int64_t i = threadIdx.x; i < n; i += 256) vnext[i] = w[i] * inv;
+  for (int64_t k = threadIdx.x; k < n; k += 1024) vnext[k] = w[k] * inv;
 }
 
 // deterministic start vector: splitmix64 of the row index, mapped to (-1, 1), normalised by norm_next_kernel
@@ -313,7 +445,7 @@ static bool lanczos_core(int64_t n, Apply&& apply, double tol, int max_iter, dou
     GBM_CUDA(cudaMemsetAsync(w, 0, sizeof(double) * ldv, stream));
     const unsigned row_blocks = static_cast<unsigned>((n + 255) / 256);
     start_vector_kernel<<<row_blocks, 256, 0, stream>>>(w, n);
-    norm_next_kernel<<<1, 256, 0, stream>>>(w, n, V, beta, m_max);  // V[:, 0] = unit start vector (beta slot unused)
+    norm_next_kernel<<<1, 1024, 0, stream>>>(w, n, V, beta, m_max);  // V[:, 0] = unit start vector (beta slot unused)
 
     std::vector<double> ha, hb, s;
     bool converged = false;
@@ -324,10 +456,10 @@ static bool lanczos_core(int64_t n, Apply&& apply, double tol, int max_iter, dou
       const double* vj = V + static_cast<int64_t>(j) * ldv;
       apply(vj, w);
       for (int pass = 0; pass < 2; ++pass) {  // classical Gram-Schmidt, twice
-        dots_kernel<<<j + 1, 256, 0, stream>>>(V, n, ldv, w, c);
+        dots_kernel<<<j + 1, 1024, 0, stream>>>(V, n, ldv, w, c);
         project_out_kernel<<<static_cast<unsigned>((n + 31) / 32), 256, 0, stream>>>(V, n, ldv, j + 1, c, w, alpha, j, pass);
       }
-      norm_next_kernel<<<1, 256, 0, stream>>>(w, n, V + static_cast<int64_t>(j + 1) * ldv, beta, j);
+      norm_next_kernel<<<1, 1024, 0, stream>>>(w, n, V + static_cast<int64_t>(j + 1) * ldv, beta, j);
       m = j + 1;
       if (m == next_check || m == m_max) {
         GBM_CUDA(cudaGetLastError());
@@ -350,7 +482,7 @@ static bool lanczos_core(int64_t n, Apply&& apply, double tol, int max_iter, dou
     if (converged) {
       GBM_CUDA(cudaMemcpyAsync(sdev, s.data(), sizeof(double) * m, cudaMemcpyHostToDevice, stream));
       combine_kernel<<<row_blocks, 256, 0, stream>>>(V, n, ldv, m, sdev, w);
-      norm_next_kernel<<<1, 256, 0, stream>>>(w, n, x_dev, beta, 0);  // unit norm
+      norm_next_kernel<<<1, 1024, 0, stream>>>(w, n, x_dev, beta, 0);  // unit norm
       // explicit residual ||Op x - theta x|| as the final word
       apply(x_dev, w);
       GBM_CUDA(cudaGetLastError());
@@ -365,7 +497,7 @@ static bool lanczos_core(int64_t n, Apply&& apply, double tol, int max_iter, dou
         r2 += r * r;
       }
       theta = static_cast<double>(rq);
-      converged = sqrt(static_cast<double>(r2)) <= std::max(20.0 * tol, 2e-13) * fabs(theta);
+      converged = sqrt(static_cast<double>(r2)) <= std::max(5.0 * tol, 2e-13) * fabs(theta);
     }
     release();
     if (theta_out) *theta_out = theta;
@@ -398,7 +530,10 @@ bool lanczos_top_eigenpair(const double* B, int64_t n, int64_t ldb, bool gram, d
   if ((ldb & 1) != 0 || (reinterpret_cast<uintptr_t>(B) & 15u) != 0) return false;
   const int64_t ldv = (n + 1) / 2 * 2;
   // gram operator: u = B' v, w = B u through chunk partials
-  Scratch u(gram ? ldv : 0, stream), partial(gram ? static_cast<size_t>(n) * kGemvChunks : 0, stream);
+  const bool fused = gram && n <= kFusedMaxN && !(n & 1) && getenv("GBM_PC1_NO_FUSED") == nullptr;
+  const int fgrid = static_cast<int>(std::min<int64_t>(n, sm_count));
+  Scratch u(gram ? ldv : 0, stream),
+      partial(gram ? static_cast<size_t>(n) * std::max<int64_t>(kGemvChunks, fused ? fgrid : 0) : 0, stream);
   const unsigned row_blocks = static_cast<unsigned>((n + 255) / 256);
   const unsigned symv_grid = static_cast<unsigned>(std::min<int64_t>((n + 7) / 8, static_cast<int64_t>(sm_count) * 8));
   // out = Op v:  Op = B (symmetric), or Op = B B' for the gram operator (B = Z: the eigenvector of Z Z' without
@@ -406,6 +541,8 @@ bool lanczos_top_eigenpair(const double* B, int64_t n, int64_t ldb, bool gram, d
   auto apply = [&](const double* v, double* out) {
     if (!gram) {
       symv_kernel<<<symv_grid, 256, 0, stream>>>(B, n, n, ldb, v, out);
+    } else if (fused && launch_gram_fused(B, n, n, ldb, v, partial.p, fgrid, stream)) {
+      partial_reduce_kernel<<<row_blocks, 256, 0, stream>>>(partial.p, n, fgrid, out);  // one pass over B
     } else {
       symv_kernel<<<symv_grid, 256, 0, stream>>>(B, n, n, ldb, v, u.p);  // u[j] = B[:, j] . v
       gemv_n_partial_kernel<<<dim3(row_blocks, kGemvChunks), 256, 0, stream>>>(B, n, n, ldb, u.p, partial.p);
@@ -427,11 +564,19 @@ bool lanczos_top_singular_sharded(const double* Zg, int64_t n, int64_t nc, int64
                                   int max_iter, double* x_dev, double* theta_out, int* iters_out, int sm_count,
                                   cudaStream_t stream) {
   if ((ld & 1) != 0 || (reinterpret_cast<uintptr_t>(Zg) & 15u) != 0) return false;
-  Scratch u(static_cast<size_t>(std::max<int64_t>(nc, 1)), stream), partial(static_cast<size_t>(n) * kGemvChunks, stream);
+  const bool fused = nc > 0 && n <= kFusedMaxN && !(n & 1) && getenv("GBM_PC1_NO_FUSED") == nullptr;
+  const int fgrid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(nc, sm_count)));
+  Scratch u(static_cast<size_t>(std::max<int64_t>(nc, 1)), stream),
+      partial(static_cast<size_t>(n) * std::max<int64_t>(kGemvChunks, fused ? fgrid : 0), stream);
   const unsigned row_blocks = static_cast<unsigned>((n + 255) / 256);
   const unsigned symv_grid =
       static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((nc + 7) / 8, static_cast<int64_t>(sm_count) * 8)));
   auto apply = [&](const double* v, double* out) {
+    if (fused && launch_gram_fused(Zg, n, nc, ld, v, partial.p, fgrid, stream)) {  // one pass over the block
+      partial_reduce_kernel<<<row_blocks, 256, 0, stream>>>(partial.p, n, fgrid, out);
+      ar->sum(out, n);
+      return;
+    }
     if (nc > 0) {  // u = Zg' v
       if (nc < 8192)
         symv_cta_kernel<<<static_cast<unsigned>(nc), 256, 0, stream>>>(Zg, n, ld, v, u.p);
