@@ -736,6 +736,24 @@ int gbm_last_timing(gbm_timing* t) {
 // ------------------------------------------------------------------------------------
 // matrices
 // ------------------------------------------------------------------------------------
+// owns a half-built matrix until it is handed to the caller (an exception in between frees the slab and the handle)
+struct MatGuard {
+  gbm_matrix* m;
+  explicit MatGuard(gbm_matrix* mm) : m(mm) {}
+  ~MatGuard() {
+    if (m) {
+      if (m->d) cudaFree(m->d);
+      if (m->d8) cudaFree(m->d8);
+      delete m;
+    }
+  }
+  gbm_matrix* release() {
+    gbm_matrix* r = m;
+    m = nullptr;
+    return r;
+  }
+};
+
 static void check_dims(int64_t n, int64_t p, int64_t lda) {
   if (n < 2) GBM_THROW(GBM_ERR_ARGUMENT, "matrix needs at least 2 rows (entries)");
   if (p < 1) GBM_THROW(GBM_ERR_ARGUMENT, "matrix needs at least 1 column (locus-allele)");
@@ -867,6 +885,7 @@ int gbm_matrix_upload_indexed(const double* A, int64_t n0, int64_t p0, int64_t l
     delete m;
     GBM_THROW(GBM_ERR_CUDA, std::string("cudaMalloc of the genotype slab failed: ") + cudaGetErrorString(e));
   }
+  MatGuard guard(m);
   GBM_CUDA(cudaMemsetAsync(m->d, 0, sizeof(double) * m->lda * p, st.stream));
   DevBuf<int64_t> dr(rows ? n : 0, st.stream), dc(cols ? p : 0, st.stream);
   if (rows) GBM_CUDA(cudaMemcpyAsync(dr.p, hr.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, st.stream));
@@ -900,7 +919,7 @@ int gbm_matrix_upload_indexed(const double* A, int64_t n0, int64_t p0, int64_t l
   sp.stop();
   GBM_CUDA(cudaStreamSynchronize(st.stream));
   st.h2d_ms = sp.ms();
-  *out = m;
+  *out = guard.release();
   GBM_API_END
 }
 
@@ -939,11 +958,12 @@ int gbm_matrix_generate(uint64_t seed, int64_t n, int64_t p, int64_t col0, int k
     delete m;
     GBM_THROW(GBM_ERR_CUDA, std::string("cudaMalloc of the genotype slab failed: ") + cudaGetErrorString(e));
   }
+  MatGuard guard(m);
   if (m->lda != n) GBM_CUDA(cudaMemsetAsync(m->d, 0, sizeof(double) * m->lda * p, st.stream));
   launch_generate(m->d, n, p, m->lda, col0, seed, kind, st.stream);
   GBM_CUDA(cudaGetLastError());
   GBM_CUDA(cudaStreamSynchronize(st.stream));
-  *out = m;
+  *out = guard.release();
   GBM_API_END
 }
 
@@ -1174,7 +1194,8 @@ static void grm_accumulate_impl(const gbm_matrix* m, int centre, double* dK, dou
   mainsp.start();
   if (m->dtype == 0) {
     launch_grm_accumulate(m->d, m->n, m->p, m->lda, dmu.p, dK, st.sm_count, st.stream, centre != 0);
-  } else if (use_int8_grm()) {
+  } else if (use_int8_grm() && 57600.0 * static_cast<double>(m->n) * static_cast<double>(m->p) < 9007199254740992.0) {
+    // (U_i = sum_j S_j c_ij <= 240 n * 240 * p must stay an exact FP64 integer)
     // packed codes: exact integer contraction on the tcgen05 INT8 tensor cores (grm_i8.cu)
     const int64_t n = m->n;
     DevBuf<double> dG(static_cast<size_t>(n) * n, st.stream), dS(m->p, st.stream), dU(n, st.stream), dM2(1, st.stream);

@@ -316,9 +316,14 @@ void launch_grm_accumulate(const double* A, int64_t n, int64_t p, int64_t lda, c
   const int steps_total = static_cast<int>((p + kKT - 1) / kKT);
 
   // slice count: fewest slices (<= 16) whose last wave is >= 95 % full, or the best seen
+  // Slices of one tile are combined with FP64 atomics, whose order varies from run to run (last-bit differences in
+  // the sums; inside the 1e-9 budget).  GBM_GRM_DETERMINISTIC=1 forbids slicing: every tile is accumulated by one
+  // CTA in a fixed order, at the price of a less full last wave for small n (n = 10,000 is unsliced anyway).
+  const char* det_env = getenv("GBM_GRM_DETERMINISTIC");
+  const int max_s = (det_env && atoi(det_env) != 0) ? 1 : 16;
   int best_s = 1;
   double best_eff = 0.0;
-  for (int s = 1; s <= 16; ++s) {
+  for (int s = 1; s <= max_s; ++s) {
     if (s > steps_total) break;
     const int64_t items = static_cast<int64_t>(num_tiles) * s;
     const int64_t waves = (items + sm_count - 1) / sm_count;

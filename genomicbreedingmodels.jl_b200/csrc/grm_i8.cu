@@ -7,8 +7,11 @@
 // no tcgen05 kind (grm.cu uses DMMA for Float64 data); for dosage data this path is ~20x
 // faster AND exact.  The centred GRM follows from exact integers,
 //     Kc[i,i'] = ( G[i,i'] - (U_i + U_i')/n + M2/n^2 ) / 240^2 ,   S_j = sum_i c_ij ,
-//     U_i = sum_j S_j c_ij ,   M2 = sum_j S_j^2 ,
-// (all < 2^53, so FP64 holds them exactly; the only rounding is the final combination).
+//     U_i = sum_j S_j c_ij ,   M2 = sum_j S_j^2 .
+// G and U are integers below 2^53 (the API checks 57600 n p < 2^53 and otherwise takes the FP64 route), so their
+// FP64 atomic accumulation is exact and order-independent; M2 may pass 2^53 and is a rounded sum, added in a fixed
+// order (code_sums_final_kernel), so the whole GRM is a deterministic function of the codes; the roundings are
+// M2's (1e-16 relative) and the final combination's.
 //
 // Kernel (one CTA per SM, 192 threads, warp-specialised):
 //   warp 0  producer lane: dynamic work fetch, TMA loads (SWIZZLE_128B boxes of 128 rows x
@@ -304,10 +307,12 @@ void launch_rowdot_u8(const uint8_t* A8, int64_t n, int64_t p, int64_t ld8, cons
   GBM_CUDA(cudaGetLastError());
 }
 
-// S_j = round(mean_j * n * 240) (exact code sums) and M2 += sum_j S_j^2
+// S_j = round(mean_j * n * 240) (exact code sums) and M2 = sum_j S_j^2.  M2 can pass 2^53 (S_j <= 240 n), so it is a
+// rounded FP64 sum: block partials are written out and added in a FIXED order by one thread (deterministic).
+constexpr int kCodeSumBlocks = 1024;
 __global__ void __launch_bounds__(256)
     code_sums_kernel(const double* __restrict__ mean, int64_t p, double n_levels, double* __restrict__ S,
-                     double* __restrict__ M2) {
+                     double* __restrict__ partial) {
   __shared__ double ws[8];
   double acc = 0.0;
   for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < p;
@@ -322,16 +327,26 @@ __global__ void __launch_bounds__(256)
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int w = 0; w < 8; ++w) t += ws[w];
-    atomicAdd(M2, t);
+    partial[blockIdx.x] = t;
   }
+}
+__global__ void code_sums_final_kernel(const double* __restrict__ partial, int blocks, double* __restrict__ M2) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double t = 0.0;
+  for (int b = 0; b < blocks; ++b) t += partial[b];
+  M2[0] += t;
 }
 
 void launch_code_sums(const double* mean, int64_t p, int64_t n, double* S, double* M2, cudaStream_t stream) {
   if (p <= 0) return;
   int grid = static_cast<int>((p + 255) / 256);
-  if (grid > 1024) grid = 1024;
-  code_sums_kernel<<<grid, 256, 0, stream>>>(mean, p, static_cast<double>(n) * 240.0, S, M2);
+  if (grid > kCodeSumBlocks) grid = kCodeSumBlocks;
+  double* partial = nullptr;
+  GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&partial), sizeof(double) * grid, stream));
+  code_sums_kernel<<<grid, 256, 0, stream>>>(mean, p, static_cast<double>(n) * 240.0, S, partial);
+  code_sums_final_kernel<<<1, 32, 0, stream>>>(partial, grid, M2);
   GBM_CUDA(cudaGetLastError());
+  GBM_CUDA(cudaFreeAsync(partial, stream));
 }
 
 // dK[i,i'] += ( G[i,i'] - centre*((U_i + U_i')/n - M2/n^2) ) / 240^2     on the lower triangle

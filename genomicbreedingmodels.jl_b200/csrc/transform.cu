@@ -461,6 +461,16 @@ int64_t transform_select(const double* beta_dev, int64_t len, int64_t n_new, dou
                          double* beta_host, bool* has_nan, int sm_count, cudaStream_t stream) {
   if (has_nan) *has_nan = false;
   if (len <= 0 || n_new <= 0) return 0;
+  {  // the full stable sort needs four key / index arrays of `len` entries plus CUB's scratch (~ another two)
+    size_t free_b = 0, total_b = 0;
+    GBM_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const double need = 48.0 * static_cast<double>(len);
+    if (need > 0.9 * static_cast<double>(free_b))
+      GBM_THROW(1, "transform screen: selecting the top effects of " + std::to_string(len) + " needs about " +
+                       std::to_string(static_cast<long long>(need / 1e9) + 1) + " GB of device scratch and " +
+                       std::to_string(static_cast<long long>(free_b / 1e9)) + " GB are free; screen the pair matrix in row "
+                       "blocks (gbm_transform2_screen_rows) or fewer loci at a time");
+  }
   Scratch<unsigned long long> k_in(len, stream), k_out(len, stream);
   Scratch<long long> v_in(len, stream), v_out(len, stream);
   abs_keys_kernel<<<grid_for(len, 256, sm_count), 256, 0, stream>>>(beta_dev, len, k_in.p, v_in.p);

@@ -176,12 +176,21 @@ def _prepare(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_ty
     else:
         pr.dm = DeviceMatrix.upload(A, rows1, cols1)
         pr.packed = pr.dm.pack() if use_packed else None
+    try:
+        return _prepare_resident(pr, genomes, phenomes, A, rows1, cols1, y, trait, subset, use_packed, GRM_type,
+                                 standardise, need_kstd, need_pc1)
+    except BaseException:
+        pr.free()  # nothing of a failed preparation stays resident
+        raise
+
+
+def _prepare_resident(pr: _Prep, genomes, phenomes, A, rows1, cols1, y, trait, subset, use_packed, GRM_type, standardise,
+                      need_kstd, need_pc1) -> _Prep:
     pr.scan_dm = pr.packed if pr.packed is not None else pr.dm
     pr.stats = pr.scan_dm.colstats()  # v = std(G, dims=1); idx_cols (:112-113)
     if np.isnan(pr.stats["sd"]).any():
         # Matrix{Float64}(::Matrix{Union{Float64,Missing}}) throws on a missing genotype
         # (prediction.jl:129); a NaN/Inf genotype shows up here as a NaN column sd.
-        pr.free()
         raise ErrorException("cannot convert a value of type Missing to Float64")
     pr.idx_cols = pr.stats["idx_cols"]
     r0 = np.arange(A.shape[0]) if rows1 is None else rows1 - 1
