@@ -1626,6 +1626,14 @@ int gbm_pack_host_check(const double* A, int64_t n, int64_t p, int64_t lda, int 
   GBM_API_END
 }
 
+int gbm_side_vector_digits(const double* Q, int64_t n, int M, int64_t ldq, int8_t* digits, int64_t ld, double* scale) {
+  GBM_API_BEGIN
+  if (!Q || !digits || !scale || n < 1 || M < 1 || M > 2 || ldq < n || ld != scan_u8_tc_digit_rows(n))
+    GBM_THROW(GBM_ERR_ARGUMENT, "gbm_side_vector_digits: bad arguments");
+  scan_u8_tc_build_digits(Q, n, M, ldq, digits, ld, scale);
+  GBM_API_END
+}
+
 int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const double* Y, int64_t T, int64_t ldy,
                   const double* C, int64_t k, int64_t ldc, int model, int flags, double* beta, double* se,
                   double* stat, double* neglog10p, double* mean, double* sd, uint8_t* keep) {

@@ -122,6 +122,11 @@ int gbm_pack_host(const double* A, int64_t n, int64_t p, int64_t lda, uint8_t* o
  * accepts column j as all-codes; the vector bodies use a division-free test that must agree with
  * fl(c/240) == a element for element */
 int gbm_pack_host_check(const double* A, int64_t n, int64_t p, int64_t lda, int isa, uint8_t* col_ok);
+/* testing hook (host only, no GPU needed): the fixed-point form of the side vectors that the tensor-core code scan
+ * multiplies (csrc/scan_u8_tc.cu).  Q: n x M (ldq), M <= 2.  digits: 16 x ld int8 with ld = n rounded up to 128 --
+ * row 0 ones, rows 1..7 / 8..14 the seven balanced base-256 digits of q_1 / q_2 (least significant first), zero padded;
+ * scale[m] = 2^(E_m - 55): q_i = scale * sum_k 256^k digit_k(i) up to one ulp of max |q|. */
+int gbm_side_vector_digits(const double* Q, int64_t n, int M, int64_t ldq, int8_t* digits, int64_t ld, double* scale);
 int gbm_matrix_download(const gbm_matrix* m, int64_t j0, int64_t ncols, double* dst, int64_t ldd);
 /* G = G[:, idx_cols] and, with standardise != 0, G = (G .- mean(G, dims=1)) ./ std(G, dims=1)'
  * (/root/reference/src/gwas.jl:114, :129) on the device; dst (host or device) is n x ncols.

@@ -359,3 +359,47 @@ int main(void) {
         out = subprocess.run([exe], capture_output=True, text=True)
         assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
         assert out.stdout.split() == ["0", "120", "240", "60", "0"]
+
+
+def test_side_vector_digits_reconstruct_the_vectors_exactly():
+    """The tensor-core code scan (csrc/scan_u8_tc.cu) multiplies the codes with FIXED-POINT side vectors: seven balanced
+    base-256 digits per element.  Host-side check (no GPU): the digits are int8, the column of ones is there, and
+    scale * sum_k 256^k d_k equals q to within one unit of the last digit -- below one ulp of max |q| -- for vectors with
+    a wide dynamic range, values within a hair of a power of two (the carry that needs the headroom bit), zeros and
+    both signs; an integer dot product with codes then equals the exact rational dot product to the same bound."""
+    import ctypes
+    from fractions import Fraction
+
+    import gbm_b200
+    from gbm_b200 import _lib as L
+
+    lib = gbm_b200.load()
+    rng = np.random.default_rng(0)
+    n = 1000
+    q1 = rng.normal(size=n) * np.exp(rng.normal(size=n) * 4.0)
+    q1[0], q1[1], q1[2], q1[3] = 0.0, np.abs(q1).max() * 1.5, -np.abs(q1).max() * 1.4999, 1e-300
+    q2 = rng.normal(size=n)
+    q2[5] = np.nextafter(4.0, 0.0)   # just below a power of two: the top digit would carry without headroom
+    q2[6] = -np.nextafter(4.0, 0.0)
+    q2[7] = 3.999
+    Q = np.asfortranarray(np.c_[q1, q2])
+    ld = (n + 127) // 128 * 128
+    dig = np.zeros((16, ld), dtype=np.int8)
+    scale = (ctypes.c_double * 2)()
+    L.check(lib.gbm_side_vector_digits(L.ptr(Q), n, 2, n, L.ptr(dig), ld, scale))
+    assert np.all(dig[0, :n] == 1) and np.all(dig[0, n:] == 0) and np.all(dig[15] == 0) and np.all(dig[:, n:] == 0)
+    for m, q in enumerate((q1, q2)):
+        sc = scale[m]
+        assert sc > 0 and np.log2(sc) == round(np.log2(sc))  # a power of two
+        d = dig[1 + 7 * m: 8 + 7 * m, :n].astype(object)
+        ints = sum(d[k] * (256 ** k) for k in range(7))      # exact Python integers
+        assert max(abs(int(v)) for v in ints) < 2 ** 54
+        err = np.array([abs(float(Fraction(int(v)) * Fraction(sc) - Fraction(float(x)))) for v, x in zip(ints, q)])
+        assert err.max() <= 0.5 * sc * (1 + 1e-12), (m, err.max(), sc)       # round to nearest unit of the last digit
+        assert sc <= 2.0 * np.spacing(np.abs(q).max())                        # that unit is within 2 ulp of max |q|
+        codes = rng.integers(0, 241, size=n)
+        exact = sum(Fraction(int(c)) * Fraction(float(x)) for c, x in zip(codes, q))
+        fixed = Fraction(sc) * sum(int(c) * int(v) for c, v in zip(codes, ints))
+        assert abs(float(fixed - exact)) <= 0.5 * sc * float(codes.sum())
+    with pytest.raises(L.ArgumentError):
+        L.check(lib.gbm_side_vector_digits(L.ptr(Q), n, 3, n, L.ptr(dig), ld, scale))
