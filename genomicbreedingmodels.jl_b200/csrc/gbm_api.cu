@@ -29,6 +29,7 @@ struct gbm_matrix {
   int dtype = 0;            // 0: Float64, 1: one-byte dosage codes (a = code / 240)
   uint8_t* d8 = nullptr;    // code slab (dtype 1), column pitch ld8 bytes
   int64_t ld8 = 0;
+  bool pooled = false;      // slab from the stream-ordered pool (small matrices: no driver call per upload / free)
 };
 
 namespace gbm {
@@ -736,14 +737,40 @@ int gbm_last_timing(gbm_timing* t) {
 // ------------------------------------------------------------------------------------
 // matrices
 // ------------------------------------------------------------------------------------
+// Slabs below 1 GB come from the device's stream-ordered pool (release threshold: never), so a steady stream of
+// small problems (BASELINE configs[0]: 24 MB per call) makes no cudaMalloc / cudaFree driver calls -- those cost ~1.3 ms
+// each and were the source of sporadic 0.03-0.8 s stalls; large slabs stay plain allocations that go back to the
+// driver when freed (an 80 GB matrix must not stay parked in a pool).
+static cudaError_t slab_malloc(gbm_matrix* m, void** ptr, size_t bytes) {
+  if (bytes <= (size_t(1) << 30)) {
+    m->pooled = true;
+    cudaError_t e = cudaMallocAsync(ptr, bytes, state().stream);
+    // the slab is filled from other streams too (copy engine lanes): make the allocation point visible to all of them
+    if (e == cudaSuccess) e = cudaStreamSynchronize(state().stream);
+    return e;
+  }
+  m->pooled = false;
+  return cudaMalloc(ptr, bytes);
+}
+static void slab_free(gbm_matrix* m) {
+  if (m->pooled && state().ready) {
+    if (m->d) cudaFreeAsync(m->d, state().stream);
+    if (m->d8) cudaFreeAsync(m->d8, state().stream);
+  } else {
+    if (m->d) cudaFree(m->d);
+    if (m->d8) cudaFree(m->d8);
+  }
+  m->d = nullptr;
+  m->d8 = nullptr;
+}
+
 // owns a half-built matrix until it is handed to the caller (an exception in between frees the slab and the handle)
 struct MatGuard {
   gbm_matrix* m;
   explicit MatGuard(gbm_matrix* mm) : m(mm) {}
   ~MatGuard() {
     if (m) {
-      if (m->d) cudaFree(m->d);
-      if (m->d8) cudaFree(m->d8);
+      slab_free(m);
       delete m;
     }
   }
@@ -774,7 +801,7 @@ int gbm_matrix_upload(const double* A, int64_t n, int64_t p, int64_t lda, gbm_ma
   m->p = p;
   m->lda = round_up(n, 16);
   m->owned = true;
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&m->d), sizeof(double) * m->lda * p);
+  cudaError_t e = slab_malloc(m, reinterpret_cast<void**>(&m->d), sizeof(double) * m->lda * p);
   if (e != cudaSuccess) {
     delete m;
     GBM_THROW(GBM_ERR_CUDA, std::string("cudaMalloc of the genotype slab failed: ") + cudaGetErrorString(e));
@@ -783,7 +810,7 @@ int gbm_matrix_upload(const double* A, int64_t n, int64_t p, int64_t lda, gbm_ma
   try {
     upload_f64(A, n, p, lda, m->d, m->lda);
   } catch (...) {
-    cudaFree(m->d);
+    slab_free(m);
     delete m;
     throw;
   }
@@ -808,13 +835,13 @@ int gbm_matrix_upload_compact(const double* A, int64_t n, int64_t p, int64_t lda
     q->dtype = 1;
     q->owned = true;
     q->ld8 = round_up(n, 128);
-    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&q->d8), static_cast<size_t>(q->ld8) * p);
+    cudaError_t e = slab_malloc(q.get(), reinterpret_cast<void**>(&q->d8), static_cast<size_t>(q->ld8) * p);
     if (e != cudaSuccess) GBM_THROW(GBM_ERR_CUDA, std::string("cudaMalloc of the code slab failed: ") + cudaGetErrorString(e));
     bool all = false;
     try {
       all = upload_codes(A, n, p, lda, q->d8, q->ld8);
     } catch (...) {
-      cudaFree(q->d8);
+      slab_free(q.get());
       throw;
     }
     if (all) {
@@ -824,14 +851,14 @@ int gbm_matrix_upload_compact(const double* A, int64_t n, int64_t p, int64_t lda
       *out = q.release();
       return GBM_OK;
     }
-    cudaFree(q->d8);  // not dosage data: Float64 slab below
+    slab_free(q.get());  // not dosage data: Float64 slab below
   }
   gbm_matrix* m = new gbm_matrix;
   m->n = n;
   m->p = p;
   m->lda = round_up(n, 16);
   m->owned = true;
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&m->d), sizeof(double) * m->lda * p);
+  cudaError_t e = slab_malloc(m, reinterpret_cast<void**>(&m->d), sizeof(double) * m->lda * p);
   if (e != cudaSuccess) {
     delete m;
     GBM_THROW(GBM_ERR_CUDA, std::string("cudaMalloc of the genotype slab failed: ") + cudaGetErrorString(e));
@@ -839,7 +866,7 @@ int gbm_matrix_upload_compact(const double* A, int64_t n, int64_t p, int64_t lda
   try {
     upload_f64(A, n, p, lda, m->d, m->lda);
   } catch (...) {
-    cudaFree(m->d);
+    slab_free(m);
     delete m;
     throw;
   }
@@ -880,7 +907,7 @@ int gbm_matrix_upload_indexed(const double* A, int64_t n0, int64_t p0, int64_t l
   m->p = p;
   m->lda = round_up(n, 16);
   m->owned = true;
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&m->d), sizeof(double) * m->lda * p);
+  cudaError_t e = slab_malloc(m, reinterpret_cast<void**>(&m->d), sizeof(double) * m->lda * p);
   if (e != cudaSuccess) {
     delete m;
     GBM_THROW(GBM_ERR_CUDA, std::string("cudaMalloc of the genotype slab failed: ") + cudaGetErrorString(e));
@@ -953,7 +980,7 @@ int gbm_matrix_generate(uint64_t seed, int64_t n, int64_t p, int64_t col0, int k
   m->p = p;
   m->lda = round_up(n, 16);
   m->owned = true;
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&m->d), sizeof(double) * m->lda * p);
+  cudaError_t e = slab_malloc(m, reinterpret_cast<void**>(&m->d), sizeof(double) * m->lda * p);
   if (e != cudaSuccess) {
     delete m;
     GBM_THROW(GBM_ERR_CUDA, std::string("cudaMalloc of the genotype slab failed: ") + cudaGetErrorString(e));
@@ -980,7 +1007,7 @@ int gbm_matrix_pack(const gbm_matrix* m, gbm_matrix** out, int64_t* n_inexact) {
   q->dtype = 1;
   q->owned = true;
   q->ld8 = round_up(m->n, 128);
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&q->d8), static_cast<size_t>(q->ld8) * m->p);
+  cudaError_t e = slab_malloc(q.get(), reinterpret_cast<void**>(&q->d8), static_cast<size_t>(q->ld8) * m->p);
   if (e != cudaSuccess) GBM_THROW(GBM_ERR_CUDA, std::string("cudaMalloc of the code slab failed: ") + cudaGetErrorString(e));
   DevBuf<unsigned long long> bad(1, st.stream);
   GBM_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(unsigned long long), st.stream));
@@ -990,7 +1017,7 @@ int gbm_matrix_pack(const gbm_matrix* m, gbm_matrix** out, int64_t* n_inexact) {
   GBM_CUDA(cudaStreamSynchronize(st.stream));
   *n_inexact = static_cast<int64_t>(h);
   if (h != 0) {
-    cudaFree(q->d8);  // not every element is a dosage code: the Float64 path must be used
+    slab_free(q.get());  // not every element is a dosage code: the Float64 path must be used
     return GBM_OK;
   }
   *out = q.release();
@@ -1009,7 +1036,7 @@ int gbm_matrix_upload_packed(const uint8_t* codes, int64_t n, int64_t p, int64_t
   q->dtype = 1;
   q->owned = true;
   q->ld8 = round_up(n, 128);
-  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&q->d8), static_cast<size_t>(q->ld8) * p);
+  cudaError_t e = slab_malloc(q.get(), reinterpret_cast<void**>(&q->d8), static_cast<size_t>(q->ld8) * p);
   if (e != cudaSuccess) GBM_THROW(GBM_ERR_CUDA, std::string("cudaMalloc of the code slab failed: ") + cudaGetErrorString(e));
   GBM_CUDA(cudaMemsetAsync(q->d8, 0, static_cast<size_t>(q->ld8) * p, st.stream));
   GBM_CUDA(cudaMemcpy2DAsync(q->d8, q->ld8, codes, ld, n, p, cudaMemcpyDefault, st.stream));
@@ -1101,9 +1128,8 @@ int gbm_matrix_free(gbm_matrix* m) {
   GBM_API_BEGIN
   if (m) {
     if (m->owned && (m->d || m->d8)) {
-      cudaStreamSynchronize(state().stream);
-      if (m->d) cudaFree(m->d);
-      if (m->d8) cudaFree(m->d8);
+      if (state().ready) cudaStreamSynchronize(state().stream);
+      slab_free(m);
     }
     delete m;
   }
