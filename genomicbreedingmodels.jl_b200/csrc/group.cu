@@ -179,7 +179,18 @@ struct Worker {
 
 }  // namespace
 
+// one GPU's side of the peer-memory all-reduce of the sharded Lanczos step (lanczos.cu: peer_sum_kernel)
+struct PeerState {
+  PeerMailbox mb;
+  double* slots = nullptr;               // this GPU's mailbox: 2 x W x npad doubles (cudaMalloc: shareable by CUDA IPC)
+  unsigned long long* flags = nullptr;   // W step counters
+  std::vector<void*> opened;             // CUDA IPC mappings of the peers' mailboxes (rank groups)
+  unsigned long long step = 0;
+};
+
 struct gbm_group {
+  std::vector<PeerState> peer;           // per local GPU
+  int64_t peer_npad = 0;                 // 0: no mailboxes yet; -1: peer access not available (NCCL is used)
   int world = 1, n_local = 1, first_rank = 0;
   bool threaded = false;  // local group: a worker thread per GPU; rank group: inline on the caller's thread
   std::vector<std::unique_ptr<State>> owned;
@@ -333,6 +344,140 @@ struct NcclSum : ShardedAllReduce {
   }
 };
 
+struct PeerSum : NcclSum {  // the per-step all-reduce over peer memory, fused with the partial-sum reduction
+  PeerState* ps;
+  PeerSum(ncclComm_t c, cudaStream_t st, PeerState* p) : NcclSum(c, st), ps(p) {}
+  void sum_partials(const double* partial, int chunks, int64_t n, double* out, cudaStream_t stream) override {
+    launch_peer_sum(ps->mb, partial, chunks, n, ++ps->step, out, stream);
+  }
+};
+
+void free_peer(gbm_group& G) {
+  if (G.peer.empty()) return;
+  try {
+    G.run([&](int g) {
+      PeerState& ps = G.peer[g];
+      cudaStreamSynchronize(state().stream);
+      for (void* p : ps.opened) cudaIpcCloseMemHandle(p);
+      ps.opened.clear();
+      if (ps.slots) cudaFree(ps.slots);
+      if (ps.flags) cudaFree(ps.flags);
+      if (ps.mb.cta_counter) cudaFree(ps.mb.cta_counter);
+      if (ps.mb.error) cudaFree(ps.mb.error);
+      ps = PeerState();
+    });
+  } catch (...) {
+  }
+  G.peer_npad = 0;
+}
+
+// Mailboxes for n-vectors on every GPU of the group, visible to every other GPU: peer access inside one process,
+// CUDA IPC mappings between processes.  Returns false (and remembers it) when the GPUs cannot reach each other's
+// memory -- the Lanczos step then uses NCCL.
+bool ensure_peer(gbm_group& G, int64_t n) {
+  const char* env = getenv("GBM_PC1_PEER");  // read per call: the tests compare both routes in one process
+  if ((env && atoi(env) == 0) || G.world > PeerMailbox::kMaxRanks || G.world < 2 || G.peer_npad < 0) return false;
+  const int64_t npad = round_up(n, 256);
+  if (G.peer_npad >= npad) return true;
+  free_peer(G);
+  G.peer.assign(G.n_local, PeerState());
+  const int W = G.world;
+  std::vector<int> okv(G.n_local, 1);
+  // (1) allocate, and in a local group switch peer access on
+  G.phase([&](int g) {
+    PeerState& ps = G.peer[g];
+    if (G.threaded) {
+      for (int h = 0; h < G.n_local; ++h) {
+        if (h == g) continue;
+        int can = 0;
+        GBM_CUDA(cudaDeviceCanAccessPeer(&can, G.ctx[g]->device, G.ctx[h]->device));
+        if (!can) {
+          okv[g] = 0;
+          return;
+        }
+        cudaError_t e = cudaDeviceEnablePeerAccess(G.ctx[h]->device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else GBM_CUDA(e);
+      }
+    }
+    GBM_CUDA(cudaMalloc(reinterpret_cast<void**>(&ps.slots), sizeof(double) * 2 * W * npad));
+    GBM_CUDA(cudaMalloc(reinterpret_cast<void**>(&ps.flags), sizeof(unsigned long long) * W));
+    GBM_CUDA(cudaMalloc(reinterpret_cast<void**>(&ps.mb.cta_counter), sizeof(unsigned int)));
+    GBM_CUDA(cudaMalloc(reinterpret_cast<void**>(&ps.mb.error), sizeof(int)));
+    GBM_CUDA(cudaMemset(ps.slots, 0, sizeof(double) * 2 * W * npad));
+    GBM_CUDA(cudaMemset(ps.flags, 0, sizeof(unsigned long long) * W));
+    GBM_CUDA(cudaMemset(ps.mb.cta_counter, 0, sizeof(unsigned int)));
+    GBM_CUDA(cudaMemset(ps.mb.error, 0, sizeof(int)));
+    GBM_CUDA(cudaDeviceSynchronize());
+  });
+  std::vector<std::vector<double>> okr(G.n_local, std::vector<double>(1, 1.0));
+  for (int g = 0; g < G.n_local; ++g) okr[g][0] = okv[g];
+  // (2) every rank learns every mailbox address
+  try {
+    if (G.threaded) {
+      G.reduce_host(okr, ncclMin);
+      if (okr[0][0] < 0.5) throw Error{GBM_ERR_RUNTIME, "no peer access"};
+      for (int g = 0; g < G.n_local; ++g)
+        for (int q = 0; q < W; ++q) {
+          G.peer[g].mb.slots[q] = G.peer[q].slots;
+          G.peer[g].mb.flags[q] = G.peer[q].flags;
+        }
+    } else {
+      // one process per GPU: CUDA IPC handles travel through an all-gather, every peer mailbox is mapped here.  The
+      // mapping can fail on some ranks only (a peer on another node, no P2P path): G.phase makes that a common verdict.
+      struct Handles {
+        cudaIpcMemHandle_t slots, flags;
+      };
+      static_assert(sizeof(Handles) == 128, "two 64-byte IPC handles");
+      std::vector<Handles> all(W);
+      G.run([&](int g) {
+        PeerState& ps = G.peer[g];
+        cudaStream_t st = state().stream;
+        const int me = G.rank_of(g);
+        GBM_CUDA(cudaIpcGetMemHandle(&all[me].slots, ps.slots));
+        GBM_CUDA(cudaIpcGetMemHandle(&all[me].flags, ps.flags));
+        Dev<uint8_t> d(sizeof(Handles) * W);
+        GBM_CUDA(cudaMemcpyAsync(d.p + sizeof(Handles) * me, &all[me], sizeof(Handles), cudaMemcpyHostToDevice, st));
+        GBM_NCCL(nccl().AllGather(d.p + sizeof(Handles) * me, d.p, sizeof(Handles), ncclUint8, G.comm[g], st));
+        GBM_CUDA(cudaMemcpyAsync(all.data(), d.p, sizeof(Handles) * W, cudaMemcpyDeviceToHost, st));
+        GBM_CUDA(cudaStreamSynchronize(st));
+      });
+      G.phase([&](int g) {
+        PeerState& ps = G.peer[g];
+        const int me = G.rank_of(g);
+        for (int q = 0; q < W; ++q) {
+          if (q == me) {
+            ps.mb.slots[q] = ps.slots;
+            ps.mb.flags[q] = ps.flags;
+            continue;
+          }
+          void *ps_q = nullptr, *pf_q = nullptr;
+          GBM_CUDA(cudaIpcOpenMemHandle(&ps_q, all[q].slots, cudaIpcMemLazyEnablePeerAccess));
+          ps.opened.push_back(ps_q);
+          GBM_CUDA(cudaIpcOpenMemHandle(&pf_q, all[q].flags, cudaIpcMemLazyEnablePeerAccess));
+          ps.opened.push_back(pf_q);
+          ps.mb.slots[q] = static_cast<double*>(ps_q);
+          ps.mb.flags[q] = static_cast<unsigned long long*>(pf_q);
+        }
+      });
+    }
+  } catch (const Error&) {
+    // Falling back is the SAME decision on every rank: one process decides for a local group, G.phase agreed on the
+    // failure for a rank group.  The Lanczos step then uses NCCL.
+    cudaGetLastError();
+    free_peer(G);
+    G.peer_npad = -1;
+    return false;
+  }
+  for (int g = 0; g < G.n_local; ++g) {
+    G.peer[g].mb.world = W;
+    G.peer[g].mb.me = G.rank_of(g);
+    G.peer[g].mb.npad = npad;
+  }
+  G.peer_npad = npad;
+  return true;
+}
+
 }  // namespace
 
 struct gbm_sharded {
@@ -443,6 +588,9 @@ double sharded_kstd_pc1(gbm_sharded* m, double* pc1_host, int* steps, int64_t* l
   const bool sharded = G.world > 1 && n >= 4096 && !no_shard;
   if (sharded) {
     const int64_t ld = round_up(n, 16);
+    // the per-step all-reduce: one kernel over peer memory (NVLink stores into every GPU's mailbox) when the GPUs can
+    // reach each other's memory, NCCL otherwise
+    const bool peer = ensure_peer(G, n);
     G.run([&](int g) {
       State& st = state();
       cudaStream_t s = st.stream;
@@ -460,7 +608,9 @@ double sharded_kstd_pc1(gbm_sharded* m, double* pc1_host, int* steps, int64_t* l
       launch_k_standardise(Z.p, n, nc, ld, mean.p, sd.p, s);
       // PCA centres the rows (gwas.jl:234): row sums of the block, summed over the ranks
       block_row_sums(Z.p, n, nc, ld, rowsum.p, s);
-      NcclSum ar(G.comm[g], s);
+      NcclSum nccl_sum(G.comm[g], s);
+      PeerSum peer_sum(G.comm[g], s, peer ? &G.peer[g] : nullptr);
+      NcclSum& ar = peer ? static_cast<NcclSum&>(peer_sum) : nccl_sum;
       ar.sum(rowsum.p, n);
       launch_row_shift(Z.p, n, nc, ld, rowsum.p, 1.0 / static_cast<double>(n), s);
       cudaEvent_t e0, e1;
@@ -476,10 +626,15 @@ double sharded_kstd_pc1(gbm_sharded* m, double* pc1_host, int* steps, int64_t* l
       cudaEventElapsedTime(&ms, e0, e1);
       cudaEventDestroy(e0);
       cudaEventDestroy(e1);
+      if (peer) {
+        int perr = 0;
+        GBM_CUDA(cudaMemcpy(&perr, G.peer[g].mb.error, sizeof(int), cudaMemcpyDeviceToHost));
+        if (perr) GBM_THROW(GBM_ERR_RUNTIME, "gbm_sharded_kstd_pc1: a GPU of the group did not reach the peer-memory all-reduce in time");
+      }
       eig[g] = ms;
       conv[g] = okc ? 1 : 0;
       iters[g] = it;
-      if (launches) launches[g] += 8 + 7 * it;
+      if (launches) launches[g] += 8 + (peer ? 6 : 7) * it;
       if (okc && g == 0 && pc1_host) {
         GBM_CUDA(cudaMemcpyAsync(pc1_host, x.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
         GBM_CUDA(cudaStreamSynchronize(s));
@@ -726,6 +881,7 @@ int gbm_group_free(gbm_group* g) {
   if (!g) return GBM_OK;
   {
     std::lock_guard<std::mutex> lk(g->mutex);
+    free_peer(*g);
     for (ncclComm_t c : g->comm)
       if (c) nccl().CommDestroy(c);
     if (g->threaded) {

@@ -142,8 +142,29 @@ bool lanczos_top_eigenpair(const double* B, int64_t n, int64_t ldb, bool gram, d
 // ranks, ordered on `stream`.  rowsum_out (nullable, n): Zg 1, the block's row sums, before any all-reduce.
 struct ShardedAllReduce {
   virtual void sum(double* buf, int64_t count) = 0;
+  // out = sum over the ranks of (sum_c partial[c][:]), c < chunks: the CTA partials of the fused Lanczos pass.  The
+  // default reduces the partials and all-reduces the result; a group with peer access overrides it with ONE kernel
+  // that does both over NVLink (peer_sum_kernel, lanczos.cu).
+  virtual void sum_partials(const double* partial, int chunks, int64_t n, double* out, cudaStream_t stream);
   virtual ~ShardedAllReduce() {}
 };
+// Mailboxes of a one-shot all-reduce over peer memory: every rank owns 2 (step parity) x W slots of npad doubles and W
+// step counters; slots[q] / flags[q] are rank q's mailbox as seen from THIS device (peer access or a CUDA IPC mapping).
+struct PeerMailbox {
+  static constexpr int kMaxRanks = 8;
+  double* slots[kMaxRanks];
+  unsigned long long* flags[kMaxRanks];
+  int world = 0, me = 0;
+  int64_t npad = 0;
+  unsigned int* cta_counter = nullptr;  // this device
+  int* error = nullptr;                 // this device: set when a peer did not show up in time
+};
+// partial-sum reduction + all-reduce in one kernel: this rank's reduced vector is stored into slot `me` of every
+// rank's mailbox over NVLink, a step counter is released, the kernel waits for the W counters of its own mailbox and
+// adds the W slots in rank order (the same order, hence the same bits, on every rank).  `step` starts at 1 and grows
+// by one per call on every rank.
+void launch_peer_sum(const PeerMailbox& mb, const double* partial, int chunks, int64_t n, unsigned long long step,
+                     double* out, cudaStream_t stream);
 void block_row_sums(const double* Zg, int64_t n, int64_t nc, int64_t ld, double* rowsum, cudaStream_t stream);
 bool lanczos_top_singular_sharded(const double* Zg, int64_t n, int64_t nc, int64_t ld, ShardedAllReduce* ar, double tol,
                                   int max_iter, double* x_dev, double* theta, int* iters, int sm_count,

@@ -10,11 +10,14 @@
 // alpha / beta stay on the device; every few steps the host solves the small tridiagonal problem
 // (bisection + inverse iteration) and tests the residual estimate beta_j |s_j| <= tol theta.  All
 // reductions have a fixed order: the result is a deterministic function of B.
+#include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
 
+#include "../../include/gbm_b200.h"
 #include "common.cuh"
 #include "kernels.h"
 
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(256) symv_cta_kernel(const double* __restrict_
 }
 
 // partial[c][i] = sum over the c-th chunk of columns of Z[i, j] u[j]   (Z column-major, pitch ld): thread = row,
-// so every load is coalesced; the chunks are summed in a fixed order by gemv_n_reduce_kernel (deterministic)
+// so every load is coalesced; the chunks are summed in a fixed order by partial_reduce_kernel (deterministic)
 constexpr int kGemvChunks = 64;
 __global__ void __launch_bounds__(256) gemv_n_partial_kernel(const double* __restrict__ Z, int64_t n, int64_t ncols,
                                                              int64_t ld, const double* __restrict__ u,
@@ -123,21 +126,13 @@ __global__ void __launch_bounds__(256) gemv_n_partial_kernel(const double* __res
   for (; j < j1; ++j) a0 = fma(Z[j * ld + i], u ? u[j] : 1.0, a0);
   partial[static_cast<int64_t>(blockIdx.y) * n + i] = (a0 + a1) + (a2 + a3);
 }
-__global__ void __launch_bounds__(256) gemv_n_reduce_kernel(const double* __restrict__ partial, int64_t n,
-                                                            double* __restrict__ w) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-  if (i >= n) return;
-  double s = 0.0;
-  for (int c = 0; c < kGemvChunks; ++c) s += partial[static_cast<int64_t>(c) * n + i];
-  w[i] = s;
-}
 
 // ---- fused gram step: partial[cta][:] = sum over the CTA's columns j of Z[:, j] (Z[:, j] . v) ----------------------
 // One pass over Z per Lanczos step instead of two (u = Z'v, then w = Z u): a CTA takes whole columns; a column is
 // brought into shared memory by one bulk copy (TMA, double-buffered, so the next column streams in while this one
 // is used), the 512 threads take its dot product with v (each thread keeps ITS rows of v in registers for the whole
 // kernel), and the column is added, scaled by that dot, to the thread's rows of the CTA's partial result (registers
-// as well).  The partials of all CTAs are summed in a fixed order by gemv_n_reduce_kernel: deterministic.
+// as well).  The partials of all CTAs are summed in a fixed order by partial_reduce_kernel: deterministic.
 // Needs 2 n doubles of shared memory: n <= 12,288; larger n use the two-pass kernels.
 constexpr int kFusedThreads = 512;
 template <int RPT>  // rows per thread: n <= 512 * RPT
@@ -211,21 +206,97 @@ __global__ void __launch_bounds__(kFusedThreads, 1)
   }
 }
 
-// w[i] = sum_c partial[c][i] over `chunks` partial vectors, fixed order
+// w[i] = sum_c partial[c][i] over `chunks` partial vectors.  A CTA owns 32 rows; its 8 warps take the chunks c = g,
+// g + 8, ... (every load a coalesced 256-byte row segment, four independent chains per thread), the 8 group sums are
+// added in a fixed order.  One thread per row walking all the chunks was a chain of up to 148 dependent L2 latencies
+// (~25 us per Lanczos step); this is ~5.
+__device__ __forceinline__ double chunk_group_sum(const double* __restrict__ partial, int64_t n, int chunks, int64_t i, int g) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int c = g;
+  for (; c + 24 < chunks; c += 32) {
+    s0 += partial[static_cast<int64_t>(c) * n + i];
+    s1 += partial[static_cast<int64_t>(c + 8) * n + i];
+    s2 += partial[static_cast<int64_t>(c + 16) * n + i];
+    s3 += partial[static_cast<int64_t>(c + 24) * n + i];
+  }
+  for (; c < chunks; c += 8) s0 += partial[static_cast<int64_t>(c) * n + i];
+  return (s0 + s1) + (s2 + s3);
+}
 __global__ void __launch_bounds__(256) partial_reduce_kernel(const double* __restrict__ partial, int64_t n, int chunks,
                                                              double* __restrict__ w) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
-  if (i >= n) return;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  int c = 0;
-  for (; c + 4 <= chunks; c += 4) {
-    s0 += partial[static_cast<int64_t>(c) * n + i];
-    s1 += partial[static_cast<int64_t>(c + 1) * n + i];
-    s2 += partial[static_cast<int64_t>(c + 2) * n + i];
-    s3 += partial[static_cast<int64_t>(c + 3) * n + i];
+  __shared__ double part[8][33];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 32 + lane;
+  part[g][lane] = i < n ? chunk_group_sum(partial, n, chunks, i, g) : 0.0;
+  __syncthreads();
+  if (g == 0 && i < n) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += part[q][lane];
+    w[i] = t;
   }
-  for (; c < chunks; ++c) s0 += partial[static_cast<int64_t>(c) * n + i];
-  w[i] = (s0 + s1) + (s2 + s3);
+}
+static void launch_partial_reduce(const double* partial, int64_t n, int chunks, double* w, cudaStream_t stream) {
+  partial_reduce_kernel<<<static_cast<unsigned>((n + 31) / 32), 256, 0, stream>>>(partial, n, chunks, w);
+}
+
+// ---- partial-sum reduction fused with the all-reduce over peer memory (NVLink P2P stores) --------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// One CTA per 32 rows (the layout of partial_reduce_kernel, the same bits for the rank's own sum).  Every CTA waits
+// inside the kernel for the other GPUs, so the whole grid must be resident at once: n <= kPeerSumMaxN.
+constexpr int64_t kPeerSumMaxN = 32 * 8 * 100;  // 800 CTAs of 256 threads: fewer than the 8 per SM a B200 holds
+__global__ void __launch_bounds__(256) peer_sum_kernel(const PeerMailbox mb, const double* __restrict__ partial, int chunks,
+                                                       int64_t n, unsigned long long step, double* __restrict__ out) {
+  __shared__ double part[8][33];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 32 + lane;
+  const int W = mb.world;
+  const int64_t par = static_cast<int64_t>(step & 1ull) * W;
+  part[g][lane] = i < n ? chunk_group_sum(partial, n, chunks, i, g) : 0.0;
+  __syncthreads();
+  if (g == 0 && i < n) {
+    double v = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v += part[q][lane];
+    for (int q = 0; q < W; ++q) mb.slots[q][(par + mb.me) * mb.npad + i] = v;  // q == me: the local mailbox
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int done = atomicAdd(mb.cta_counter, 1u);
+    if (done == gridDim.x - 1) {  // every CTA of this rank has stored its rows: publish the step to all mailboxes
+      *mb.cta_counter = 0u;
+      __threadfence_system();
+      for (int q = 0; q < W; ++q) st_release_sys(mb.flags[q] + mb.me, step);
+    }
+  }
+  if (threadIdx.x < W) {  // wait for every rank's contribution to THIS mailbox (bounded: a dead peer must not hang the GPU)
+    const unsigned long long* f = mb.flags[mb.me] + threadIdx.x;
+    volatile int* err = mb.error;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) < step) {
+      if (*err) break;                        // an earlier step already gave up: do not wait 10 s per step
+      if (clock64() - t0 > 20000000000ll) {  // ~10 s
+        *err = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  if (g == 0 && i < n) {
+    const double* mine = mb.slots[mb.me];
+    double t = 0.0;
+    for (int r = 0; r < W; ++r) t += __ldcv(mine + (par + r) * mb.npad + i);  // rank order; volatile: bypass L1
+    out[i] = t;
+  }
 }
 
 constexpr int64_t kFusedMaxN = 512 * 24;
@@ -318,6 +389,111 @@ __global__ void __launch_bounds__(1024) norm_next_kernel(const double* __restric
   }
   __syncthreads();
   for (int64_t k = threadIdx.x; k < n; k += 1024) vnext[k] = w[k] * inv;
+}
+
+// ---- the whole reorthogonalisation of one Lanczos step in ONE cooperative kernel ---------------------------------------
+// Classical Gram-Schmidt twice, alpha, beta and the next basis vector were five launches (dots, project, dots, project,
+// norm) of a few microseconds each -- with the matrix pass at ~0.02-0.12 ms they, and the gaps between them, were a
+// third to a half of a step.  Here the five phases are separated by grid barriers instead of kernel boundaries:
+//   c = V'w | w -= V c, alpha_j = c_j | c = V'w | w -= V c, alpha_j += c_j, row-group norms | beta_j, v_{j+1} = w / beta_j
+// Work split: a CTA per column for the dots, a CTA per 32 rows (16 warps = 16 column groups) for the projections.
+// Values produced inside the kernel are read back with ld.cg (L2), never through L1.  Every reduction has a fixed
+// order, independent of the grid size: the result is the same function of (V, w) on every GPU.
+namespace cg = cooperative_groups;
+constexpr int kReorthThreads = 512;
+__global__ void __launch_bounds__(kReorthThreads, 3) reorth_kernel(const double* __restrict__ V, int64_t n, int64_t ldv, int j,
+                                                                double* __restrict__ w, double* __restrict__ c,
+                                                                double* __restrict__ alpha, double* __restrict__ beta,
+                                                                double* __restrict__ normpart, double* __restrict__ vnext) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sh[32];
+  __shared__ double part[kReorthThreads / 32][33];
+  __shared__ double inv_sh;
+  const int cols = j + 1;
+  const int tid = threadIdx.x, lane = tid & 31, wg = tid >> 5;
+  const int64_t ngroups = (n + 31) / 32;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int k = blockIdx.x; k < cols; k += gridDim.x) {  // c[k] = V[:, k] . w
+      const double* col = V + static_cast<int64_t>(k) * ldv;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int64_t i = tid;
+      for (; i + 3 * kReorthThreads < n; i += 4 * kReorthThreads) {
+        s0 = fma(col[i], __ldcg(w + i), s0);
+        s1 = fma(col[i + kReorthThreads], __ldcg(w + i + kReorthThreads), s1);
+        s2 = fma(col[i + 2 * kReorthThreads], __ldcg(w + i + 2 * kReorthThreads), s2);
+        s3 = fma(col[i + 3 * kReorthThreads], __ldcg(w + i + 3 * kReorthThreads), s3);
+      }
+      for (; i < n; i += kReorthThreads) s0 = fma(col[i], __ldcg(w + i), s0);
+      const double t = block_sum((s0 + s1) + (s2 + s3), sh);
+      if (tid == 0) c[k] = t;
+      __syncthreads();  // sh is reused by the next column
+    }
+    grid.sync();
+    for (int64_t rg = blockIdx.x; rg < ngroups; rg += gridDim.x) {  // w -= V c on rows 32 rg .. 32 rg + 31
+      const int64_t i = rg * 32 + lane;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      if (i < n) {
+        constexpr int kW = kReorthThreads / 32;
+        int k = wg;
+        for (; k + 3 * kW < cols; k += 4 * kW) {
+          a0 = fma(V[static_cast<int64_t>(k) * ldv + i], __ldcg(c + k), a0);
+          a1 = fma(V[static_cast<int64_t>(k + kW) * ldv + i], __ldcg(c + k + kW), a1);
+          a2 = fma(V[static_cast<int64_t>(k + 2 * kW) * ldv + i], __ldcg(c + k + 2 * kW), a2);
+          a3 = fma(V[static_cast<int64_t>(k + 3 * kW) * ldv + i], __ldcg(c + k + 3 * kW), a3);
+        }
+        for (; k < cols; k += kW) a0 = fma(V[static_cast<int64_t>(k) * ldv + i], __ldcg(c + k), a0);
+      }
+      part[wg][lane] = (a0 + a1) + (a2 + a3);
+      __syncthreads();
+      if (wg == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < kReorthThreads / 32; ++q) t += part[q][lane];  // fixed order
+        double wn = 0.0;
+        if (i < n) {
+          wn = __ldcg(w + i) - t;
+          w[i] = wn;
+        }
+        if (pass == 1) {
+          double sq = wn * wn;
+#pragma unroll
+          for (int m = 16; m > 0; m >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, m);
+          if (lane == 0) normpart[rg] = sq;
+        }
+      }
+      __syncthreads();  // part is reused by the next row group
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+      const double cj = __ldcg(c + j);
+      alpha[j] = pass ? alpha[j] + cj : cj;  // the projection on v_j is the Lanczos alpha
+    }
+    grid.sync();
+  }
+  // beta_j = ||w|| from the row-group sums of squares: the same order, hence the same bits, in every CTA
+  double s = 0.0;
+  for (int64_t g = tid; g < ngroups; g += kReorthThreads) s += __ldcg(normpart + g);
+  const double t = block_sum(s, sh);
+  if (tid == 0) {
+    const double b = sqrt(t);
+    if (blockIdx.x == 0) beta[j] = b;
+    inv_sh = b > 0.0 ? 1.0 / b : 0.0;
+  }
+  __syncthreads();
+  const double inv = inv_sh;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kReorthThreads + tid; i < n; i += static_cast<int64_t>(gridDim.x) * kReorthThreads)
+    vnext[i] = __ldcg(w + i) * inv;
+}
+
+// CTAs of reorth_kernel that can be resident at once on the current device (0: no cooperative launch)
+static int reorth_max_grid() {
+  if (const char* e = getenv("GBM_PC1_NO_COOP"))
+    if (atoi(e) != 0) return 0;
+  int dev = 0, coop = 0, sms = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop)
+    return 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reorth_kernel, kReorthThreads, 0) != cudaSuccess) return 0;
+  return sms * std::min(per_sm, 3);
 }
 
 // deterministic start vector: splitmix64 of the row index, mapped to (-1, 1), normalised by norm_next_kernel
@@ -430,9 +606,11 @@ static bool lanczos_core(int64_t n, Apply&& apply, double tol, int max_iter, dou
   const int m_max = static_cast<int>(std::min<int64_t>(max_iter, n - 1));
   if (m_max < 2) return false;
   const int64_t ldv = (n + 1) / 2 * 2;
-  double *V = nullptr, *w = nullptr, *c = nullptr, *alpha = nullptr, *beta = nullptr, *sdev = nullptr;
+  double *V = nullptr, *w = nullptr, *c = nullptr, *alpha = nullptr, *beta = nullptr, *sdev = nullptr, *normpart = nullptr;
+  const int64_t ngroups = (n + 31) / 32;
+  const int coop_grid = static_cast<int>(std::min<int64_t>(reorth_max_grid(), ngroups));
   auto release = [&] {
-    for (double* p : {V, w, c, alpha, beta, sdev})
+    for (double* p : {V, w, c, alpha, beta, sdev, normpart})
       if (p) cudaFreeAsync(p, stream);
   };
   try {
@@ -442,6 +620,7 @@ static bool lanczos_core(int64_t n, Apply&& apply, double tol, int max_iter, dou
     GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&alpha), sizeof(double) * (m_max + 1), stream));
     GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&beta), sizeof(double) * (m_max + 1), stream));
     GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&sdev), sizeof(double) * (m_max + 1), stream));
+    GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&normpart), sizeof(double) * ngroups, stream));
     GBM_CUDA(cudaMemsetAsync(w, 0, sizeof(double) * ldv, stream));
     const unsigned row_blocks = static_cast<unsigned>((n + 255) / 256);
     start_vector_kernel<<<row_blocks, 256, 0, stream>>>(w, n);
@@ -455,11 +634,20 @@ static bool lanczos_core(int64_t n, Apply&& apply, double tol, int max_iter, dou
     for (int j = 0; j < m_max; ++j) {
       const double* vj = V + static_cast<int64_t>(j) * ldv;
       apply(vj, w);
-      for (int pass = 0; pass < 2; ++pass) {  // classical Gram-Schmidt, twice
-        dots_kernel<<<j + 1, 1024, 0, stream>>>(V, n, ldv, w, c);
-        project_out_kernel<<<static_cast<unsigned>((n + 31) / 32), 256, 0, stream>>>(V, n, ldv, j + 1, c, w, alpha, j, pass);
+      double* vnext = V + static_cast<int64_t>(j + 1) * ldv;
+      if (coop_grid > 0) {  // Gram-Schmidt twice + alpha_j + beta_j + v_{j+1} in one cooperative launch
+        int64_t n_arg = n, ldv_arg = ldv;
+        int j_arg = j;
+        void* args[] = {&V, &n_arg, &ldv_arg, &j_arg, &w, &c, &alpha, &beta, &normpart, &vnext};
+        GBM_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(reorth_kernel), dim3(coop_grid), dim3(kReorthThreads),
+                                             args, 0, stream));
+      } else {
+        for (int pass = 0; pass < 2; ++pass) {  // classical Gram-Schmidt, twice
+          dots_kernel<<<j + 1, 1024, 0, stream>>>(V, n, ldv, w, c);
+          project_out_kernel<<<static_cast<unsigned>((n + 31) / 32), 256, 0, stream>>>(V, n, ldv, j + 1, c, w, alpha, j, pass);
+        }
+        norm_next_kernel<<<1, 1024, 0, stream>>>(w, n, vnext, beta, j);
       }
-      norm_next_kernel<<<1, 1024, 0, stream>>>(w, n, V + static_cast<int64_t>(j + 1) * ldv, beta, j);
       m = j + 1;
       if (m == next_check || m == m_max) {
         GBM_CUDA(cudaGetLastError());
@@ -542,21 +730,34 @@ bool lanczos_top_eigenpair(const double* B, int64_t n, int64_t ldb, bool gram, d
     if (!gram) {
       symv_kernel<<<symv_grid, 256, 0, stream>>>(B, n, n, ldb, v, out);
     } else if (fused && launch_gram_fused(B, n, n, ldb, v, partial.p, fgrid, stream)) {
-      partial_reduce_kernel<<<row_blocks, 256, 0, stream>>>(partial.p, n, fgrid, out);  // one pass over B
+      launch_partial_reduce(partial.p, n, fgrid, out, stream);  // one pass over B
     } else {
       symv_kernel<<<symv_grid, 256, 0, stream>>>(B, n, n, ldb, v, u.p);  // u[j] = B[:, j] . v
       gemv_n_partial_kernel<<<dim3(row_blocks, kGemvChunks), 256, 0, stream>>>(B, n, n, ldb, u.p, partial.p);
-      gemv_n_reduce_kernel<<<row_blocks, 256, 0, stream>>>(partial.p, n, out);
+      launch_partial_reduce(partial.p, n, kGemvChunks, out, stream);
     }
   };
   return lanczos_core(n, apply, tol, max_iter, x_dev, theta_out, iters_out, stream);
+}
+
+void launch_peer_sum(const PeerMailbox& mb, const double* partial, int chunks, int64_t n, unsigned long long step,
+                     double* out, cudaStream_t stream) {
+  if (n > kPeerSumMaxN || mb.world < 1 || mb.world > PeerMailbox::kMaxRanks || n > mb.npad)
+    GBM_THROW(GBM_ERR_ARGUMENT, "launch_peer_sum: the vector does not fit the mailboxes / a resident grid");
+  peer_sum_kernel<<<static_cast<unsigned>((n + 31) / 32), 256, 0, stream>>>(mb, partial, chunks, n, step, out);
+  GBM_CUDA(cudaGetLastError());
+}
+
+void ShardedAllReduce::sum_partials(const double* partial, int chunks, int64_t n, double* out, cudaStream_t stream) {
+  launch_partial_reduce(partial, n, chunks, out, stream);
+  sum(out, n);
 }
 
 void block_row_sums(const double* Zg, int64_t n, int64_t nc, int64_t ld, double* rowsum, cudaStream_t stream) {
   Scratch partial(static_cast<size_t>(n) * kGemvChunks, stream);
   const unsigned row_blocks = static_cast<unsigned>((n + 255) / 256);
   gemv_n_partial_kernel<<<dim3(row_blocks, kGemvChunks), 256, 0, stream>>>(Zg, n, nc, ld, nullptr, partial.p);
-  gemv_n_reduce_kernel<<<row_blocks, 256, 0, stream>>>(partial.p, n, rowsum);
+  launch_partial_reduce(partial.p, n, kGemvChunks, rowsum, stream);
   GBM_CUDA(cudaGetLastError());
 }
 
@@ -573,8 +774,7 @@ bool lanczos_top_singular_sharded(const double* Zg, int64_t n, int64_t nc, int64
       static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((nc + 7) / 8, static_cast<int64_t>(sm_count) * 8)));
   auto apply = [&](const double* v, double* out) {
     if (fused && launch_gram_fused(Zg, n, nc, ld, v, partial.p, fgrid, stream)) {  // one pass over the block
-      partial_reduce_kernel<<<row_blocks, 256, 0, stream>>>(partial.p, n, fgrid, out);
-      ar->sum(out, n);
+      ar->sum_partials(partial.p, fgrid, n, out, stream);
       return;
     }
     if (nc > 0) {  // u = Zg' v
@@ -584,7 +784,7 @@ bool lanczos_top_singular_sharded(const double* Zg, int64_t n, int64_t nc, int64
         symv_kernel<<<symv_grid, 256, 0, stream>>>(Zg, n, nc, ld, v, u.p);
     }
     gemv_n_partial_kernel<<<dim3(row_blocks, kGemvChunks), 256, 0, stream>>>(Zg, n, nc, ld, u.p, partial.p);
-    gemv_n_reduce_kernel<<<row_blocks, 256, 0, stream>>>(partial.p, n, out);         // this rank's Zg u
+    launch_partial_reduce(partial.p, n, kGemvChunks, out, stream);                   // this rank's Zg u
     ar->sum(out, n);                                                                   // sum over the ranks
   };
   return lanczos_core(n, apply, tol, max_iter, x_dev, theta_out, iters_out, stream);

@@ -161,10 +161,11 @@ int gbm_grm_finalize(double* dK, int64_t n, double scale);
  * Kstd = (K .- mean(K, dims=1)) ./ std(K, dims=1)               (gwas.jl:130)
  * pc1  = MultivariateStats.fit(PCA, Kstd; maxoutdim=1).proj[:,1] (gwas.jl:234, :357):
  *        rows centred, top left singular vector (unit norm, sign arbitrary).  Only this one vector is
- *        needed, so n >= 1024 uses Lanczos with full reorthogonalisation on the device (csrc/lanczos.cu;
- *        residual ||Bx - theta x|| <= 2e-13 theta), smaller or non-converging problems and
- *        GBM_PC1_SOLVER=cusolver use cusolverDnDsyevdx.  K host or device; Kstd nullable; eig_ms (nullable) =
- *        time of the eigen step alone. */
+ *        needed, so n >= 1024 uses Lanczos with full reorthogonalisation on the operator Z Z' (Z = the
+ *        row-centred Kstd; never formed: one fused pass over Z per step, csrc/lanczos.cu; residual
+ *        ||Z Z'x - theta x|| <= 5e-13 theta), smaller or non-converging problems and GBM_PC1_SOLVER=cusolver use
+ *        cusolverDnDsyevdx.  K host or device; Kstd nullable; eig_ms (nullable) = time of the eigen step alone.
+ *        Multi-GPU form: gbm_sharded_kstd_pc1 (columns of K sharded over the group). */
 int gbm_kstd_pc1(const double* K, int64_t n, double* Kstd, double* pc1, double* eig_ms);
 
 /* ---- the marker scan: the loops of gwasols (gwas.jl:239-249) and gwaslmm (:363-389) ---

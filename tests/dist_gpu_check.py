@@ -46,7 +46,16 @@ def main():
     dm2 = gbm_b200.DeviceMatrix.generate(seed, n2, c1 - c0, synth.KIND_DIPLOID, col0=c0)
     sg2 = sharded.ShardedGWAS(dm2, p2, c0)
     K2 = sg2.grm("simple")
+    pc2 = sg2.pc1()                       # per-step all-reduce over peer memory (CUDA IPC mailboxes, peer_sum_kernel)
+    t_peer = time.perf_counter()
     pc2 = sg2.pc1()
+    t_peer = time.perf_counter() - t_peer
+    os.environ["GBM_PC1_PEER"] = "0"      # the same through NCCL
+    pc2_nccl = sg2.pc1()
+    t_nccl = time.perf_counter()
+    pc2_nccl = sg2.pc1()
+    t_nccl = time.perf_counter() - t_nccl
+    del os.environ["GBM_PC1_PEER"]
     # larger GRM timing incl. the all-reduce
     big_n, big_p = 4096, 65536 * world
     b0, b1 = sharded.shard_bounds(big_p, world, rank)
@@ -71,12 +80,13 @@ def main():
         e_1 = np.max(np.abs(z1 - z_ref) / np.maximum(np.abs(z_ref), 1e-3 * np.abs(z_ref).max()))
         _, pc2_ref, _ = gbm_b200.kstd_pc1(K2, want_kstd=False)
         e_pc = min(np.max(np.abs(pc2 - pc2_ref)), np.max(np.abs(pc2 + pc2_ref)))
+        e_pc = max(e_pc, min(np.max(np.abs(pc2_nccl - pc2_ref)), np.max(np.abs(pc2_nccl + pc2_ref))))
         ok = (np.array_equal(idx, prep.idx_cols) and np.array_equal(one["idx_cols"], prep.idx_cols) and e_k < 1e-11
               and e_z < 1e-9 and e_1 < 1e-9 and one["timing"]["ploidy"] == 4 and e_pc < 1e-9)
         tf = big_n * (big_n + 1) * big_p / dt / 1e12
         print(f"dist_gpu_check world={world}: idx_cols equal={np.array_equal(idx, prep.idx_cols)} "
               f"grm rel err={e_k:.2e} z rel err={e_z:.2e} one-call z rel err={e_1:.2e} "
-              f"sharded-Lanczos PC1 (n={n2}) vs single-GPU {e_pc:.2e} | sharded GRM n={big_n} p={big_p}: {dt*1e3:.1f} ms "
+              f"sharded-Lanczos PC1 (n={n2}) vs single-GPU {e_pc:.2e} (peer memory {t_peer*1e3:.1f} ms, NCCL {t_nccl*1e3:.1f} ms) | sharded GRM n={big_n} p={big_p}: {dt*1e3:.1f} ms "
               f"= {tf:.1f} TFLOP/s aggregate incl. all-reduce -> {'OK' if ok else 'FAIL'}", flush=True)
         if not ok:
             sys.exit(1)

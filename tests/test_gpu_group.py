@@ -108,6 +108,32 @@ def test_sharded_grm_and_pc1_match_the_oracle(gbm, grp, grm_type, kind, n, p):
         sm.free()
 
 
+def test_sharded_lanczos_pc1_over_peer_memory_and_over_nccl(gbm, grp, monkeypatch):
+    """n >= 4,096: the columns of K are sharded and every Lanczos step ends in an all-reduce of an n-vector -- one kernel
+    over peer memory (peer_sum_kernel: NVLink stores into every GPU's mailbox, rank-order sum) or, with
+    GBM_PC1_PEER=0, NCCL.  Both must give the single-GPU routine's vector (gwas.jl:234)."""
+    from gbm_b200 import multigpu
+
+    n, p = 4224, 4096
+    A = synth.block(17, n, 0, p, synth.KIND_DIPLOID)
+    K = go.grm_simple(A)
+    _, pc_one, _ = gbm.kstd_pc1(K, want_kstd=False)
+    sm = multigpu.ShardedMatrix.upload(grp, A[:, :64])
+    try:
+        got = {}
+        for route in ("1", "0", "1"):
+            monkeypatch.setenv("GBM_PC1_PEER", route)
+            pc, ms = sm.kstd_pc1(K)
+            assert ms > 0 and abs(np.linalg.norm(pc) - 1) < 1e-12
+            assert min(np.max(np.abs(pc - pc_one)), np.max(np.abs(pc + pc_one))) < 1e-9
+            if route in got:  # the same route twice: the same bits (fixed-order sums, no atomics)
+                assert np.array_equal(pc, got[route])
+            got[route] = pc
+        assert min(np.max(np.abs(got["1"] - got["0"])), np.max(np.abs(got["1"] + got["0"]))) < 1e-10
+    finally:
+        sm.free()
+
+
 @pytest.mark.parametrize("model,grm_type,kind,n,p", [("lmm", "simple", synth.KIND_DIPLOID, 400, 3001),
                                                      ("ols", "ploidy-aware", synth.KIND_TETRAPLOID, 300, 2000),
                                                      ("lmm", "simple", synth.KIND_CONTINUOUS, 1200, 900)])

@@ -211,6 +211,28 @@ def test_kstd_pc1_matches_oracle(gbm, n):
     assert np.max(np.abs(sgn * pc - want_pc)) < 1e-9
 
 
+@pytest.mark.parametrize("n", [2048, 1301])
+def test_pc1_cooperative_reorthogonalisation_equals_the_five_kernel_route(gbm, n, monkeypatch):
+    """The Lanczos step's Gram-Schmidt (twice), alpha, beta and the next basis vector run as ONE cooperative kernel
+    (reorth_kernel, csrc/lanczos.cu); GBM_PC1_NO_COOP=1 keeps the five separate launches.  Same arithmetic up to the
+    order of the fixed-order sums: the vectors agree far inside the 1e-9 they both owe the oracle, and each route
+    repeats its own bits."""
+    A = synth.block(21, n, 0, 2 * n, synth.KIND_DIPLOID)
+    K = go.grm_simple(A)
+    want = go.pca_pc1(go.standardise_K(K))
+    monkeypatch.delenv("GBM_PC1_SOLVER", raising=False)
+    monkeypatch.delenv("GBM_PC1_NO_COOP", raising=False)
+    _, pc_coop, _ = gbm.kstd_pc1(K, want_kstd=False)
+    assert gbm.last_timing()["launches"] > 20
+    _, pc_coop2, _ = gbm.kstd_pc1(K, want_kstd=False)
+    monkeypatch.setenv("GBM_PC1_NO_COOP", "1")
+    _, pc_five, _ = gbm.kstd_pc1(K, want_kstd=False)
+    assert np.array_equal(pc_coop, pc_coop2)
+    assert np.max(np.abs(pc_coop - np.sign(pc_coop @ pc_five) * pc_five)) < 1e-10
+    for pc in (pc_coop, pc_five):
+        assert np.max(np.abs(np.sign(pc @ want) * pc - want)) < 1e-9
+
+
 @pytest.mark.parametrize("n,kind", [(1024, synth.KIND_DIPLOID), (1500, synth.KIND_CONTINUOUS), (2600, synth.KIND_TETRAPLOID),
                                     (1301, synth.KIND_DIPLOID)])
 def test_pc1_lanczos_matches_oracle_and_cusolver(gbm, n, kind, monkeypatch):
