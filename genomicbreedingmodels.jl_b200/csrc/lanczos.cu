@@ -15,6 +15,8 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "../../include/gbm_b200.h"
@@ -598,6 +600,45 @@ void tridiag_top(const std::vector<double>& a, const std::vector<double>& b, int
   }
 }
 
+// Small pinned host buffers, reused across calls and threads (cudaMallocHost costs ~0.1 ms and synchronises): a lease
+// takes one that is large enough from the free list or allocates it; buffers live until the process ends.
+struct PinnedLease {
+  double* p = nullptr;
+  size_t count = 0;
+  explicit PinnedLease(size_t n) {
+    {
+      std::lock_guard<std::mutex> lk(mutex());
+      auto& fl = free_list();
+      for (size_t i = 0; i < fl.size(); ++i)
+        if (fl[i].second >= n) {
+          p = fl[i].first;
+          count = fl[i].second;
+          fl.erase(fl.begin() + i);
+          break;
+        }
+    }
+    if (!p) {
+      count = std::max<size_t>(n, 4 * 3001);
+      GBM_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&p), sizeof(double) * count, cudaHostAllocPortable));
+    }
+  }
+  ~PinnedLease() {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(mutex());
+    free_list().emplace_back(p, count);
+  }
+  PinnedLease(const PinnedLease&) = delete;
+  PinnedLease& operator=(const PinnedLease&) = delete;
+  static std::mutex& mutex() {
+    static std::mutex m;
+    return m;
+  }
+  static std::vector<std::pair<double*, size_t>>& free_list() {
+    static std::vector<std::pair<double*, size_t>> v;
+    return v;
+  }
+};
+
 // Lanczos with full reorthogonalisation on the operator `apply(v, out)` (out = Op v, both device n-vectors, launched
 // on `stream`); Op symmetric positive semi-definite.
 template <typename Apply>
@@ -607,13 +648,22 @@ static bool lanczos_core(int64_t n, Apply&& apply, double tol, int max_iter, dou
   if (m_max < 2) return false;
   const int64_t ldv = (n + 1) / 2 * 2;
   double *V = nullptr, *w = nullptr, *c = nullptr, *alpha = nullptr, *beta = nullptr, *sdev = nullptr, *normpart = nullptr;
+  PinnedLease pin(static_cast<size_t>(4) * (m_max + 1));  // two slots of (alpha, beta) for the asynchronous checks
+  cudaEvent_t ev[2] = {nullptr, nullptr};
   const int64_t ngroups = (n + 31) / 32;
   const int coop_grid = static_cast<int>(std::min<int64_t>(reorth_max_grid(), ngroups));
   auto release = [&] {
     for (double* p : {V, w, c, alpha, beta, sdev, normpart})
       if (p) cudaFreeAsync(p, stream);
+    for (cudaEvent_t& e : ev)
+      if (e) {
+        cudaEventSynchronize(e);  // the pinned buffer goes back to the pool: no copy may still be in flight
+        cudaEventDestroy(e);
+        e = nullptr;
+      }
   };
   try {
+    for (cudaEvent_t& e : ev) GBM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&V), sizeof(double) * ldv * (m_max + 1), stream));
     GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&w), sizeof(double) * ldv, stream));
     GBM_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&c), sizeof(double) * (m_max + 1), stream));
@@ -631,7 +681,25 @@ static bool lanczos_core(int64_t n, Apply&& apply, double tol, int max_iter, dou
     int m = 0;
     double theta = 0.0;
     int next_check = 30;
-    for (int j = 0; j < m_max; ++j) {
+    // Convergence checks do not drain the stream: alpha / beta go to a pinned buffer behind an event and are examined
+    // ONE check later, while the GPU is already working on the following steps (a synchronous check idled the GPU for
+    // the round trip + the host's tridiagonal solve every 6-10 steps).  The decision is taken on the same m as before,
+    // so the result is unchanged; the steps enqueued past that m touch neither V[:, 0..m) nor alpha / beta[0..m).
+    struct Pending {
+      int m = 0;
+      int slot = 0;
+    } pending;
+    int slot = 0;
+    auto examine = [&](const Pending& c) {  // true: converged at c.m
+      GBM_CUDA(cudaEventSynchronize(ev[c.slot]));
+      const double* pa = pin.p + static_cast<size_t>(c.slot) * 2 * (m_max + 1);
+      ha.assign(pa, pa + c.m);
+      hb.assign(pa + (m_max + 1), pa + (m_max + 1) + c.m);
+      tridiag_top(ha, hb, c.m, &theta, &s);
+      const double resid = fabs(hb[c.m - 1] * s[c.m - 1]);
+      return resid <= tol * fabs(theta) || !(hb[c.m - 1] > 1e-14 * fabs(theta));
+    };
+    for (int j = 0; j < m_max && !converged; ++j) {
       const double* vj = V + static_cast<int64_t>(j) * ldv;
       apply(vj, w);
       double* vnext = V + static_cast<int64_t>(j + 1) * ldv;
@@ -648,24 +716,26 @@ static bool lanczos_core(int64_t n, Apply&& apply, double tol, int max_iter, dou
         }
         norm_next_kernel<<<1, 1024, 0, stream>>>(w, n, vnext, beta, j);
       }
-      m = j + 1;
-      if (m == next_check || m == m_max) {
+      if (j + 1 == next_check || j + 1 == m_max) {
         GBM_CUDA(cudaGetLastError());
-        ha.resize(m);
-        hb.resize(m);
-        GBM_CUDA(cudaMemcpyAsync(ha.data(), alpha, sizeof(double) * m, cudaMemcpyDeviceToHost, stream));
-        GBM_CUDA(cudaMemcpyAsync(hb.data(), beta, sizeof(double) * m, cudaMemcpyDeviceToHost, stream));
-        GBM_CUDA(cudaStreamSynchronize(stream));
-        tridiag_top(ha, hb, m, &theta, &s);
-        const double resid = fabs(hb[m - 1] * s[m - 1]);
-        if (resid <= tol * fabs(theta) || !(hb[m - 1] > 1e-14 * fabs(theta))) {
+        double* pa = pin.p + static_cast<size_t>(slot) * 2 * (m_max + 1);
+        GBM_CUDA(cudaMemcpyAsync(pa, alpha, sizeof(double) * (j + 1), cudaMemcpyDeviceToHost, stream));
+        GBM_CUDA(cudaMemcpyAsync(pa + (m_max + 1), beta, sizeof(double) * (j + 1), cudaMemcpyDeviceToHost, stream));
+        GBM_CUDA(cudaEventRecord(ev[slot], stream));
+        if (pending.m > 0 && examine(pending)) {
           converged = true;
+          m = pending.m;
           break;
         }
-        // a check is one stream synchronisation + an O(m) host solve: cheap next to the steps an overshoot costs
-        // (every step past convergence is a pass over the matrix and, when sharded, an all-reduce)
-        next_check = m + (m < 100 ? 10 : 6);
+        pending.m = j + 1;
+        pending.slot = slot;
+        slot ^= 1;
+        next_check = j + 1 + (j + 1 < 100 ? 10 : 6);
       }
+    }
+    if (!converged && pending.m > 0) {  // the last check enqueued
+      converged = examine(pending);
+      m = pending.m;
     }
     if (converged) {
       GBM_CUDA(cudaMemcpyAsync(sdev, s.data(), sizeof(double) * m, cudaMemcpyHostToDevice, stream));
