@@ -79,8 +79,8 @@ function upload(A::Matrix{Float64}, rows::Union{Nothing,Vector{Int64}}, cols::Un
     p = isnothing(cols) ? p0 : length(cols)
     check(ccall((:gbm_matrix_upload_indexed, LIBGBM), Cint,
                 (Ptr{Float64}, Int64, Int64, Int64, Ptr{Int64}, Int64, Ptr{Int64}, Int64, Ref{Ptr{Cvoid}}),
-                A, n0, p0, n0, isnothing(rows) ? C_NULL : pointer(rows), n,
-                isnothing(cols) ? C_NULL : pointer(cols), p, h))
+                A, n0, p0, n0, isnothing(rows) ? C_NULL : rows, n,   # arrays, not pointer(...): ccall roots them
+                isnothing(cols) ? C_NULL : cols, p, h))
     DeviceMatrix(h[], n, p)
 end
 
@@ -108,7 +108,7 @@ function kstd_pc1(K::Matrix{Float64}; want_kstd::Bool = true, want_pc1::Bool = t
     pc = want_pc1 ? Vector{Float64}(undef, n) : nothing
     ms = Ref{Float64}(0.0)
     check(ccall((:gbm_kstd_pc1, LIBGBM), Cint, (Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
-                K, n, want_kstd ? pointer(Ks) : C_NULL, want_pc1 ? pointer(pc) : C_NULL, ms))
+                K, n, want_kstd ? Ks : C_NULL, want_pc1 ? pc : C_NULL, ms))
     (Ks, pc)
 end
 
@@ -320,12 +320,19 @@ gwaslmm(; genomes::Genomes, phenomes::Phenomes, idx_entries::Union{Nothing,Vecto
 
 # gwasreml (src/gwas.jl:549-613): GRM-covariance LMM, variance components re-estimated per marker.
 # Engine: K = U S U' (cuSOLVER), U'A by the FP64 DMMA GEMM, per-marker REML delta search on the
-# device.  Uses the symmetric un-standardised GRM and the standard REML likelihood (the reference
-# passes the column-standardised K and minimises a non-standard objective; see oracle/lmm_oracle.py).
+# device.  `objective` (an extension; the reference has no such keyword):
+#   "reml" (default)  the symmetric un-standardised GRM and the standard REML likelihood, z with the profiled sigma^2;
+#   "reference"       the reference's OWN objective, box and statistic (src/gwas.jl:478, :588, :596-599) on the symmetric
+#                     part of the column-standardised K that gwasprep hands to loglikreml (:130, :564-573).
+# What a rotation-based engine cannot reproduce (the non-symmetric part of that K, the L-BFGS path) is quantified in
+# oracle/lmm_oracle.py and DESIGN.md section 2.
+const GBM_LMM_REFERENCE_OBJECTIVE = Cint(8)
 function gwasreml(; genomes::Genomes, phenomes::Phenomes, idx_entries::Union{Nothing,Vector{Int64}} = nothing,
     idx_loci_alleles::Union{Nothing,Vector{Int64}} = nothing, idx_trait::Int64 = 1, GRM_type::String = "simple",
-    verbose::Bool = false)::Fit
-    pr = prepare(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type, false; need_kstd = false, need_pc1 = false)
+    verbose::Bool = false, objective::String = "reml")::Fit
+    objective in ("reml", "reference") || throw(ArgumentError("objective must be \"reml\" or \"reference\""))
+    ref = objective == "reference"
+    pr = prepare(genomes, phenomes, idx_entries, idx_loci_alleles, idx_trait, GRM_type, ref; need_kstd = ref, need_pc1 = false)
     if length(pr.entries) != size(pr.K, 1)
         free!(pr.dm)
         throw(ArgumentError("The GRM is computed on all entries of `genomes` but some entries were dropped: y and the GRM have different sizes."))
@@ -336,12 +343,12 @@ function gwasreml(; genomes::Genomes, phenomes::Phenomes, idx_entries::Union{Not
     plan = Ref{Ptr{Cvoid}}(C_NULL); eig_ms = Ref{Float64}(0.0); lam0 = Ref{Float64}(0.0)
     check(ccall((:gbm_lmm_plan_create, LIBGBM), Cint,
                 (Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Ref{Ptr{Cvoid}}, Ref{Float64}, Ref{Float64}),
-                pr.K, pr.dm.n, y, C_NULL, 0, pr.dm.n, plan, eig_ms, lam0))
+                ref ? 0.5 .* (pr.K .+ pr.K') : pr.K, pr.dm.n, y, C_NULL, 0, pr.dm.n, plan, eig_ms, lam0))
     stat = Vector{Float64}(undef, pr.dm.p)
     tf = Ref{Float64}(0.0); sms = Ref{Float64}(0.0)
     rc = ccall((:gbm_lmm_plan_run, LIBGBM), Cint,
                (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ref{Float64}),
-               plan[], pr.dm.handle, 0, C_NULL, C_NULL, stat, C_NULL, C_NULL, tf, sms)
+               plan[], pr.dm.handle, ref ? GBM_LMM_REFERENCE_OBJECTIVE : Cint(0), C_NULL, C_NULL, stat, C_NULL, C_NULL, tf, sms)
     ccall((:gbm_lmm_plan_free, LIBGBM), Cint, (Ptr{Cvoid},), plan[])
     free!(pr.dm)
     check(rc)

@@ -403,3 +403,143 @@ def test_side_vector_digits_reconstruct_the_vectors_exactly():
         assert abs(float(fixed - exact)) <= 0.5 * sc * float(codes.sum())
     with pytest.raises(L.ArgumentError):
         L.check(lib.gbm_side_vector_digits(L.ptr(Q), n, 3, n, L.ptr(dig), ld, scale))
+
+
+# ---- the Julia shim against the header (static: there is no Julia runtime in the image) ---------------------------
+def _split_top_level(text):
+    """Split on commas that are not nested in (), [] or {}."""
+    parts, depth, cur = [], 0, []
+    for ch in text:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append("".join(cur).strip())
+            cur = []
+        else:
+            cur.append(ch)
+    tail = "".join(cur).strip()
+    if tail:
+        parts.append(tail)
+    return parts
+
+
+def _balanced(text, start):
+    """text[start] == '(' -> index just past its matching ')'."""
+    depth = 0
+    in_str = False
+    i = start
+    while i < len(text):
+        ch = text[i]
+        if ch == '"' and text[i - 1] != "\\":
+            in_str = not in_str
+        elif not in_str:
+            if ch == "(":
+                depth += 1
+            elif ch == ")":
+                depth -= 1
+                if depth == 0:
+                    return i + 1
+        i += 1
+    raise AssertionError("unbalanced parenthesis in the Julia shim")
+
+
+def _c_kind(ctype):
+    t = ctype.strip()
+    if "*" in t:
+        return "ptr"
+    t = re.sub(r"\bconst\b", "", t).split()
+    base = t[0] if t else ""
+    return {"int64_t": "i64", "double": "f64", "int": "i32", "int32_t": "i32", "uint64_t": "i64"}.get(base, base)
+
+
+def _julia_kind(jtype):
+    t = jtype.strip()
+    if t.startswith(("Ptr{", "Ref{")) or t == "Cstring":
+        return "ptr"
+    return {"Int64": "i64", "Float64": "f64", "Cint": "i32", "Int32": "i32", "UInt64": "i64"}.get(t, t)
+
+
+def header_prototypes():
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    protos = {}
+    for ret, name, args in re.findall(r"\b(int|const char\s*\*)\s+(gbm_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        args = " ".join(args.split())
+        kinds = []
+        if args and args != "void":
+            for a in _split_top_level(args):
+                a = re.sub(r"/\*.*?\*/", "", a)
+                # drop the parameter name: everything up to the last identifier
+                m = re.match(r"(.*?)([A-Za-z_][A-Za-z0-9_]*)?$", a.strip())
+                ctype = m.group(1) if m.group(2) and m.group(1).strip() else a
+                kinds.append(_c_kind(ctype))
+        protos[name] = ("ptr" if "*" in ret else "i32", kinds)
+    return protos
+
+
+@pytest.mark.parametrize("shim", ["genomicbreedingmodels.jl_b200/julia/GenomicBreedingModelsB200.jl"])
+def test_julia_shim_ccalls_match_the_header(shim):
+    """Every `ccall((:gbm_x, LIBGBM), Ret, (ArgTypes...), args...)` of the Julia shim (never executed here) binds a
+    symbol the header declares, with the header's return kind, the same number of parameters, the same kind (pointer /
+    Int64 / Cint / Float64) in every position, and as many actual arguments as declared types."""
+    text = open(os.path.join(ROOT, shim)).read()
+    protos = header_prototypes()
+    assert len(protos) >= 40
+    seen = set()
+    for m in re.finditer(r"ccall\(\(:(gbm_[a-z0-9_]+),\s*LIBGBM\)\s*,", text):
+        name = m.group(1)
+        assert name in protos, f"{name}: not declared in include/gbm_b200.h"
+        call_open = text.index("(", m.start())
+        body = text[call_open + 1:_balanced(text, call_open) - 1]
+        parts = _split_top_level(re.sub(r"#[^\n]*", "", body))
+        ret, argtypes, actual = parts[1], parts[2], parts[3:]
+        assert argtypes.startswith("(") and argtypes.endswith(")"), (name, argtypes)
+        jkinds = [_julia_kind(t) for t in _split_top_level(argtypes[1:-1])]
+        want_ret, ckinds = protos[name]
+        assert _julia_kind(ret) == want_ret, (name, ret)
+        assert jkinds == ckinds, f"{name}: Julia {jkinds} vs header {ckinds}"
+        assert len(actual) == len(ckinds), f"{name}: {len(actual)} arguments for {len(ckinds)} parameters"
+        seen.add(name)
+    # the hot path's entry points are all bound
+    for must in ("gbm_init", "gbm_matrix_upload_compact", "gbm_matrix_upload_indexed", "gbm_colstats", "gbm_grm",
+                 "gbm_kstd_pc1", "gbm_scan", "gbm_group_create_local", "gbm_sharded_upload", "gbm_sharded_gwas",
+                 "gbm_lmm_plan_create", "gbm_lmm_plan_run", "gbm_transform1_screen", "gbm_transform2_screen"):
+        assert must in seen, must
+
+
+def test_julia_shim_timing_struct_matches_the_header():
+    """`GwasTiming` (passed by reference to gbm_sharded_gwas) has gbm_gwas_timing's fields in order and width."""
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    body = re.search(r"typedef struct gbm_gwas_timing \{(.*?)\} gbm_gwas_timing;", src, flags=re.S).group(1)
+    c_fields = []
+    for decl in body.split(";"):
+        decl = " ".join(decl.split())
+        if not decl:
+            continue
+        ctype, names = decl.split(" ", 1)
+        c_fields += [(n.strip(), _c_kind(ctype)) for n in names.split(",")]
+    text = open(os.path.join(ROOT, "genomicbreedingmodels.jl_b200/julia/GenomicBreedingModelsB200.jl")).read()
+    jbody = re.search(r"struct GwasTiming[^\n]*\n(.*?)\nend", text, flags=re.S).group(1)
+    j_fields = [(n, _julia_kind(t)) for n, t in re.findall(r"([a-z_0-9]+)::([A-Za-z0-9]+)", jbody)]
+    assert j_fields == c_fields
+
+
+def test_ctypes_signatures_match_the_header():
+    """gbm_b200/_lib.py: restype and the kind (pointer / int64 / int / double) of every argtype equal the header's."""
+    import ctypes
+
+    from gbm_b200 import _lib as L
+
+    def kind(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or isinstance(t, type(ctypes.POINTER(ctypes.c_int))) and hasattr(t, "_type_") and not isinstance(t._type_, str):
+            return "ptr"
+        return {ctypes.c_int64: "i64", ctypes.c_uint64: "i64", ctypes.c_int: "i32", ctypes.c_int32: "i32",
+                ctypes.c_double: "f64"}[t]
+
+    protos = header_prototypes()
+    assert sorted(protos) == sorted(L.SIGNATURES)
+    for name, (res, args) in L.SIGNATURES.items():
+        want_ret, ckinds = protos[name]
+        assert kind(res) == want_ret, name
+        assert [kind(a) for a in args] == ckinds, f"{name}: ctypes {[kind(a) for a in args]} vs header {ckinds}"
