@@ -182,8 +182,7 @@ struct Worker {
 // one GPU's side of the peer-memory all-reduce of the sharded Lanczos step (lanczos.cu: peer_sum_kernel)
 struct PeerState {
   PeerMailbox mb;
-  double* slots = nullptr;               // this GPU's mailbox: 2 x W x npad doubles (cudaMalloc: shareable by CUDA IPC)
-  unsigned long long* flags = nullptr;   // W step counters
+  double* slots = nullptr;               // this GPU's mailbox: 2 x W x npad entries of 16 bytes (cudaMalloc: shareable by CUDA IPC)
   std::vector<void*> opened;             // CUDA IPC mappings of the peers' mailboxes (rank groups)
   unsigned long long step = 0;
 };
@@ -361,8 +360,6 @@ void free_peer(gbm_group& G) {
       for (void* p : ps.opened) cudaIpcCloseMemHandle(p);
       ps.opened.clear();
       if (ps.slots) cudaFree(ps.slots);
-      if (ps.flags) cudaFree(ps.flags);
-      if (ps.mb.cta_counter) cudaFree(ps.mb.cta_counter);
       if (ps.mb.error) cudaFree(ps.mb.error);
       ps = PeerState();
     });
@@ -400,13 +397,9 @@ bool ensure_peer(gbm_group& G, int64_t n) {
         else GBM_CUDA(e);
       }
     }
-    GBM_CUDA(cudaMalloc(reinterpret_cast<void**>(&ps.slots), sizeof(double) * 2 * W * npad));
-    GBM_CUDA(cudaMalloc(reinterpret_cast<void**>(&ps.flags), sizeof(unsigned long long) * W));
-    GBM_CUDA(cudaMalloc(reinterpret_cast<void**>(&ps.mb.cta_counter), sizeof(unsigned int)));
+    GBM_CUDA(cudaMalloc(reinterpret_cast<void**>(&ps.slots), sizeof(double) * 2 * 2 * W * npad));
     GBM_CUDA(cudaMalloc(reinterpret_cast<void**>(&ps.mb.error), sizeof(int)));
-    GBM_CUDA(cudaMemset(ps.slots, 0, sizeof(double) * 2 * W * npad));
-    GBM_CUDA(cudaMemset(ps.flags, 0, sizeof(unsigned long long) * W));
-    GBM_CUDA(cudaMemset(ps.mb.cta_counter, 0, sizeof(unsigned int)));
+    GBM_CUDA(cudaMemset(ps.slots, 0, sizeof(double) * 2 * 2 * W * npad));  // stamp 0: no step has it
     GBM_CUDA(cudaMemset(ps.mb.error, 0, sizeof(int)));
     GBM_CUDA(cudaDeviceSynchronize());
   });
@@ -418,24 +411,20 @@ bool ensure_peer(gbm_group& G, int64_t n) {
       G.reduce_host(okr, ncclMin);
       if (okr[0][0] < 0.5) throw Error{GBM_ERR_RUNTIME, "no peer access"};
       for (int g = 0; g < G.n_local; ++g)
-        for (int q = 0; q < W; ++q) {
-          G.peer[g].mb.slots[q] = G.peer[q].slots;
-          G.peer[g].mb.flags[q] = G.peer[q].flags;
-        }
+        for (int q = 0; q < W; ++q) G.peer[g].mb.slots[q] = G.peer[q].slots;
     } else {
       // one process per GPU: CUDA IPC handles travel through an all-gather, every peer mailbox is mapped here.  The
       // mapping can fail on some ranks only (a peer on another node, no P2P path): G.phase makes that a common verdict.
       struct Handles {
-        cudaIpcMemHandle_t slots, flags;
+        cudaIpcMemHandle_t slots;
       };
-      static_assert(sizeof(Handles) == 128, "two 64-byte IPC handles");
+      static_assert(sizeof(Handles) == 64, "a 64-byte IPC handle");
       std::vector<Handles> all(W);
       G.run([&](int g) {
         PeerState& ps = G.peer[g];
         cudaStream_t st = state().stream;
         const int me = G.rank_of(g);
         GBM_CUDA(cudaIpcGetMemHandle(&all[me].slots, ps.slots));
-        GBM_CUDA(cudaIpcGetMemHandle(&all[me].flags, ps.flags));
         Dev<uint8_t> d(sizeof(Handles) * W);
         GBM_CUDA(cudaMemcpyAsync(d.p + sizeof(Handles) * me, &all[me], sizeof(Handles), cudaMemcpyHostToDevice, st));
         GBM_NCCL(nccl().AllGather(d.p + sizeof(Handles) * me, d.p, sizeof(Handles), ncclUint8, G.comm[g], st));
@@ -448,16 +437,12 @@ bool ensure_peer(gbm_group& G, int64_t n) {
         for (int q = 0; q < W; ++q) {
           if (q == me) {
             ps.mb.slots[q] = ps.slots;
-            ps.mb.flags[q] = ps.flags;
             continue;
           }
-          void *ps_q = nullptr, *pf_q = nullptr;
+          void* ps_q = nullptr;
           GBM_CUDA(cudaIpcOpenMemHandle(&ps_q, all[q].slots, cudaIpcMemLazyEnablePeerAccess));
           ps.opened.push_back(ps_q);
-          GBM_CUDA(cudaIpcOpenMemHandle(&pf_q, all[q].flags, cudaIpcMemLazyEnablePeerAccess));
-          ps.opened.push_back(pf_q);
           ps.mb.slots[q] = static_cast<double*>(ps_q);
-          ps.mb.flags[q] = static_cast<unsigned long long*>(pf_q);
         }
       });
     }
@@ -472,6 +457,7 @@ bool ensure_peer(gbm_group& G, int64_t n) {
   for (int g = 0; g < G.n_local; ++g) {
     G.peer[g].mb.world = W;
     G.peer[g].mb.me = G.rank_of(g);
+    G.peer[g].mb.mine = G.peer[g].mb.slots[G.rank_of(g)];
     G.peer[g].mb.npad = npad;
   }
   G.peer_npad = npad;

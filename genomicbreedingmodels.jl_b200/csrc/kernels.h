@@ -148,21 +148,23 @@ struct ShardedAllReduce {
   virtual void sum_partials(const double* partial, int chunks, int64_t n, double* out, cudaStream_t stream);
   virtual ~ShardedAllReduce() {}
 };
-// Mailboxes of a one-shot all-reduce over peer memory: every rank owns 2 (step parity) x W slots of npad doubles and W
-// step counters; slots[q] / flags[q] are rank q's mailbox as seen from THIS device (peer access or a CUDA IPC mapping).
+// Mailboxes of a one-shot all-reduce over peer memory.  Every rank owns 2 (step parity) x W (source rank) x npad
+// entries of 16 bytes; slots[q] is rank q's mailbox as seen from THIS device (peer access or a CUDA IPC mapping).  An
+// entry carries one double as two 8-byte words {step << 32 | low half, step << 32 | high half}: the step number travels
+// in the same (atomic) 8-byte store as the data, so a reader that sees the stamp has the data -- no fence, no separate
+// flag, one NVLink crossing per exchange (the idea of NCCL's LL protocol, for FP64 payloads).
 struct PeerMailbox {
   static constexpr int kMaxRanks = 8;
-  double* slots[kMaxRanks];
-  unsigned long long* flags[kMaxRanks];
+  double* slots[kMaxRanks];  // 2 doubles of storage per entry
+  double* mine = nullptr;    // = slots[me]
   int world = 0, me = 0;
   int64_t npad = 0;
-  unsigned int* cta_counter = nullptr;  // this device
-  int* error = nullptr;                 // this device: set when a peer did not show up in time
+  int* error = nullptr;  // this device: set when a peer did not show up in time
 };
-// partial-sum reduction + all-reduce in one kernel: this rank's reduced vector is stored into slot `me` of every
-// rank's mailbox over NVLink, a step counter is released, the kernel waits for the W counters of its own mailbox and
-// adds the W slots in rank order (the same order, hence the same bits, on every rank).  `step` starts at 1 and grows
-// by one per call on every rank.
+// partial-sum reduction + all-reduce in one kernel: this rank's reduced vector is stored, stamped with `step`, into slot
+// `me` of every rank's mailbox over NVLink; the kernel then polls the W slots of its own mailbox for the stamp and adds
+// them in rank order (the same order, hence the same bits, on every rank).  `step` starts at 1 and grows by one per
+// call on every rank; a slot is reused two steps later, when every reader is provably past it.
 void launch_peer_sum(const PeerMailbox& mb, const double* partial, int chunks, int64_t n, unsigned long long step,
                      double* out, cudaStream_t stream);
 void block_row_sums(const double* Zg, int64_t n, int64_t nc, int64_t ld, double* rowsum, cudaStream_t stream);

@@ -243,12 +243,12 @@ static void launch_partial_reduce(const double* partial, int64_t n, int chunks, 
 }
 
 // ---- partial-sum reduction fused with the all-reduce over peer memory (NVLink P2P stores) --------------------------
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_volatile_v2(double* p, unsigned long long a, unsigned long long b) {
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+__device__ __forceinline__ ulonglong2 ld_volatile_v2(const double* p) {
+  ulonglong2 v;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
   return v;
 }
 // One CTA per 32 rows (the layout of partial_reduce_kernel, the same bits for the rank's own sum).  Every CTA waits
@@ -261,30 +261,37 @@ __global__ void __launch_bounds__(256) peer_sum_kernel(const PeerMailbox mb, con
   const int64_t i = static_cast<int64_t>(blockIdx.x) * 32 + lane;
   const int W = mb.world;
   const int64_t par = static_cast<int64_t>(step & 1ull) * W;
+  const unsigned long long stamp = (step & 0xffffffffull) << 32;
   part[g][lane] = i < n ? chunk_group_sum(partial, n, chunks, i, g) : 0.0;
   __syncthreads();
-  if (g == 0 && i < n) {
-    double v = 0.0;
+  if (g != 0 || i >= n) return;
+  double v = 0.0;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) v += part[q][lane];
-    for (int q = 0; q < W; ++q) mb.slots[q][(par + mb.me) * mb.npad + i] = v;  // q == me: the local mailbox
-    __threadfence_system();
+  for (int q = 0; q < 8; ++q) v += part[q][lane];
+  {  // this rank's rows into slot `me` of every mailbox (q == me: the local one), data and stamp in the same words
+    const unsigned long long u = static_cast<unsigned long long>(__double_as_longlong(v));
+    const unsigned long long lo = stamp | (u & 0xffffffffull), hi = stamp | (u >> 32);
+    const int64_t at = 2 * ((par + mb.me) * mb.npad + i);
+#pragma unroll
+    for (int q = 0; q < PeerMailbox::kMaxRanks; ++q)
+      if (q < W) st_volatile_v2(mb.slots[q] + at, lo, hi);
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned int done = atomicAdd(mb.cta_counter, 1u);
-    if (done == gridDim.x - 1) {  // every CTA of this rank has stored its rows: publish the step to all mailboxes
-      *mb.cta_counter = 0u;
-      __threadfence_system();
-      for (int q = 0; q < W; ++q) st_release_sys(mb.flags[q] + mb.me, step);
-    }
-  }
-  if (threadIdx.x < W) {  // wait for every rank's contribution to THIS mailbox (bounded: a dead peer must not hang the GPU)
-    const unsigned long long* f = mb.flags[mb.me] + threadIdx.x;
-    volatile int* err = mb.error;
-    const long long t0 = clock64();
-    while (ld_acquire_sys(f) < step) {
+  // every rank's contribution to THIS mailbox: poll until all W entries of the row carry the stamp (bounded: a dead
+  // peer must not hang the GPU)
+  const double* mine = mb.mine + 2 * (par * mb.npad + i);
+  ulonglong2 x[PeerMailbox::kMaxRanks];
+  volatile int* err = mb.error;
+  const long long t0 = clock64();
+  for (unsigned spin = 0;; ++spin) {
+#pragma unroll
+    for (int r = 0; r < PeerMailbox::kMaxRanks; ++r)  // all W loads in flight before any of them is examined
+      if (r < W) x[r] = ld_volatile_v2(mine + 2 * r * mb.npad);
+    bool all = true;
+#pragma unroll
+    for (int r = 0; r < PeerMailbox::kMaxRanks; ++r)
+      if (r < W) all &= ((x[r].x & 0xffffffff00000000ull) == stamp) & ((x[r].y & 0xffffffff00000000ull) == stamp);
+    if (all) break;
+    if ((spin & 255u) == 255u) {
       if (*err) break;                        // an earlier step already gave up: do not wait 10 s per step
       if (clock64() - t0 > 20000000000ll) {  // ~10 s
         *err = 1;
@@ -292,13 +299,11 @@ __global__ void __launch_bounds__(256) peer_sum_kernel(const PeerMailbox mb, con
       }
     }
   }
-  __syncthreads();
-  if (g == 0 && i < n) {
-    const double* mine = mb.slots[mb.me];
-    double t = 0.0;
-    for (int r = 0; r < W; ++r) t += __ldcv(mine + (par + r) * mb.npad + i);  // rank order; volatile: bypass L1
-    out[i] = t;
-  }
+  double t = 0.0;
+#pragma unroll
+  for (int r = 0; r < PeerMailbox::kMaxRanks; ++r)  // rank order
+    if (r < W) t += __longlong_as_double(static_cast<long long>((x[r].x & 0xffffffffull) | (x[r].y << 32)));
+  out[i] = t;
 }
 
 constexpr int64_t kFusedMaxN = 512 * 24;

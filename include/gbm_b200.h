@@ -162,7 +162,8 @@ int gbm_grm_finalize(double* dK, int64_t n, double scale);
  * pc1  = MultivariateStats.fit(PCA, Kstd; maxoutdim=1).proj[:,1] (gwas.jl:234, :357):
  *        rows centred, top left singular vector (unit norm, sign arbitrary).  Only this one vector is
  *        needed, so n >= 1024 uses Lanczos with full reorthogonalisation on the operator Z Z' (Z = the
- *        row-centred Kstd; never formed: one fused pass over Z per step, csrc/lanczos.cu; residual
+ *        row-centred Kstd; never formed: one fused pass over Z per step, the whole reorthogonalisation in one
+ *        cooperative kernel (GBM_PC1_NO_COOP=1: five launches), csrc/lanczos.cu; residual
  *        ||Z Z'x - theta x|| <= 5e-13 theta), smaller or non-converging problems and GBM_PC1_SOLVER=cusolver use
  *        cusolverDnDsyevdx.  K host or device; Kstd nullable; eig_ms (nullable) = time of the eigen step alone.
  *        Multi-GPU form: gbm_sharded_kstd_pc1 (columns of K sharded over the group). */
@@ -331,7 +332,11 @@ int gbm_sharded_colstats(gbm_sharded* m, double* mean, double* sd, double* min_n
  * all-reduce), i.e. the aggregate rate of the group. */
 int gbm_sharded_grm(gbm_sharded* m, int grm_type, int ploidy, int flags, double* K, double* tflops);
 /* gbm_kstd_pc1 on the GRM left resident by gbm_sharded_grm (K = NULL) or on K (host, n x n, every process the same):
- * columns of K sharded, Lanczos with one n-vector all-reduce per step.  pc1: host, n. */
+ * columns of K sharded (n >= 4096), Lanczos with one n-vector all-reduce per step.  That all-reduce is ONE kernel fused
+ * with the reduction of the step's partial sums: every GPU stores its vector, stamped with the step number, into a
+ * mailbox on every other GPU over NVLink (peer access inside a process, CUDA IPC mappings between processes) and adds
+ * the W contributions in rank order -- identical bits on every GPU.  GPUs without a peer path, more than 8 ranks or
+ * GBM_PC1_PEER=0: ncclAllReduce.  pc1: host, n. */
 int gbm_sharded_kstd_pc1(gbm_sharded* m, const double* K, double* pc1, double* eig_ms);
 /* gbm_scan over the shards: outputs p x T column-major (ld p) / length p, host, on every process */
 int gbm_sharded_scan(gbm_sharded* m, const double* Y, int64_t T, int64_t ldy, const double* C, int64_t k, int64_t ldc,
