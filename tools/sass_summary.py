@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Per-object SASS opcode summary of libgbm_b200.so's CUDA units (cuobjdump -sass on csrc/*.o): the mnemonics that
 prove which hardware paths the kernels use -- TMA (UTMALDG / UBLKCP), mbarrier (SYNCS), FP64 tensor pipe (DMMA),
-tcgen05 (UTCIMMA = kind::i8 MMA, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit), REDUX, dp4a (IDP.4A).
+tcgen05 (UTCIMMA = kind::i8 MMA, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit), REDUX, dp4a (IDP.4A), and the
+system-scope 16-byte stores / loads of the peer-memory all-reduce (peer_sum_kernel: STG / LDG.E.128.STRONG.SYS).
 
     python tools/sass_summary.py > profiles/r02_sass_summary.md
 """
@@ -14,7 +15,7 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "genomicbreedingmodels.jl_b200", "csrc")
 KEYS = ["UTMALDG", "UBLKCP", "SYNCS", "DMMA", "UTCIMMA", "UTCBAR", "LDTM", "REDUX", "IDP.4A", "I2F.F64", "DFMA", "RED.E.ADD.F64",
-        "ATOMG", "LDS.128", "LDS.64", "HMMA", "IMMA"]
+        "ATOMG", "LDS.128", "LDS.64", "HMMA", "IMMA", "STG.E.128.STRONG.SYS", "LDG.E.128.STRONG.SYS"]
 
 
 def main():
