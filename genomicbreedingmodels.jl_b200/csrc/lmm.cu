@@ -257,7 +257,7 @@ __device__ __forceinline__ RemlEval<Q0 + 2> warp_eval(const LmmParams& prm, cons
 }
 
 template <int Q0>
-__global__ void __launch_bounds__(256) lmm_delta_kernel(const LmmParams prm) {
+__global__ void __launch_bounds__(256, Q0 == 1 ? 3 : 1) lmm_delta_kernel(const LmmParams prm) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
