@@ -365,18 +365,21 @@ void free_peer(gbm_group& G) {
     });
   } catch (...) {
   }
+  G.peer.clear();
   G.peer_npad = 0;
 }
 
 // Mailboxes for n-vectors on every GPU of the group, visible to every other GPU: peer access inside one process,
 // CUDA IPC mappings between processes.  Returns false (and remembers it) when the GPUs cannot reach each other's
-// memory -- the Lanczos step then uses NCCL.
+// memory -- the Lanczos step then uses NCCL.  The mailboxes are sized ONCE, for the largest n the fused Lanczos step
+// takes (kLanczosFusedMaxN: 3 MB per GPU at 8 ranks), and live as long as the group: a mailbox is never freed while
+// another process may still map it.
 bool ensure_peer(gbm_group& G, int64_t n) {
   const char* env = getenv("GBM_PC1_PEER");  // read per call: the tests compare both routes in one process
   if ((env && atoi(env) == 0) || G.world > PeerMailbox::kMaxRanks || G.world < 2 || G.peer_npad < 0) return false;
-  const int64_t npad = round_up(n, 256);
-  if (G.peer_npad >= npad) return true;
-  free_peer(G);
+  if (n > kLanczosFusedMaxN) return false;  // larger n take the two-pass step, whose all-reduce is NCCL's
+  const int64_t npad = round_up(kLanczosFusedMaxN, 256);
+  if (G.peer_npad == npad) return true;
   G.peer.assign(G.n_local, PeerState());
   const int W = G.world;
   std::vector<int> okv(G.n_local, 1);

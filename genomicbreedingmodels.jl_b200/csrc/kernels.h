@@ -148,6 +148,8 @@ struct ShardedAllReduce {
   virtual void sum_partials(const double* partial, int chunks, int64_t n, double* out, cudaStream_t stream);
   virtual ~ShardedAllReduce() {}
 };
+// the fused one-pass Lanczos step holds a column of Z twice in shared memory: n <= kLanczosFusedMaxN
+constexpr int64_t kLanczosFusedMaxN = 512 * 24;
 // Mailboxes of a one-shot all-reduce over peer memory.  Every rank owns 2 (step parity) x W (source rank) x npad
 // entries of 16 bytes; slots[q] is rank q's mailbox as seen from THIS device (peer access or a CUDA IPC mapping).  An
 // entry carries one double as two 8-byte words {step << 32 | low half, step << 32 | high half}: the step number travels

@@ -306,7 +306,9 @@ __global__ void __launch_bounds__(256) peer_sum_kernel(const PeerMailbox mb, con
   out[i] = t;
 }
 
-constexpr int64_t kFusedMaxN = 512 * 24;
+constexpr int64_t kFusedMaxN = kLanczosFusedMaxN;
+static_assert(kFusedMaxN == 512 * 24, "gram_fused_kernel<24>: 24 rows per thread");
+static_assert(kFusedMaxN <= kPeerSumMaxN, "the peer exchange must take every n the fused step takes");
 static size_t gram_fused_smem(int64_t n) { return static_cast<size_t>((n + 1) / 2 * 2) * 16 + 16 + 16 * 8 + 128; }
 
 // launches the fused step on `grid` CTAs; returns false when n is too large for it
