@@ -1660,6 +1660,14 @@ int gbm_side_vector_digits(const double* Q, int64_t n, int M, int64_t ldq, int8_
   GBM_API_END
 }
 
+int gbm_tridiag_top(const double* alpha, const double* beta, int64_t m, double* theta, double* s) {
+  GBM_API_BEGIN
+  if (!alpha || (m > 1 && !beta) || !theta || !s || m < 1 || m > 100000)
+    GBM_THROW(GBM_ERR_ARGUMENT, "gbm_tridiag_top: bad arguments");
+  lanczos_tridiag_top(alpha, beta, static_cast<int>(m), theta, s);
+  GBM_API_END
+}
+
 int gbm_scan_host(const double* A, int64_t n, int64_t p, int64_t lda, const double* Y, int64_t T, int64_t ldy,
                   const double* C, int64_t k, int64_t ldc, int model, int flags, double* beta, double* se,
                   double* stat, double* neglog10p, double* mean, double* sd, uint8_t* keep) {

@@ -148,6 +148,9 @@ struct ShardedAllReduce {
   virtual void sum_partials(const double* partial, int chunks, int64_t n, double* out, cudaStream_t stream);
   virtual ~ShardedAllReduce() {}
 };
+// host part of the Lanczos solver: largest eigenvalue (Sturm bisection) and its unit eigenvector (inverse iteration
+// with a pivoted tridiagonal solve) of the m x m symmetric tridiagonal with diagonal a[0..m) and off-diagonal b[0..m-1)
+void lanczos_tridiag_top(const double* a, const double* b, int m, double* theta, double* s);
 // the fused one-pass Lanczos step holds a column of Z twice in shared memory: n <= kLanczosFusedMaxN
 constexpr int64_t kLanczosFusedMaxN = 512 * 24;
 // Mailboxes of a one-shot all-reduce over peer memory.  Every rank owns 2 (step parity) x W (source rank) x npad

@@ -825,6 +825,13 @@ void launch_peer_sum(const PeerMailbox& mb, const double* partial, int chunks, i
   GBM_CUDA(cudaGetLastError());
 }
 
+void lanczos_tridiag_top(const double* a, const double* b, int m, double* theta, double* s) {
+  std::vector<double> va(a, a + m), vb(m, 0.0), vs;
+  for (int i = 0; i + 1 < m; ++i) vb[i] = b[i];
+  tridiag_top(va, vb, m, theta, &vs);
+  for (int i = 0; i < m; ++i) s[i] = vs[i];
+}
+
 void ShardedAllReduce::sum_partials(const double* partial, int chunks, int64_t n, double* out, cudaStream_t stream) {
   launch_partial_reduce(partial, n, chunks, out, stream);
   sum(out, n);

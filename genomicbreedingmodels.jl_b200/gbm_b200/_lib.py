@@ -82,6 +82,7 @@ SIGNATURES = {
     "gbm_pack_host": (c_int, [_P, c_int64, c_int64, c_int64, _P, c_int64, POINTER(c_int64)]),
     "gbm_pack_host_check": (c_int, [_P, c_int64, c_int64, c_int64, c_int, _P]),
     "gbm_side_vector_digits": (c_int, [_P, c_int64, c_int, c_int64, _P, c_int64, POINTER(c_double)]),
+    "gbm_tridiag_top": (c_int, [_P, _P, c_int64, POINTER(c_double), _P]),
     "gbm_matrix_download": (c_int, [c_void_p, c_int64, c_int64, _P, c_int64]),
     "gbm_matrix_download_cols": (c_int, [c_void_p, _P, c_int64, c_int, _P, c_int64]),
     "gbm_matrix_info": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_void_p)]),

@@ -127,6 +127,10 @@ int gbm_pack_host_check(const double* A, int64_t n, int64_t p, int64_t lda, int 
  * row 0 ones, rows 1..7 / 8..14 the seven balanced base-256 digits of q_1 / q_2 (least significant first), zero padded;
  * scale[m] = 2^(E_m - 55): q_i = scale * sum_k 256^k digit_k(i) up to one ulp of max |q|. */
 int gbm_side_vector_digits(const double* Q, int64_t n, int M, int64_t ldq, int8_t* digits, int64_t ld, double* scale);
+/* testing hook (host only, no GPU needed): the host half of the Lanczos PC1 solver (csrc/lanczos.cu) -- largest
+ * eigenvalue theta (Sturm bisection) and unit eigenvector s (inverse iteration) of the m x m symmetric tridiagonal with
+ * diagonal alpha[0..m) and off-diagonal beta[0..m-1); the solver's stopping test is |beta_m s_m| <= tol theta. */
+int gbm_tridiag_top(const double* alpha, const double* beta, int64_t m, double* theta, double* s);
 int gbm_matrix_download(const gbm_matrix* m, int64_t j0, int64_t ncols, double* dst, int64_t ldd);
 /* G = G[:, idx_cols] and, with standardise != 0, G = (G .- mean(G, dims=1)) ./ std(G, dims=1)'
  * (/root/reference/src/gwas.jl:114, :129) on the device; dst (host or device) is n x ncols.

@@ -546,3 +546,61 @@ def test_ctypes_signatures_match_the_header():
         want_ret, ckinds = protos[name]
         assert kind(res) == want_ret, name
         assert [kind(a) for a in args] == ckinds, f"{name}: ctypes {[kind(a) for a in args]} vs header {ckinds}"
+
+
+# ---- host half of the Lanczos PC1 solver (csrc/lanczos.cu: tridiag_top), no GPU needed ------------------------------
+def _tridiag_top(alpha, beta):
+    import ctypes
+
+    from gbm_b200 import _lib as L
+
+    lib = L.load()
+    m = len(alpha)
+    a = np.ascontiguousarray(alpha, dtype=np.float64)
+    b = np.ascontiguousarray(beta if m > 1 else np.zeros(1), dtype=np.float64)
+    s = np.empty(m)
+    theta = ctypes.c_double()
+    L.check(lib.gbm_tridiag_top(L.ptr(a), L.ptr(b), m, ctypes.byref(theta), L.ptr(s)))
+    return theta.value, s
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 17, 120, 400])
+def test_tridiagonal_top_eigenpair_matches_lapack(m):
+    """Sturm bisection + inverse iteration against numpy's eigh on the dense tridiagonal: random matrices, a Lanczos-like
+    one (a large leading entry coupled weakly to a clustered bulk, as for the standardised GRM) and one with a nearly
+    double top eigenvalue (the vector is then only defined up to the gap; the residual still has to be tiny)."""
+    rng = np.random.default_rng(m)
+    cases = []
+    cases.append((rng.normal(size=m), np.abs(rng.normal(size=max(m - 1, 0)))))
+    a = 1.0 + 0.01 * rng.normal(size=m)
+    a[0] = 300.0
+    b = 0.3 * np.abs(rng.normal(size=max(m - 1, 0))) + 0.05
+    cases.append((a, b))
+    if m >= 3:
+        a2 = np.concatenate([[5.0, 5.0 + 1e-9], rng.uniform(0, 1, size=m - 2)])
+        b2 = np.concatenate([[1e-10], 0.1 * np.abs(rng.normal(size=m - 2))])[: m - 1]
+        cases.append((a2, b2))
+    for a, b in cases:
+        T = np.diag(a) + np.diag(b, 1) + np.diag(b, -1) if m > 1 else np.array([[a[0]]])
+        w, V = np.linalg.eigh(T)
+        theta, s = _tridiag_top(a, b)
+        scale = max(np.abs(w).max(), 1e-300)
+        assert abs(theta - w[-1]) <= 4e-15 * scale
+        assert abs(np.linalg.norm(s) - 1.0) < 1e-12
+        assert np.linalg.norm(T @ s - theta * s) <= 2e-13 * scale     # what the solver's stopping test relies on
+        gap = (w[-1] - w[-2]) / scale if m > 1 else 1.0
+        if gap > 1e-6:  # a separated top eigenvalue: the vector itself
+            v = V[:, -1]
+            assert min(np.abs(s - v).max(), np.abs(s + v).max()) <= 1e-12 / gap
+
+
+def test_tridiagonal_top_argument_errors():
+    from gbm_b200 import _lib as L
+
+    lib = L.load()
+    s = np.empty(2)
+    import ctypes
+
+    theta = ctypes.c_double()
+    assert lib.gbm_tridiag_top(None, None, 2, ctypes.byref(theta), L.ptr(s)) == L.GBM_ERR_ARGUMENT
+    assert lib.gbm_tridiag_top(L.ptr(np.ones(2)), L.ptr(np.ones(1)), 0, ctypes.byref(theta), L.ptr(s)) == L.GBM_ERR_ARGUMENT
