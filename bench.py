@@ -514,12 +514,28 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             best = max(best, 2 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        # ... and SUSTAINED: back to back for ~1.5 s (the figure a long GEMM-bound phase such as the GRM sees)
+        reps = max(4, int(1.5 * best * 1e12 / (2 * 8192 ** 3)))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        sustained = reps * 2 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
         del a, b, dK
         line["grm"] = {"metric": "GRM FP64 TFLOP/s", "value": float(np.median(tfs)), "unit": "TFLOP/s",
                        "flops_convention": "n(n+1)p (SYRK)", "n": gn, "p": gp,
                        "workload": f"grmsimple n={gn} p={gp} diploid (BASELINE configs[1])",
                        "cublas_dgemm_8192_tflops": best, "frac_of_cublas_dgemm": float(np.median(tfs)) / best,
-                       "datasheet_fp64_tflops": 40.0, "frac_of_datasheet": float(np.median(tfs)) / 40.0}
+                       "cublas_dgemm_8192_tflops_sustained": sustained,
+                       "frac_of_cublas_dgemm_sustained": float(np.median(tfs)) / sustained,
+                       "datasheet_fp64_tflops": 40.0, "frac_of_datasheet": float(np.median(tfs)) / 40.0,
+                       "roofline": {"bound": "tensor", "kernel": "grm_dmma_kernel", "achieved": float(np.median(tfs)),
+                                    "peak": sustained, "unit": "TFLOP/s", "frac": float(np.median(tfs)) / sustained,
+                                    "peak_source": "cuBLAS DGEMM 8192^3 back to back for ~1.5 s in this run "
+                                                   "(MEASURED_PEAKS.json has no FP64 figure); burst = cublas_dgemm_8192_tflops",
+                                    "traffic": None}}
         if i8 is not None:
             line["grm_int8"] = i8
 
