@@ -212,3 +212,45 @@ def test_quantify_engine_models_against_the_literal_gwasreml():
     assert np.allclose(th_lit, 0.5)
     # the statistics of all three are strongly correlated (same GLS form, different V)
     assert np.corrcoef(z_lit, z_ref)[0, 1] > 0.9 and np.corrcoef(z_ref, std["z"])[0, 1] > 0.9
+
+
+def test_pca_oracle_against_scikit_learn():
+    """The oracle's PC1 (rows centred, top left singular vector: MultivariateStats' `fit(PCA, K; maxoutdim = 1).proj[:, 1]`
+    with the COLUMNS of K as observations, gwas.jl:234) against an independent implementation of the same definition:
+    scikit-learn's PCA on the transposed matrix (observations in rows there).  Not the Julia package, but a second,
+    unrelated code path for the one PCA convention the reference relies on."""
+    from sklearn.decomposition import PCA
+
+    for seed, n in ((3, 60), (4, 211)):
+        A = synth.block(seed, n, 0, 3 * n, synth.KIND_DIPLOID)
+        Ks = go.standardise_K(go.grm_simple(A))
+        pc = go.pca_pc1(Ks)
+        sk = PCA(n_components=1, svd_solver="full").fit(Ks.T).components_[0]
+        assert abs(np.linalg.norm(pc) - 1) < 1e-12
+        assert min(np.abs(pc - sk).max(), np.abs(pc + sk).max()) < 1e-9
+        # the same vector from the eigendecomposition of Z Z' (the route the CUDA path takes)
+        Z = Ks - Ks.mean(axis=1, keepdims=True)
+        w, V = np.linalg.eigh(Z @ Z.T)
+        assert min(np.abs(pc - V[:, -1]).max(), np.abs(pc + V[:, -1]).max()) < 1e-9
+
+
+def test_ols_statistic_against_scipy_lstsq():
+    """b = pinv(X'X) X'y, stat = b[end] / sqrt(pinv(X'X)[end, end]) (gwas.jl:241-245) against SciPy's least-squares
+    solver and an explicit inverse of the normal matrix, on full-rank markers."""
+    from scipy import linalg
+
+    n, p = 120, 40
+    A = synth.block(9, n, 0, p, synth.KIND_CONTINUOUS)
+    y = synth.phenotype(9, n, p, synth.KIND_CONTINUOUS)
+    ys = (y - y.mean()) / y.std(ddof=1)
+    sd = A.std(axis=0, ddof=1)
+    keep = sd > 1e-12                                  # the fixed-locus filter (gwas.jl:112-113)
+    assert keep.sum() >= 20
+    G = (A[:, keep] - A[:, keep].mean(axis=0)) / sd[keep]
+    pc = go.pca_pc1(go.standardise_K(go.grm_simple(A)))
+    got = go.gwasols_literal(G, ys, pc)
+    for j in range(G.shape[1]):
+        X = np.column_stack([np.ones(n), pc, G[:, j]])
+        b = linalg.lstsq(X, ys, lapack_driver="gelsy")[0]
+        v = linalg.inv(X.T @ X)[2, 2]
+        assert abs(got[j] - b[2] / np.sqrt(v)) <= 1e-9 * max(1.0, abs(got[j]))
